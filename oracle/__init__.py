@@ -1,0 +1,203 @@
+"""ctypes front-end of the CPU oracle (oracle/oracle.c).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, ``__graft_entry__.smoke()`` and
+bench.py's ``cpu_baseline`` / ``--impl reference`` legs.  The product package
+``compute_b200`` never imports this module.
+
+Parity pinning: pinned against the reference's own golden vectors
+(tests/golden/reference_vectors.json); the reference cannot be compiled in this
+image (no Boost, no OpenCL), see oracle/Makefile.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+DTYPES = ["char", "uchar", "short", "ushort", "int", "uint", "long", "ulong", "float", "double"]
+NP_DTYPES = {
+    "char": np.int8, "uchar": np.uint8, "short": np.int16, "ushort": np.uint16,
+    "int": np.int32, "uint": np.uint32, "long": np.int64, "ulong": np.uint64,
+    "float": np.float32, "double": np.float64,
+}
+OPS = ["plus", "multiplies", "min", "max", "bit_and", "bit_or", "bit_xor", "minus", "divides"]
+
+
+def dtype_code(name_or_np) -> int:
+    if isinstance(name_or_np, str):
+        return DTYPES.index(name_or_np)
+    dt = np.dtype(name_or_np)
+    for i, n in enumerate(DTYPES):
+        if np.dtype(NP_DTYPES[n]) == dt:
+            return i
+    raise ValueError(f"unsupported dtype {dt}")
+
+
+def op_code(name: str) -> int:
+    return OPS.index(name)
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE] + (["-B"] if force else []))
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(_LIB_PATH)
+        vp, sz, i32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+        L.orc_radix_key.restype = ctypes.c_uint64
+        L.orc_radix_key.argtypes = [i32, i32, ctypes.c_uint64]
+        L.orc_radix_sort.argtypes = [i32, i32, vp, sz, vp, sz]
+        L.orc_insertion_sort.argtypes = [i32, i32, vp, sz, vp, sz]
+        L.orc_sort.argtypes = [i32, i32, vp, sz]
+        L.orc_sort_by_key.argtypes = [i32, i32, vp, sz, vp, sz]
+        L.orc_stable_sort.argtypes = [i32, i32, vp, sz]
+        L.orc_stable_sort_by_key.argtypes = [i32, i32, vp, sz, vp, sz]
+        L.orc_scan.argtypes = [i32, i32, i32, i32, vp, vp, sz, vp]
+        L.orc_reduce.argtypes = [i32, i32, i32, vp, sz, vp]
+        L.orc_accumulate.argtypes = [i32, i32, i32, i32, vp, sz, vp, vp]
+        L.orc_sum_f64.argtypes = [i32, vp, sz, vp, vp]
+        L.orc_prefix_f64.argtypes = [i32, vp, sz, vp, vp]
+        L.orc_is_sorted.argtypes = [i32, i32, vp, sz]
+        L.orc_merge_sort_on_cpu_u32.argtypes = [vp, sz, i32]
+        L.orc_scan_on_cpu_i32.argtypes = [vp, vp, sz, i32, ctypes.c_int32, i32]
+        L.orc_reduce_on_cpu_i32.argtypes = [vp, sz, vp, i32]
+        _lib = L
+    return _lib
+
+
+def _ptr(a: np.ndarray):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError(f"oracle {what} failed with code {rc}")
+
+
+def radix_key(dtype: str, ascending: bool, bits: int) -> int:
+    return int(lib().orc_radix_key(dtype_code(dtype), int(ascending), ctypes.c_uint64(bits)))
+
+
+def _sort_call(fn_name, keys, descending, values=None, flag_is_ascending=False):
+    keys = np.ascontiguousarray(keys).copy()
+    code = dtype_code(keys.dtype)
+    flag = int(not descending) if flag_is_ascending else int(descending)
+    fn = getattr(lib(), fn_name)
+    if values is None:
+        if fn_name in ("orc_sort", "orc_stable_sort"):
+            _check(fn(code, flag, _ptr(keys), keys.size), fn_name)
+        else:
+            _check(fn(code, flag, _ptr(keys), keys.size, None, 0), fn_name)
+        return keys
+    values = np.ascontiguousarray(values).copy()
+    vb = values.nbytes // max(1, keys.size) if keys.size else values.dtype.itemsize
+    _check(fn(code, flag, _ptr(keys), keys.size, _ptr(values), vb), fn_name)
+    return keys, values
+
+
+def radix_sort(keys, descending=False, values=None):
+    """detail::radix_sort / radix_sort_by_key (radix_sort.hpp:428-462)."""
+    return _sort_call("orc_radix_sort", keys, descending, values, flag_is_ascending=True)
+
+
+def insertion_sort(keys, descending=False, values=None):
+    return _sort_call("orc_insertion_sort", keys, descending, values)
+
+
+def sort(keys, descending=False):
+    return _sort_call("orc_sort", keys, descending)
+
+
+def sort_by_key(keys, values, descending=False):
+    return _sort_call("orc_sort_by_key", keys, descending, values)
+
+
+def stable_sort(keys, descending=False):
+    return _sort_call("orc_stable_sort", keys, descending)
+
+
+def stable_sort_by_key(keys, values, descending=False):
+    return _sort_call("orc_stable_sort_by_key", keys, descending, values)
+
+
+def scan(x, op="plus", exclusive=False, init=None, out_dtype=None):
+    x = np.ascontiguousarray(x)
+    out_np = np.dtype(out_dtype) if out_dtype is not None else x.dtype
+    out = np.empty(x.shape, dtype=out_np)
+    init_arr = np.zeros(1, dtype=out_np) if init is None else np.array([init]).astype(out_np)
+    _check(lib().orc_scan(dtype_code(x.dtype), dtype_code(out_np), op_code(op), int(exclusive),
+                          _ptr(x), _ptr(out), x.size, _ptr(init_arr)), "scan")
+    return out
+
+
+def reduce(x, op="plus", result_dtype=None):
+    x = np.ascontiguousarray(x)
+    res_np = np.dtype(result_dtype) if result_dtype is not None else x.dtype
+    out = np.zeros(1, dtype=res_np)
+    _check(lib().orc_reduce(dtype_code(x.dtype), dtype_code(res_np), op_code(op), _ptr(x), x.size, _ptr(out)), "reduce")
+    return out[0]
+
+
+def accumulate(x, init, op="plus", op_dtype=None, acc_dtype=None):
+    """init's dtype (acc_dtype) is the return type; op_dtype is the functor's type (defaults to x.dtype)."""
+    x = np.ascontiguousarray(x)
+    acc_np = np.dtype(acc_dtype) if acc_dtype is not None else np.asarray(init).dtype
+    op_np = np.dtype(op_dtype) if op_dtype is not None else x.dtype
+    init_arr = np.array([init]).astype(acc_np)
+    out = np.zeros(1, dtype=acc_np)
+    _check(lib().orc_accumulate(dtype_code(x.dtype), dtype_code(op_np), dtype_code(acc_np), op_code(op),
+                                _ptr(x), x.size, _ptr(init_arr), _ptr(out)), "accumulate")
+    return out[0]
+
+
+def sum_f64(x):
+    x = np.ascontiguousarray(x)
+    s = ctypes.c_double()
+    a = ctypes.c_double()
+    _check(lib().orc_sum_f64(dtype_code(x.dtype), _ptr(x), x.size, ctypes.byref(s), ctypes.byref(a)), "sum_f64")
+    return s.value, a.value
+
+
+def prefix_f64(x):
+    x = np.ascontiguousarray(x)
+    p = np.empty(x.size, dtype=np.float64)
+    a = np.empty(x.size, dtype=np.float64)
+    _check(lib().orc_prefix_f64(dtype_code(x.dtype), _ptr(x), x.size, _ptr(p), _ptr(a)), "prefix_f64")
+    return p, a
+
+
+def is_sorted(keys, descending=False) -> bool:
+    keys = np.ascontiguousarray(keys)
+    return bool(lib().orc_is_sorted(dtype_code(keys.dtype), int(descending), _ptr(keys), keys.size))
+
+
+def merge_sort_on_cpu_u32(keys: np.ndarray, threads: int) -> None:
+    """In-place; keys must be a contiguous uint32 array (CPU-device sort path, sort.hpp:117-121)."""
+    assert keys.dtype == np.uint32 and keys.flags.c_contiguous
+    _check(lib().orc_merge_sort_on_cpu_u32(_ptr(keys), keys.size, threads), "merge_sort_on_cpu")
+
+
+def scan_on_cpu_i32(x: np.ndarray, out: np.ndarray, exclusive: bool, init: int, threads: int) -> None:
+    assert x.dtype == np.int32 and out.dtype == np.int32
+    _check(lib().orc_scan_on_cpu_i32(_ptr(x), _ptr(out), x.size, int(exclusive), init, threads), "scan_on_cpu")
+
+
+def reduce_on_cpu_i32(x: np.ndarray, threads: int) -> int:
+    assert x.dtype == np.int32
+    out = np.zeros(1, dtype=np.int32)
+    _check(lib().orc_reduce_on_cpu_i32(_ptr(x), x.size, _ptr(out), threads), "reduce_on_cpu")
+    return int(out[0])
