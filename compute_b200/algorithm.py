@@ -1,0 +1,214 @@
+"""Host-side mirror of the reference's algorithm dispatch for the sort / scan / reduce path.
+
+Each function keeps the name, argument meaning and edge-case behaviour of its Boost.Compute counterpart
+(cited per function; paths relative to include/boost/compute/) and forwards to the C ABI of
+include/compute_b200.h.  Ranges are 1-D contiguous CUDA tensors (``first``..``last`` = the tensor, a slice
+of a tensor is a sub-range); the queue argument plays the role of ``command_queue &queue``.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from ._capi import check, lib
+from .core import NP_OF_CODE, TORCH_OF_CODE, command_queue, default_queue, dtype_code, op_code
+
+
+def _q(queue):
+    return queue if queue is not None else default_queue()
+
+
+def _range(t: torch.Tensor, what="range"):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError(f"{what} must be a CUDA tensor (is_device_iterator static assert in the reference)")
+    if t.dim() != 1 and t.numel() > 0 and what == "range":
+        raise ValueError("ranges are 1-D")
+    if not t.is_contiguous():
+        raise ValueError(f"{what} must be contiguous")
+    return t
+
+
+def _values(values: torch.Tensor, n: int):
+    _range(values, "values")
+    if values.shape[0] != n:
+        raise ValueError("values range is shorter than the key range")
+    vb = values.element_size() * (values.numel() // n if n else 1)
+    return values, vb
+
+
+def _host_scalar(value, code: int):
+    return np.array([value]).astype(NP_OF_CODE[code])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# sort family
+# ---------------------------------------------------------------------------------------------------------
+def radix_sort(keys: torch.Tensor, ascending: bool = True, queue: command_queue | None = None) -> None:
+    """detail::radix_sort(first, last[, ascending], queue) -- algorithm/detail/radix_sort.hpp:428-452."""
+    _range(keys)
+    check(lib().bcb_radix_sort(_q(queue).handle, dtype_code(keys.dtype), int(ascending), keys.data_ptr(),
+                               keys.numel(), None, 0))
+
+
+def radix_sort_by_key(keys: torch.Tensor, values: torch.Tensor, ascending: bool = True,
+                      queue: command_queue | None = None) -> None:
+    """detail::radix_sort_by_key -- algorithm/detail/radix_sort.hpp:436-461 (stable, any payload size)."""
+    _range(keys)
+    n = keys.numel()
+    values, vb = _values(values, n)
+    check(lib().bcb_radix_sort(_q(queue).handle, dtype_code(keys.dtype), int(ascending), keys.data_ptr(), n,
+                               values.data_ptr(), vb))
+
+
+def insertion_sort(keys: torch.Tensor, values: torch.Tensor | None = None, descending: bool = False,
+                   queue: command_queue | None = None) -> None:
+    """detail::serial_insertion_sort(_by_key) -- algorithm/detail/insertion_sort.hpp:25-159."""
+    _range(keys)
+    n = keys.numel()
+    vptr, vb = None, 0
+    if values is not None:
+        values, vb = _values(values, n)
+        vptr = values.data_ptr()
+    check(lib().bcb_insertion_sort(_q(queue).handle, dtype_code(keys.dtype), int(descending), keys.data_ptr(), n, vptr, vb))
+
+
+def sort(keys: torch.Tensor, descending: bool = False, queue: command_queue | None = None) -> None:
+    """sort(first, last, less<T>() | greater<T>(), queue) -- algorithm/sort.hpp:182-202 via dispatch_gpu_sort
+    :34-81: n < 2 nothing, n <= 32 insertion sort, else radix sort."""
+    _range(keys)
+    n = keys.numel()
+    if n < 2:
+        return
+    if n <= 32:
+        insertion_sort(keys, None, descending, queue)
+    else:
+        radix_sort(keys, not descending, queue)
+
+
+def sort_host(host_keys: np.ndarray, descending: bool = False, queue: command_queue | None = None) -> None:
+    """sort(host_first, host_last, queue) -- algorithm/sort.hpp:125-148 (maps the host range, sorts, copies back)."""
+    if not isinstance(host_keys, np.ndarray) or not host_keys.flags.c_contiguous:
+        raise TypeError("sort_host needs a contiguous numpy array")
+    check(lib().bcb_sort_host(_q(queue).handle, dtype_code(host_keys.dtype), int(descending),
+                              host_keys.ctypes.data, host_keys.size))
+
+
+def sort_by_key(keys: torch.Tensor, values: torch.Tensor, descending: bool = False,
+                queue: command_queue | None = None) -> None:
+    """sort_by_key -- algorithm/sort_by_key.hpp:135-163 via dispatch_gpu_sort_by_key :33-86:
+    n < 32 insertion sort by key, else radix_sort_by_key."""
+    _range(keys)
+    n = keys.numel()
+    if n < 32:
+        insertion_sort(keys, values, descending, queue)
+    else:
+        radix_sort_by_key(keys, values, not descending, queue)
+
+
+def stable_sort(keys: torch.Tensor, descending: bool = False, queue: command_queue | None = None) -> None:
+    """stable_sort with less / greater -- algorithm/stable_sort.hpp:52-71: straight to radix sort."""
+    radix_sort(keys, not descending, queue)
+
+
+def stable_sort_by_key(keys: torch.Tensor, values: torch.Tensor, descending: bool = False,
+                       queue: command_queue | None = None) -> None:
+    """stable_sort_by_key with less / greater -- algorithm/stable_sort_by_key.hpp:29-80: radix_sort_by_key."""
+    radix_sort_by_key(keys, values, not descending, queue)
+
+
+def is_sorted(keys: torch.Tensor, descending: bool = False, queue: command_queue | None = None) -> bool:
+    """is_sorted(first, last[, greater<T>()], queue) -- algorithm/is_sorted.hpp:39-68."""
+    _range(keys)
+    res = ctypes.c_int(1)
+    check(lib().bcb_is_sorted(_q(queue).handle, dtype_code(keys.dtype), int(descending), keys.data_ptr(), keys.numel(),
+                              ctypes.byref(res)))
+    return bool(res.value)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# scan family
+# ---------------------------------------------------------------------------------------------------------
+def _scan(first: torch.Tensor, result: torch.Tensor, exclusive: bool, init, op, queue):
+    _range(first)
+    _range(result)
+    n = first.numel()
+    if result.numel() < n:
+        raise ValueError("result range is shorter than the input range")
+    out_code = dtype_code(result.dtype)
+    init_arr = _host_scalar(init, out_code)
+    check(lib().bcb_scan(_q(queue).handle, dtype_code(first.dtype), out_code, op_code(op), int(exclusive),
+                         first.data_ptr(), result.data_ptr(), n, init_arr.ctypes.data))
+    return result[n:] if result.numel() > n else result[n:n]  # "result + n" (scan_on_gpu.hpp:266)
+
+
+def exclusive_scan(first: torch.Tensor, result: torch.Tensor, init=0, op="plus", queue: command_queue | None = None):
+    """exclusive_scan(first, last, result[, init[, binary_op]], queue) -- algorithm/exclusive_scan.hpp:55-104.
+    out[i] = init op x0 op ... op x(i-1), arithmetic in result's value type; first may alias result."""
+    return _scan(first, result, True, init, op, queue)
+
+
+def inclusive_scan(first: torch.Tensor, result: torch.Tensor, op="plus", queue: command_queue | None = None):
+    """inclusive_scan(first, last, result[, binary_op], queue) -- algorithm/inclusive_scan.hpp:53-87."""
+    return _scan(first, result, False, 0, op, queue)
+
+
+def partial_sum(first: torch.Tensor, result: torch.Tensor, queue: command_queue | None = None):
+    """partial_sum == inclusive_scan with plus -- algorithm/partial_sum.hpp:31-41."""
+    return inclusive_scan(first, result, "plus", queue)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reduce / accumulate
+# ---------------------------------------------------------------------------------------------------------
+def reduce(first: torch.Tensor, result=None, op="plus", result_dtype=None, queue: command_queue | None = None):
+    """reduce(first, last, result[, function], queue) -- algorithm/reduce.hpp:275-305.
+
+    ``result`` may be a CUDA tensor (device iterator: the value is written to result[0], enqueue-and-return)
+    or None / a 1-element numpy array (host pointer: blocks and returns the value).  ``result_dtype`` is the
+    functor's type U for ``plus<U>`` over a T range (defaults to the input type).  An empty range leaves the
+    result untouched (reduce.hpp:283-285) and returns None for the host form.
+    """
+    _range(first)
+    n = first.numel()
+    in_code = dtype_code(first.dtype)
+    if isinstance(result, torch.Tensor):
+        _range(result, "result")
+        check(lib().bcb_reduce(_q(queue).handle, in_code, dtype_code(result.dtype), op_code(op), first.data_ptr(), n,
+                               result.data_ptr(), 1))
+        return None
+    res_code = dtype_code(result_dtype) if result_dtype is not None else (
+        dtype_code(result.dtype) if isinstance(result, np.ndarray) else in_code)
+    host = result if isinstance(result, np.ndarray) else np.zeros(1, dtype=NP_OF_CODE[res_code])
+    check(lib().bcb_reduce(_q(queue).handle, in_code, res_code, op_code(op), first.data_ptr(), n, host.ctypes.data, 0))
+    if n == 0 and not isinstance(result, np.ndarray):
+        return None
+    return host[0]
+
+
+def accumulate(first: torch.Tensor, init, op="plus", op_dtype=None, acc_dtype=None, queue: command_queue | None = None):
+    """accumulate(first, last, init[, function], queue) -- algorithm/accumulate.hpp:165-188.
+
+    Returns ``init op x0 op x1 ...`` as a host value of init's type T (``acc_dtype``; default: init's numpy
+    dtype, or the input type for plain Python numbers).  ``op_dtype`` is the functor's type (default: the input
+    value type, accumulate.hpp:185-187)."""
+    _range(first)
+    in_code = dtype_code(first.dtype)
+    if acc_dtype is None:
+        acc_code = dtype_code(init.dtype) if isinstance(init, np.generic) else in_code
+    else:
+        acc_code = dtype_code(acc_dtype)
+    opd_code = dtype_code(op_dtype) if op_dtype is not None else in_code
+    init_arr = _host_scalar(init, acc_code)
+    out = np.zeros(1, dtype=NP_OF_CODE[acc_code])
+    check(lib().bcb_accumulate(_q(queue).handle, in_code, opd_code, acc_code, op_code(op), first.data_ptr(),
+                               first.numel(), init_arr.ctypes.data, out.ctypes.data))
+    return out[0]
+
+
+__all__ = [
+    "radix_sort", "radix_sort_by_key", "insertion_sort", "sort", "sort_host", "sort_by_key", "stable_sort",
+    "stable_sort_by_key", "is_sorted", "exclusive_scan", "inclusive_scan", "partial_sum", "reduce", "accumulate",
+]
+_ = TORCH_OF_CODE

@@ -1,0 +1,134 @@
+// common.cuh -- shared helpers for the sm_100a kernels behind include/compute_b200.h
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/compute_b200.h"
+
+namespace bcb {
+
+#define BCB_CUDA_TRY(expr)                                   \
+    do {                                                     \
+        cudaError_t _e = (expr);                             \
+        if (_e != cudaSuccess) { (void)cudaGetLastError(); return (int)_e; } \
+    } while (0)
+
+#define BCB_TRY(expr)                      \
+    do {                                   \
+        int _s = (expr);                   \
+        if (_s != BCB_SUCCESS) return _s;  \
+    } while (0)
+
+inline size_t dtype_size(int dtype)
+{
+    switch (dtype) {
+    case BCB_CHAR: case BCB_UCHAR: return 1;
+    case BCB_SHORT: case BCB_USHORT: return 2;
+    case BCB_INT: case BCB_UINT: case BCB_FLOAT: return 4;
+    case BCB_LONG: case BCB_ULONG: case BCB_DOUBLE: return 8;
+    default: return 0;
+    }
+}
+inline bool dtype_is_float(int d) { return d == BCB_FLOAT || d == BCB_DOUBLE; }
+inline bool dtype_is_signed_int(int d) { return d == BCB_CHAR || d == BCB_SHORT || d == BCB_INT || d == BCB_LONG; }
+
+// ---- per-stream scratch (runtime.cu) -------------------------------------------------------
+// Grow-only, stream-ordered (cudaMallocAsync / cudaFreeAsync on the owning stream), so a
+// launcher never frees memory a still-running kernel of an earlier call may touch.
+struct StreamState {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    // bulk scratch (temporary key/value buffers, partials ...)
+    void *scratch = nullptr;
+    size_t scratch_bytes = 0;
+    // small persistent control block, zeroed once at creation:
+    //   [0]   u64 ticket counter (monotonic across calls; launchers pass the base)
+    //   [1..] reserved
+    unsigned long long *control = nullptr;
+    unsigned long long ticket_base = 0;
+    // decoupled look-back descriptors (scan + sort); zeroed at (re)allocation, validated by epoch tags
+    void *lookback = nullptr;
+    size_t lookback_bytes = 0;
+    uint32_t epoch = 0;  // 30-bit generation tag, bumped once per launch that uses `lookback`
+    // radix digit histograms / bases
+    uint32_t *hist = nullptr;  // [8 passes][256]
+    // pinned, device-mapped result slot for host-returning calls
+    void *pinned_slot = nullptr;      // host address
+    void *pinned_slot_dev = nullptr;  // device alias
+    int sm_count = 0;
+    // optional per-kernel timing (bcb_timing_*): CUDA event pairs recorded around each launch
+    bool timing = false;
+    struct TimedLaunch { int kind; cudaEvent_t start, stop; };
+    TimedLaunch *timed = nullptr;
+    int timed_count = 0, timed_capacity = 0;
+};
+
+// RAII helper used by the launchers: records an event pair around a kernel launch when timing is on
+struct LaunchTimer {
+    StreamState *st;
+    int slot = -1;
+    LaunchTimer(StreamState *s, int kind);
+    ~LaunchTimer();
+};
+
+int stream_state(cudaStream_t stream, StreamState **out);
+int scratch_reserve(StreamState *st, size_t bytes, void **out);
+int lookback_reserve(StreamState *st, size_t bytes, void **out);
+// next epoch tag in [1, 2^30): wraps by zeroing the look-back array
+int next_epoch(StreamState *st, uint32_t *epoch);
+
+constexpr int kControlTicket = 0;
+
+// ---- device helpers ------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned lanemask_lt()
+{
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// single-copy-atomic 64-bit accesses that bypass the (incoherent) L1
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// streaming 128-bit load: read-once data, do not pollute L1
+__device__ __forceinline__ uint4 ld_stream_v4(const void *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream_v4(void *p, uint4 v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
+#endif  // __CUDACC__
+
+}  // namespace bcb

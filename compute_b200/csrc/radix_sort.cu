@@ -1,0 +1,616 @@
+// radix_sort.cu -- stable LSD radix sort (keys and key-value pairs) for sm_100a: onesweep, 8-bit digits.
+//
+// Replaces radix_sort_impl of the reference (algorithm/detail/radix_sort.hpp:252-426): 4-bit digits, per pass a
+// count kernel, a recursive exclusive_scan over per-block counters, a 16-entry scan task and a scatter kernel
+// whose in-block rank is an O(block) serial loop -- about 100 B/key of DRAM traffic and 48+ launches for 32-bit
+// keys.  Here a 32-bit sort is 6 launches and 36 B/key (K + P*2*(K+V), P = key bytes):
+//   1. radix_histogram: ONE read of the keys builds the 256-bin histogram of every digit position
+//      (128-bit loads, shared-memory atomics, one flush per CTA);
+//   2. digit_scan: exclusive scan of each 256-bin histogram -> global base of every digit value;
+//   3. onesweep_pass, once per digit: each CTA takes a tile id from an atomic ticket, loads its keys
+//      warp-striped, ranks them with warp-level multi-split (__match_any_sync) against per-warp shared-memory
+//      histograms, publishes the tile's 256 digit counts, obtains the counts of all earlier tiles by decoupled
+//      look-back (one thread per digit value), reorders the tile through shared memory and writes each digit's
+//      run to its final position.  The scatter is stable (ranks follow the original order), so the result is
+//      identical to the reference's stable 4-bit LSD sort by the same transformed key.
+// Keys stay in their original bit pattern in memory; the reference's order-preserving transform
+// (radix_sort.hpp:100-127, asc and desc, incl. its descending quirks) is applied in registers when a digit is
+// extracted, because the descending float transform is not invertible (-0.0 and +denorm_min collide).
+// Look-back words are 64-bit {epoch<<2|status, count} so no per-pass initialisation is needed and counts up to
+// 2^32-1 fit.
+#include "ops.cuh"
+
+#include <cstdlib>
+#include <cstring>
+
+namespace bcb {
+
+constexpr int kRadixBits = 8;
+constexpr int kRadixSize = 1 << kRadixBits;
+constexpr int kHistThreads = 512;
+
+enum : unsigned { kLbInvalid = 0u, kLbPartial = 1u, kLbInclusive = 2u };
+
+// order-preserving transform parameters (uniform): key' = ((x ^ nm) - nm) ^ xc ^ (asr(x) & fa)
+struct Transform {
+    unsigned long long nm;  // all-ones: negate x first (descending signed / float)
+    unsigned long long xc;  // xor constant: sign bit (signed, float) or all-ones (descending unsigned)
+    unsigned long long fa;  // float only: bits below the sign, selected when x is negative
+};
+
+static Transform make_transform(int dtype, bool ascending)
+{
+    const unsigned w = (unsigned)dtype_size(dtype) * 8;
+    const unsigned long long ones = (w == 64) ? ~0ull : ((1ull << w) - 1);
+    const unsigned long long sign = 1ull << (w - 1);
+    Transform t{0, 0, 0};
+    const bool sgn = dtype_is_signed_int(dtype), flt = dtype_is_float(dtype);
+    if (sgn || flt) {
+        t.xc = sign;
+        if (!ascending) t.nm = ~0ull;
+        if (flt) t.fa = ones & ~sign;
+    } else if (!ascending) {
+        t.xc = ones;
+    }
+    return t;
+}
+
+template <typename K> struct key_traits;
+template <> struct key_traits<unsigned char> { typedef unsigned U; typedef int S; };
+template <> struct key_traits<unsigned short> { typedef unsigned U; typedef int S; };
+template <> struct key_traits<unsigned> { typedef unsigned U; typedef int S; };
+template <> struct key_traits<unsigned long long> { typedef unsigned long long U; typedef long long S; };
+
+template <typename K>
+__device__ __forceinline__ unsigned digit_of(K raw, int shift, const Transform &tf)
+{
+    typedef typename key_traits<K>::U U;
+    typedef typename key_traits<K>::S S;
+    const U x = (U)raw;
+    const U nm = (U)tf.nm;
+    // asr over the compute width: only meaningful (fa != 0) for float / double keys, whose width IS the compute width
+    const U neg = (U)((S)x >> (sizeof(U) * 8 - 1));
+    const U t = ((x ^ nm) - nm) ^ (U)tf.xc ^ (neg & (U)tf.fa);
+    return (unsigned)(t >> shift) & (kRadixSize - 1);
+}
+
+// ---- 1. histogram of all digit positions in one read ------------------------------------------
+template <typename K>
+__global__ void __launch_bounds__(kHistThreads)
+radix_histogram(const K *__restrict__ keys, size_t n, unsigned *__restrict__ hist, Transform tf)
+{
+    constexpr int NPASS = sizeof(K);
+    constexpr int VEC = 16 / sizeof(K);
+    __shared__ unsigned sh[NPASS][kRadixSize];
+    for (int i = threadIdx.x; i < NPASS * kRadixSize; i += kHistThreads) (&sh[0][0])[i] = 0;
+    __syncthreads();
+
+    const size_t gthreads = (size_t)gridDim.x * blockDim.x;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t head = ((16 - ((uintptr_t)keys & 15)) & 15) / sizeof(K);
+    if (head > n) head = n;
+    const size_t nvec = (n - head) / VEC;
+    const size_t tail_start = head + nvec * VEC;
+    const uint4 *vin = reinterpret_cast<const uint4 *>(keys + head);
+
+    auto count_key = [&](K k) {
+#pragma unroll
+        for (int p = 0; p < NPASS; p++) atomicAdd(&sh[p][digit_of<K>(k, p * kRadixBits, tf)], 1u);
+    };
+    size_t v = gid;
+    for (; v + gthreads < nvec; v += 2 * gthreads) {  // two independent 128-bit loads in flight
+        const uint4 a = ld_stream_v4(vin + v);
+        const uint4 b = ld_stream_v4(vin + v + gthreads);
+        const K *ea = reinterpret_cast<const K *>(&a);
+        const K *eb = reinterpret_cast<const K *>(&b);
+#pragma unroll
+        for (int k = 0; k < VEC; k++) count_key(ea[k]);
+#pragma unroll
+        for (int k = 0; k < VEC; k++) count_key(eb[k]);
+    }
+    for (; v < nvec; v += gthreads) {
+        const uint4 a = ld_stream_v4(vin + v);
+        const K *ea = reinterpret_cast<const K *>(&a);
+#pragma unroll
+        for (int k = 0; k < VEC; k++) count_key(ea[k]);
+    }
+    if (gid < head) count_key(keys[gid]);
+    if (tail_start + gid < n) count_key(keys[tail_start + gid]);
+
+    __syncthreads();
+    for (int i = threadIdx.x; i < NPASS * kRadixSize; i += kHistThreads) {
+        const unsigned c = (&sh[0][0])[i];
+        if (c) atomicAdd(hist + i, c);
+    }
+}
+
+// ---- 2. exclusive scan of each digit histogram: hist[p][d] -> base[p][d] -------------------------
+__global__ void __launch_bounds__(kRadixSize) digit_scan(const unsigned *__restrict__ hist, unsigned *__restrict__ base)
+{
+    __shared__ unsigned wsum[kRadixSize / 32];
+    const unsigned d = threadIdx.x, lane = d & 31u, warp = d >> 5;
+    const unsigned c = hist[blockIdx.x * kRadixSize + d];
+    unsigned s = c;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned o = __shfl_up_sync(0xffffffffu, s, off);
+        if ((int)lane >= off) s += o;
+    }
+    if (lane == 31) wsum[warp] = s;
+    __syncthreads();
+    unsigned add = 0;
+    for (unsigned w = 0; w < warp; w++) add += wsum[w];
+    base[blockIdx.x * kRadixSize + d] = s - c + add;
+}
+
+// ---- 3. one onesweep pass ---------------------------------------------------------------------------
+template <int VB> struct value_type;
+template <> struct value_type<0> { typedef unsigned char type; };
+template <> struct value_type<1> { typedef unsigned char type; };
+template <> struct value_type<2> { typedef unsigned short type; };
+template <> struct value_type<4> { typedef unsigned type; };
+template <> struct value_type<8> { typedef unsigned long long type; };
+template <> struct value_type<16> { typedef uint4 type; };
+
+template <typename K, int VB, int THREADS, int ITEMS>
+struct PassSmem {
+    static constexpr int WARPS = THREADS / 32;
+    static constexpr int TILE = THREADS * ITEMS;
+    static constexpr size_t kElem = (sizeof(K) > (size_t)VB) ? sizeof(K) : (size_t)VB;
+    static constexpr size_t kWarpHist = (size_t)WARPS * kRadixSize * sizeof(unsigned);
+    static constexpr size_t kSmall = 2 * kRadixSize * sizeof(unsigned) + 64;  // digit_start, out_base, misc
+    static constexpr size_t kBytes = kWarpHist + kSmall + (size_t)TILE * kElem + 16;
+};
+
+template <typename K, int VB, int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS)
+onesweep_pass(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *__restrict__ vals_in_v,
+              void *__restrict__ vals_out_v, const unsigned *__restrict__ digit_base, unsigned long long *lookback,
+              unsigned epoch, unsigned long long *ticket, unsigned long long ticket_base, size_t n, int shift, Transform tf)
+{
+    typedef PassSmem<K, VB, THREADS, ITEMS> L;
+    typedef typename value_type<VB>::type V;
+    constexpr int WARPS = L::WARPS, TILE = L::TILE;
+    static_assert(THREADS >= kRadixSize && THREADS % 32 == 0, "one look-back thread per digit value");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned(*warp_hist)[kRadixSize] = reinterpret_cast<unsigned(*)[kRadixSize]>(smem_raw);
+    unsigned *digit_start = reinterpret_cast<unsigned *>(smem_raw + L::kWarpHist);
+    unsigned *out_base = digit_start + kRadixSize;
+    unsigned *misc = out_base + kRadixSize;  // [0..1] tile id (u64), [2..9] warp sums of the digit scan
+    unsigned char *elem_buf = smem_raw + L::kWarpHist + L::kSmall;
+    K *keys_sorted = reinterpret_cast<K *>(elem_buf);
+
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+
+    if (tid == 0) *reinterpret_cast<unsigned long long *>(misc) = atomicAdd(ticket, 1ull) - ticket_base;
+    // zero this warp's histogram row while the ticket is in flight
+#pragma unroll
+    for (int j = lane; j < kRadixSize; j += 32) warp_hist[warp][j] = 0;
+    __syncthreads();
+    const size_t tile = (size_t)*reinterpret_cast<unsigned long long *>(misc);
+    const size_t tile_base = tile * (size_t)TILE;
+    const bool full = tile_base + TILE <= n;
+    const unsigned valid = full ? (unsigned)TILE : (unsigned)(n - tile_base);
+    const unsigned warp_off = warp * (ITEMS * 32) + lane;  // in-tile index of this thread's item 0
+
+    // ---- load keys, warp-striped: item i of lane l = tile_base + warp*ITEMS*32 + i*32 + l ----
+    K key[ITEMS];
+    if (full) {
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) key[i] = keys_in[tile_base + warp_off + i * 32];
+    } else {
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            const unsigned t = warp_off + i * 32;
+            key[i] = t < valid ? keys_in[tile_base + t] : (K)0;
+        }
+    }
+
+    // ---- rank: warp-level multi-split against this warp's histogram row (stable: item-major, lane-minor) ----
+    unsigned short rank[ITEMS];
+    const unsigned lt_mask = lanemask_lt();
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) {
+        unsigned d = digit_of<K>(key[i], shift, tf);
+        if (!full && warp_off + i * 32 >= valid) d = kRadixSize - 1;  // padding sorts last within the tile
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        unsigned before = 0;
+        if ((int)lane == leader) {
+            before = warp_hist[warp][d];
+            warp_hist[warp][d] = before + __popc(peers);
+        }
+        __syncwarp();
+        before = __shfl_sync(0xffffffffu, before, leader);
+        rank[i] = (unsigned short)(before + __popc(peers & lt_mask));
+    }
+    __syncthreads();
+
+    // ---- per digit: exclusive prefix over warps (in place), tile count, then scan over the 256 digits ----
+    unsigned count = 0;
+    if (tid < kRadixSize) {
+        unsigned run = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; w++) {
+            const unsigned c = warp_hist[w][tid];
+            warp_hist[w][tid] = run;
+            run += c;
+        }
+        count = run;
+    }
+    unsigned incl = count;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned o = __shfl_up_sync(0xffffffffu, incl, off);
+        if ((int)lane >= off) incl += o;
+    }
+    if (tid < kRadixSize && lane == 31) misc[2 + warp] = incl;
+    __syncthreads();
+    unsigned my_start = 0;
+    if (tid < kRadixSize) {
+        unsigned add = 0;
+        for (unsigned w = 0; w < warp; w++) add += misc[2 + w];
+        my_start = incl - count + add;
+        digit_start[tid] = my_start;
+        if (!full && tid == kRadixSize - 1) count -= (unsigned)TILE - valid;  // drop the padding from the published count
+        // publish this tile's count for digit `tid`
+        const unsigned status = (tile == 0) ? kLbInclusive : kLbPartial;
+        st_relaxed_u64(lookback + tile * kRadixSize + tid, ((unsigned long long)((epoch << 2) | status) << 32) | count);
+    }
+    __syncthreads();
+
+    // ---- decoupled look-back (threads 0..255, one digit each); the other warps start reordering meanwhile ----
+    if (tid < kRadixSize) {
+        unsigned excl = 0;
+        if (tile > 0) {
+            size_t j = tile - 1;
+            while (true) {
+                const unsigned long long w = ld_relaxed_u64(lookback + j * kRadixSize + tid);
+                const unsigned tag = (unsigned)(w >> 32);
+                if ((tag >> 2) != epoch) continue;  // not published yet
+                excl += (unsigned)w;
+                if ((tag & 3u) == kLbInclusive) break;
+                --j;
+            }
+            st_relaxed_u64(lookback + tile * kRadixSize + tid,
+                           ((unsigned long long)((epoch << 2) | kLbInclusive) << 32) | (unsigned)(excl + count));
+        }
+        out_base[tid] = digit_base[tid] + excl - my_start;  // global index = out_base[d] + position in the sorted tile
+    }
+
+    // ---- reorder the tile through shared memory ----
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) {
+        unsigned d = digit_of<K>(key[i], shift, tf);
+        if (!full && warp_off + i * 32 >= valid) d = kRadixSize - 1;
+        const unsigned pos = digit_start[d] + warp_hist[warp][d] + rank[i];
+        rank[i] = (unsigned short)pos;
+        keys_sorted[pos] = key[i];
+    }
+    __syncthreads();
+
+    // ---- write keys: consecutive threads -> consecutive addresses inside each digit run ----
+    unsigned char dig[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) {
+        const unsigned p = i * THREADS + tid;
+        if (p < valid) {
+            const K k = keys_sorted[p];
+            const unsigned d = digit_of<K>(k, shift, tf);
+            dig[i] = (unsigned char)d;
+            keys_out[(size_t)(out_base[d] + p)] = k;
+        }
+    }
+
+    if constexpr (VB > 0) {
+        const V *vals_in = reinterpret_cast<const V *>(vals_in_v);
+        V *vals_out = reinterpret_cast<V *>(vals_out_v);
+        V *vals_sorted = reinterpret_cast<V *>(elem_buf);
+        V val[ITEMS];
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            const unsigned t = warp_off + i * 32;
+            if (t < valid) val[i] = vals_in[tile_base + t];
+        }
+        __syncthreads();  // everyone is done reading keys_sorted
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            const unsigned t = warp_off + i * 32;
+            if (t < valid) vals_sorted[rank[i]] = val[i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            const unsigned p = i * THREADS + tid;
+            if (p < valid) vals_out[(size_t)(out_base[dig[i]] + p)] = vals_sorted[p];
+        }
+    }
+}
+
+// ---- helpers for payloads whose size is not 1/2/4/8/16 bytes: sort (key, index), then gather ----
+__global__ void iota_u32_kernel(unsigned *p, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = (unsigned)i;
+}
+__global__ void gather_bytes_kernel(const unsigned char *src, const unsigned *idx, unsigned char *dst, size_t n, size_t w)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n * w; i += stride) {
+        const size_t e = i / w, b = i - e * w;
+        dst[i] = src[(size_t)idx[e] * w + b];
+    }
+}
+
+// serial_insertion_sort(_by_key): algorithm/detail/insertion_sort.hpp:25-159 -- one thread, native compare
+template <typename T>
+__global__ void insertion_sort_kernel(T *keys, size_t n, int greater, unsigned char *vals, size_t vb)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    for (size_t i = 1; i < n; i++) {
+        const T key = keys[i];
+        unsigned char tmp[256];
+        if (vals) for (size_t b = 0; b < vb; b++) tmp[b] = vals[i * vb + b];
+        size_t pos = i;
+        while (pos > 0 && (greater ? (key > keys[pos - 1]) : (key < keys[pos - 1]))) {
+            keys[pos] = keys[pos - 1];
+            if (vals) for (size_t b = 0; b < vb; b++) vals[pos * vb + b] = vals[(pos - 1) * vb + b];
+            pos--;
+        }
+        keys[pos] = key;
+        if (vals) for (size_t b = 0; b < vb; b++) vals[pos * vb + b] = tmp[b];
+    }
+}
+
+// ---- launch plumbing -----------------------------------------------------------------------------------
+template <typename K, int VB, int THREADS, int ITEMS>
+static int launch_pass(StreamState *st, const void *kin, void *kout, const void *vin, void *vout, const unsigned *base,
+                       unsigned long long *lookback, size_t n, int shift, const Transform &tf)
+{
+    typedef PassSmem<K, VB, THREADS, ITEMS> L;
+    static bool configured[64] = {};  // per instantiation and device: opt in to > 48 KB dynamic shared memory once
+    auto kernel = onesweep_pass<K, VB, THREADS, ITEMS>;
+    if (st->device >= 64 || !configured[st->device]) {
+        BCB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kBytes));
+        if (st->device < 64) configured[st->device] = true;
+    }
+    const size_t tiles = (n + L::TILE - 1) / L::TILE;
+    unsigned epoch;
+    BCB_TRY(next_epoch(st, &epoch));
+    const unsigned long long tbase = st->ticket_base;
+    st->ticket_base += tiles;
+    LaunchTimer timer(st, BCB_K_ONESWEEP_PASS);
+    kernel<<<(unsigned)tiles, THREADS, L::kBytes, st->stream>>>((const K *)kin, (K *)kout, vin, vout, base, lookback, epoch,
+                                                                st->control + kControlTicket, tbase, n, shift, tf);
+    BCB_CUDA_TRY(cudaGetLastError());
+    return BCB_SUCCESS;
+}
+
+// tile shapes: (key bytes, value bytes) -> THREADS x ITEMS
+template <typename K, int VB> struct PassConfig { static constexpr int THREADS = 384, ITEMS = 16; };
+template <> struct PassConfig<unsigned, 0> { static constexpr int THREADS = 384, ITEMS = 20; };
+template <> struct PassConfig<unsigned short, 0> { static constexpr int THREADS = 384, ITEMS = 20; };
+template <> struct PassConfig<unsigned char, 0> { static constexpr int THREADS = 384, ITEMS = 20; };
+template <> struct PassConfig<unsigned long long, 0> { static constexpr int THREADS = 384, ITEMS = 12; };
+template <typename K> struct PassConfig<K, 8> { static constexpr int THREADS = 384, ITEMS = 12; };
+template <typename K> struct PassConfig<K, 16> { static constexpr int THREADS = 384, ITEMS = 8; };
+template <> struct PassConfig<unsigned long long, 4> { static constexpr int THREADS = 384, ITEMS = 12; };
+
+static int g_sort_variant = -1;  // BCB_SORT_VARIANT: tuning variants of the u32 keys-only pass
+static int sort_variant()
+{
+    if (g_sort_variant < 0) {
+        const char *e = std::getenv("BCB_SORT_VARIANT");
+        g_sort_variant = e ? std::atoi(e) : 0;
+    }
+    return g_sort_variant;
+}
+
+template <typename K, int VB>
+static int tile_size_for()
+{
+    if constexpr (sizeof(K) == 4 && VB == 0) {
+        switch (sort_variant()) {
+        case 1: return 512 * 16;
+        case 2: return 256 * 24;
+        case 3: return 512 * 12;
+        case 4: return 384 * 16;
+        default: break;
+        }
+    }
+    return PassConfig<K, VB>::THREADS * PassConfig<K, VB>::ITEMS;
+}
+
+template <typename K, int VB>
+static int run_pass(StreamState *st, const void *kin, void *kout, const void *vin, void *vout, const unsigned *base,
+                    unsigned long long *lookback, size_t n, int shift, const Transform &tf)
+{
+    if constexpr (sizeof(K) == 4 && VB == 0) {
+        switch (sort_variant()) {
+        case 1: return launch_pass<K, VB, 512, 16>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
+        case 2: return launch_pass<K, VB, 256, 24>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
+        case 3: return launch_pass<K, VB, 512, 12>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
+        case 4: return launch_pass<K, VB, 384, 16>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
+        default: break;
+        }
+    }
+    return launch_pass<K, VB, PassConfig<K, VB>::THREADS, PassConfig<K, VB>::ITEMS>(st, kin, kout, vin, vout, base, lookback, n,
+                                                                                     shift, tf);
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+template <typename K, int VB>
+static int sort_typed(StreamState *st, void *keys, void *values, size_t n, const Transform &tf)
+{
+    constexpr int NPASS = sizeof(K);
+    const size_t kbytes = align_up(n * sizeof(K), 256);
+    const size_t vbytes = align_up(n * (size_t)VB, 256);
+    void *scratch;
+    BCB_TRY(scratch_reserve(st, kbytes + vbytes, &scratch));
+    void *tmp_keys = scratch;
+    void *tmp_vals = VB ? (void *)((char *)scratch + kbytes) : nullptr;
+
+    const size_t tile = (size_t)tile_size_for<K, VB>();
+    const size_t tiles = (n + tile - 1) / tile;
+    void *lb;
+    BCB_TRY(lookback_reserve(st, tiles * kRadixSize * sizeof(unsigned long long), &lb));
+
+    unsigned *hist = st->hist;
+    unsigned *base = st->hist + 8 * kRadixSize;
+    BCB_CUDA_TRY(cudaMemsetAsync(hist, 0, NPASS * kRadixSize * sizeof(unsigned), st->stream));
+    {
+        size_t blocks = (n * sizeof(K) + (size_t)kHistThreads * 32 - 1) / ((size_t)kHistThreads * 32);
+        const size_t cap = (size_t)st->sm_count * (2048 / kHistThreads);
+        if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
+        {
+            LaunchTimer timer(st, BCB_K_RADIX_HISTOGRAM);
+            radix_histogram<K><<<(unsigned)blocks, kHistThreads, 0, st->stream>>>((const K *)keys, n, hist, tf);
+        }
+        BCB_CUDA_TRY(cudaGetLastError());
+        {
+            LaunchTimer timer(st, BCB_K_DIGIT_SCAN);
+            digit_scan<<<NPASS, kRadixSize, 0, st->stream>>>(hist, base);
+        }
+        BCB_CUDA_TRY(cudaGetLastError());
+    }
+    void *kin = keys, *kout = tmp_keys, *vin = values, *vout = tmp_vals;
+    for (int p = 0; p < NPASS; p++) {
+        BCB_TRY((run_pass<K, VB>(st, kin, kout, vin, vout, base + p * kRadixSize, (unsigned long long *)lb, n, p * kRadixBits, tf)));
+        void *t = kin; kin = kout; kout = t;
+        t = vin; vin = vout; vout = t;
+    }
+    if (kin != keys) {  // odd pass count (8-bit keys): result is in the temporary
+        BCB_CUDA_TRY(cudaMemcpyAsync(keys, kin, n * sizeof(K), cudaMemcpyDeviceToDevice, st->stream));
+        if (VB) BCB_CUDA_TRY(cudaMemcpyAsync(values, vin, n * (size_t)VB, cudaMemcpyDeviceToDevice, st->stream));
+    }
+    return BCB_SUCCESS;
+}
+
+template <typename K>
+static int sort_by_value_size(StreamState *st, void *keys, void *values, size_t vb, size_t n, const Transform &tf)
+{
+    if (!values || vb == 0) return sort_typed<K, 0>(st, keys, nullptr, n, tf);
+    const bool aligned = ((uintptr_t)values % (vb <= 16 ? vb : 1)) == 0;
+    if (aligned) {
+        switch (vb) {
+        case 1: return sort_typed<K, 1>(st, keys, values, n, tf);
+        case 2: return sort_typed<K, 2>(st, keys, values, n, tf);
+        case 4: return sort_typed<K, 4>(st, keys, values, n, tf);
+        case 8: return sort_typed<K, 8>(st, keys, values, n, tf);
+        case 16: return sort_typed<K, 16>(st, keys, values, n, tf);
+        default: break;
+        }
+    }
+    // generic payload: stable-sort (key, original index) pairs, then gather the payload bytes
+    unsigned *idx;
+    unsigned char *gathered;
+    BCB_CUDA_TRY(cudaMallocAsync((void **)&idx, n * sizeof(unsigned), st->stream));
+    cudaError_t e = cudaMallocAsync((void **)&gathered, n * vb, st->stream);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); (void)cudaFreeAsync(idx, st->stream); return (int)e; }
+    size_t blocks = (n + 255) / 256;
+    const size_t cap = (size_t)st->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    iota_u32_kernel<<<(unsigned)blocks, 256, 0, st->stream>>>(idx, n);
+    int rc = sort_typed<K, 4>(st, keys, idx, n, tf);
+    if (rc == BCB_SUCCESS) {
+        gather_bytes_kernel<<<(unsigned)blocks, 256, 0, st->stream>>>((const unsigned char *)values, idx, gathered, n, vb);
+        if (cudaMemcpyAsync(values, gathered, n * vb, cudaMemcpyDeviceToDevice, st->stream) != cudaSuccess) rc = (int)cudaGetLastError();
+    }
+    (void)cudaFreeAsync(idx, st->stream);
+    (void)cudaFreeAsync(gathered, st->stream);
+    if (rc == BCB_SUCCESS) {
+        cudaError_t le = cudaGetLastError();
+        if (le != cudaSuccess) rc = (int)le;
+    }
+    return rc;
+}
+
+static int radix_sort_impl(StreamState *st, int key_dtype, int ascending, void *keys, size_t n, void *values, size_t vb)
+{
+    const Transform tf = make_transform(key_dtype, ascending != 0);
+    switch (dtype_size(key_dtype)) {
+    case 1: return sort_by_value_size<unsigned char>(st, keys, values, vb, n, tf);
+    case 2: return sort_by_value_size<unsigned short>(st, keys, values, vb, n, tf);
+    case 4: return sort_by_value_size<unsigned>(st, keys, values, vb, n, tf);
+    case 8: return sort_by_value_size<unsigned long long>(st, keys, values, vb, n, tf);
+    default: return BCB_EINVAL;
+    }
+}
+
+static int insertion_sort_impl(StreamState *st, int key_dtype, int greater, void *keys, size_t n, void *values, size_t vb)
+{
+    unsigned char *v = (values && vb) ? (unsigned char *)values : nullptr;
+    switch (key_dtype) {
+#define X(DT, T) case DT: insertion_sort_kernel<T><<<1, 32, 0, st->stream>>>((T *)keys, n, greater, v, vb); break;
+        BCB_FOR_EACH_TYPE(X)
+#undef X
+    default: return BCB_EINVAL;
+    }
+    BCB_CUDA_TRY(cudaGetLastError());
+    return BCB_SUCCESS;
+}
+
+}  // namespace bcb
+
+using namespace bcb;
+
+extern "C" {
+
+int bcb_radix_sort(bcb_stream stream, int key_dtype, int ascending, void *keys, size_t n, void *values, size_t value_bytes)
+{
+    if (!dtype_size(key_dtype)) return BCB_EINVAL;
+    if (n < 2) return BCB_SUCCESS;
+    if (!keys) return BCB_EINVAL;
+    if (n >= 0xffff0000ull) return BCB_ETOOLARGE;
+    StreamState *st;
+    BCB_TRY(stream_state((cudaStream_t)stream, &st));
+    return radix_sort_impl(st, key_dtype, ascending, keys, n, values, values ? value_bytes : 0);
+}
+
+int bcb_insertion_sort(bcb_stream stream, int key_dtype, int greater, void *keys, size_t n, void *values, size_t value_bytes)
+{
+    if (!dtype_size(key_dtype)) return BCB_EINVAL;
+    if (n < 2) return BCB_SUCCESS;  // insertion_sort.hpp:34-37
+    if (!keys) return BCB_EINVAL;
+    if (n > 4096 || (values && value_bytes > 256)) return BCB_ETOOLARGE;
+    StreamState *st;
+    BCB_TRY(stream_state((cudaStream_t)stream, &st));
+    return insertion_sort_impl(st, key_dtype, greater, keys, n, values, value_bytes);
+}
+
+int bcb_sort_host(bcb_stream stream, int key_dtype, int descending, void *host_keys, size_t n)
+{
+    const size_t w = dtype_size(key_dtype);
+    if (!w) return BCB_EINVAL;
+    if (n < 2) return BCB_SUCCESS;  // sort.hpp:45-48
+    if (!host_keys) return BCB_EINVAL;
+    if (n >= 0xffff0000ull) return BCB_ETOOLARGE;
+    StreamState *st;
+    BCB_TRY(stream_state((cudaStream_t)stream, &st));
+    void *dev;
+    BCB_CUDA_TRY(cudaMallocAsync(&dev, n * w, st->stream));
+    int rc = BCB_SUCCESS;
+    cudaError_t e = cudaMemcpyAsync(dev, host_keys, n * w, cudaMemcpyHostToDevice, st->stream);
+    if (e != cudaSuccess) rc = (int)e;
+    if (rc == BCB_SUCCESS) {
+        // dispatch_gpu_sort, sort.hpp:34-81
+        rc = (n <= 32) ? insertion_sort_impl(st, key_dtype, descending, dev, n, nullptr, 0)
+                       : radix_sort_impl(st, key_dtype, !descending, dev, n, nullptr, 0);
+    }
+    if (rc == BCB_SUCCESS) {
+        e = cudaMemcpyAsync(host_keys, dev, n * w, cudaMemcpyDeviceToHost, st->stream);
+        if (e != cudaSuccess) rc = (int)e;
+    }
+    (void)cudaFreeAsync(dev, st->stream);
+    e = cudaStreamSynchronize(st->stream);
+    if (rc == BCB_SUCCESS && e != cudaSuccess) rc = (int)e;
+    if (rc != BCB_SUCCESS) (void)cudaGetLastError();
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,451 @@
+// runtime.cu -- device / stream / buffer plumbing and the per-stream scratch cache.
+// Replaces the subset of Boost.Compute's L1 core (system.hpp, command_queue.hpp, buffer.hpp)
+// that the sort / scan / reduce path touches; see include/compute_b200.h for the citations.
+#include "common.cuh"
+
+#include <mutex>
+#include <unordered_map>
+#include <cstring>
+#include <cstdio>
+
+namespace bcb {
+
+namespace {
+struct Key {
+    int device;
+    cudaStream_t stream;
+    bool operator==(const Key &o) const { return device == o.device && stream == o.stream; }
+};
+struct KeyHash {
+    size_t operator()(const Key &k) const { return std::hash<const void *>()((const void *)k.stream) * 31u + (size_t)k.device; }
+};
+std::mutex g_mutex;
+std::unordered_map<Key, StreamState *, KeyHash> g_states;
+constexpr size_t kControlBytes = 256;
+constexpr size_t kHistBytes = 8 * 256 * sizeof(uint32_t) * 2;  // counts + bases
+constexpr size_t kPinnedSlotBytes = 64;
+}  // namespace
+
+int stream_state(cudaStream_t stream, StreamState **out)
+{
+    int device = 0;
+    BCB_CUDA_TRY(cudaGetDevice(&device));
+    std::lock_guard<std::mutex> lock(g_mutex);
+    Key key{device, stream};
+    auto it = g_states.find(key);
+    if (it != g_states.end()) { *out = it->second; return BCB_SUCCESS; }
+    StreamState *st = new StreamState();
+    st->device = device;
+    st->stream = stream;
+    cudaError_t e = cudaDeviceGetAttribute(&st->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&st->control, kControlBytes);
+    if (e == cudaSuccess) e = cudaMemset(st->control, 0, kControlBytes);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&st->hist, kHistBytes);
+    if (e == cudaSuccess) e = cudaHostAlloc(&st->pinned_slot, kPinnedSlotBytes, cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer(&st->pinned_slot_dev, st->pinned_slot, 0);
+    if (e == cudaSuccess) {
+        // keep freed scratch cached in the pool instead of returning it to the OS at every sync
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long threshold = ~0ull;
+            (void)cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+        }
+        (void)cudaGetLastError();
+    }
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        if (st->control) cudaFree(st->control);
+        if (st->hist) cudaFree(st->hist);
+        if (st->pinned_slot) cudaFreeHost(st->pinned_slot);
+        delete st;
+        return (int)e;
+    }
+    g_states.emplace(key, st);
+    *out = st;
+    return BCB_SUCCESS;
+}
+
+int scratch_reserve(StreamState *st, size_t bytes, void **out)
+{
+    if (bytes > st->scratch_bytes) {
+        if (st->scratch) BCB_CUDA_TRY(cudaFreeAsync(st->scratch, st->stream));
+        st->scratch = nullptr;
+        st->scratch_bytes = 0;
+        size_t want = bytes + (bytes >> 3);  // headroom so slowly growing sizes do not realloc each call
+        want = (want + 255) & ~(size_t)255;
+        cudaError_t e = cudaMallocAsync(&st->scratch, want, st->stream);
+        if (e != cudaSuccess) {  // retry without headroom
+            (void)cudaGetLastError();
+            want = (bytes + 255) & ~(size_t)255;
+            BCB_CUDA_TRY(cudaMallocAsync(&st->scratch, want, st->stream));
+        }
+        st->scratch_bytes = want;
+    }
+    *out = st->scratch;
+    return BCB_SUCCESS;
+}
+
+int lookback_reserve(StreamState *st, size_t bytes, void **out)
+{
+    if (bytes > st->lookback_bytes) {
+        if (st->lookback) BCB_CUDA_TRY(cudaFreeAsync(st->lookback, st->stream));
+        st->lookback = nullptr;
+        st->lookback_bytes = 0;
+        size_t want = (bytes + (bytes >> 2) + 255) & ~(size_t)255;
+        BCB_CUDA_TRY(cudaMallocAsync(&st->lookback, want, st->stream));
+        st->lookback_bytes = want;
+        BCB_CUDA_TRY(cudaMemsetAsync(st->lookback, 0, want, st->stream));
+        st->epoch = 0;
+    }
+    *out = st->lookback;
+    return BCB_SUCCESS;
+}
+
+int next_epoch(StreamState *st, uint32_t *epoch)
+{
+    if (st->epoch >= (1u << 30) - 2) {
+        if (st->lookback) BCB_CUDA_TRY(cudaMemsetAsync(st->lookback, 0, st->lookback_bytes, st->stream));
+        st->epoch = 0;
+    }
+    *epoch = ++st->epoch;
+    return BCB_SUCCESS;
+}
+
+LaunchTimer::LaunchTimer(StreamState *s, int kind) : st(s)
+{
+    if (!st->timing) return;
+    if (st->timed_count == st->timed_capacity) {
+        const int cap = st->timed_capacity ? st->timed_capacity * 2 : 256;
+        auto *grown = new StreamState::TimedLaunch[cap];
+        for (int i = 0; i < st->timed_count; i++) grown[i] = st->timed[i];
+        delete[] st->timed;
+        st->timed = grown;
+        st->timed_capacity = cap;
+    }
+    StreamState::TimedLaunch &t = st->timed[st->timed_count];
+    t.kind = kind;
+    if (cudaEventCreate(&t.start) != cudaSuccess || cudaEventCreate(&t.stop) != cudaSuccess) { (void)cudaGetLastError(); return; }
+    slot = st->timed_count++;
+    (void)cudaEventRecord(t.start, st->stream);
+}
+
+LaunchTimer::~LaunchTimer()
+{
+    if (slot >= 0) (void)cudaEventRecord(st->timed[slot].stop, st->stream);
+}
+
+// ---- small helper kernels ---------------------------------------------------------------------
+template <typename T>
+__global__ void fill_kernel(T *p, size_t n, T v)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = v;
+}
+
+__global__ void fill_bytes_kernel(unsigned char *p, size_t n, const unsigned char *pattern, size_t w)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n * w; i += stride) p[i] = pattern[i % w];
+}
+
+template <typename T>
+__global__ void iota_kernel(T *p, size_t n, T start)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = (T)(start + (T)i);
+}
+
+// is_sorted.hpp:39-68: adjacent_find(first, last, greater) == last, i.e. no i with x[i] > x[i+1]
+template <typename T>
+__global__ void unsorted_pairs_kernel(const T *p, size_t n, int descending, int *flag)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    int bad = 0;
+    for (; i + 1 < n; i += stride) {
+        T a = p[i], b = p[i + 1];
+        bad |= descending ? (a < b) : (a > b);
+    }
+    if (bad) *flag = 1;
+}
+
+static int grid_for(size_t n, int sm_count)
+{
+    size_t blocks = (n + 255) / 256;
+    size_t cap = (size_t)sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace bcb
+
+using namespace bcb;
+
+extern "C" {
+
+const char *bcb_error_string(int status)
+{
+    switch (status) {
+    case BCB_SUCCESS: return "success";
+    case BCB_EINVAL: return "compute_b200: invalid argument";
+    case BCB_EUNSUPPORTED: return "compute_b200: unsupported dtype/op combination for this path";
+    case BCB_ETOOLARGE: return "compute_b200: element count beyond the supported range";
+    case BCB_ENODEVICE: return "compute_b200: no CUDA device found";
+    default: break;
+    }
+    if (status > 0 && status < 10000) return cudaGetErrorString((cudaError_t)status);
+    return "compute_b200: unknown error";
+}
+
+int bcb_version(void) { return 100; }
+
+int bcb_device_count(int *count)
+{
+    if (!count) return BCB_EINVAL;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); *count = 0; return BCB_ENODEVICE; }
+    return *count > 0 ? BCB_SUCCESS : BCB_ENODEVICE;
+}
+
+int bcb_device_info(int device, char *name, size_t name_capacity, int *compute_units, size_t *global_mem_bytes,
+                    int *cc_major, int *cc_minor)
+{
+    cudaDeviceProp prop;
+    BCB_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (name && name_capacity) { std::strncpy(name, prop.name, name_capacity - 1); name[name_capacity - 1] = 0; }
+    if (compute_units) *compute_units = prop.multiProcessorCount;
+    if (global_mem_bytes) *global_mem_bytes = prop.totalGlobalMem;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    return BCB_SUCCESS;
+}
+
+int bcb_set_device(int device) { BCB_CUDA_TRY(cudaSetDevice(device)); return BCB_SUCCESS; }
+int bcb_get_device(int *device) { if (!device) return BCB_EINVAL; BCB_CUDA_TRY(cudaGetDevice(device)); return BCB_SUCCESS; }
+
+int bcb_stream_create(int device, bcb_stream *stream)
+{
+    if (!stream) return BCB_EINVAL;
+    BCB_CUDA_TRY(cudaSetDevice(device));
+    cudaStream_t s;
+    BCB_CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *stream = (bcb_stream)s;
+    return BCB_SUCCESS;
+}
+
+int bcb_timing_enable(bcb_stream stream, int enable)
+{
+    StreamState *st;
+    BCB_TRY(stream_state((cudaStream_t)stream, &st));
+    st->timing = enable != 0;
+    return BCB_SUCCESS;
+}
+
+int bcb_timing_read(bcb_stream stream, int kind, double *total_ms, unsigned long long *launches)
+{
+    StreamState *st;
+    BCB_TRY(stream_state((cudaStream_t)stream, &st));
+    BCB_CUDA_TRY(cudaStreamSynchronize(st->stream));
+    double ms = 0.0;
+    unsigned long long count = 0;
+    int kept = 0;
+    for (int i = 0; i < st->timed_count; i++) {
+        StreamState::TimedLaunch &t = st->timed[i];
+        if (t.kind == kind) {
+            float e = 0.f;
+            if (cudaEventElapsedTime(&e, t.start, t.stop) == cudaSuccess) { ms += e; count++; }
+            (void)cudaEventDestroy(t.start);
+            (void)cudaEventDestroy(t.stop);
+        } else {
+            st->timed[kept++] = t;
+        }
+    }
+    st->timed_count = kept;
+    (void)cudaGetLastError();
+    if (total_ms) *total_ms = ms;
+    if (launches) *launches = count;
+    return BCB_SUCCESS;
+}
+
+int bcb_workspace_release(bcb_stream stream)
+{
+    int device = 0;
+    BCB_CUDA_TRY(cudaGetDevice(&device));
+    StreamState *st = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_mutex);
+        auto it = g_states.find(Key{device, (cudaStream_t)stream});
+        if (it == g_states.end()) return BCB_SUCCESS;
+        st = it->second;
+        g_states.erase(it);
+    }
+    (void)cudaStreamSynchronize(st->stream);
+    if (st->scratch) (void)cudaFreeAsync(st->scratch, st->stream);
+    if (st->lookback) (void)cudaFreeAsync(st->lookback, st->stream);
+    (void)cudaStreamSynchronize(st->stream);
+    if (st->control) (void)cudaFree(st->control);
+    if (st->hist) (void)cudaFree(st->hist);
+    if (st->pinned_slot) (void)cudaFreeHost(st->pinned_slot);
+    (void)cudaGetLastError();
+    delete st;
+    return BCB_SUCCESS;
+}
+
+int bcb_workspace_bytes(bcb_stream stream, size_t *bytes)
+{
+    if (!bytes) return BCB_EINVAL;
+    int device = 0;
+    BCB_CUDA_TRY(cudaGetDevice(&device));
+    std::lock_guard<std::mutex> lock(g_mutex);
+    auto it = g_states.find(Key{device, (cudaStream_t)stream});
+    *bytes = (it == g_states.end()) ? 0 : it->second->scratch_bytes + it->second->lookback_bytes;
+    return BCB_SUCCESS;
+}
+
+int bcb_stream_destroy(bcb_stream stream)
+{
+    (void)bcb_workspace_release(stream);
+    if (stream) BCB_CUDA_TRY(cudaStreamDestroy((cudaStream_t)stream));
+    return BCB_SUCCESS;
+}
+
+int bcb_stream_synchronize(bcb_stream stream)
+{
+    BCB_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return BCB_SUCCESS;
+}
+
+int bcb_malloc(void **device_ptr, size_t bytes)
+{
+    if (!device_ptr) return BCB_EINVAL;
+    *device_ptr = nullptr;
+    if (bytes == 0) return BCB_SUCCESS;
+    BCB_CUDA_TRY(cudaMalloc(device_ptr, bytes));
+    return BCB_SUCCESS;
+}
+
+int bcb_free(void *device_ptr)
+{
+    if (device_ptr) BCB_CUDA_TRY(cudaFree(device_ptr));
+    return BCB_SUCCESS;
+}
+
+int bcb_host_alloc(void **host_ptr, size_t bytes)
+{
+    if (!host_ptr) return BCB_EINVAL;
+    *host_ptr = nullptr;
+    if (bytes == 0) return BCB_SUCCESS;
+    BCB_CUDA_TRY(cudaHostAlloc(host_ptr, bytes, cudaHostAllocDefault));
+    return BCB_SUCCESS;
+}
+
+int bcb_host_free(void *host_ptr)
+{
+    if (host_ptr) BCB_CUDA_TRY(cudaFreeHost(host_ptr));
+    return BCB_SUCCESS;
+}
+
+int bcb_memcpy_h2d(bcb_stream stream, void *dst, const void *src, size_t bytes)
+{
+    if (bytes == 0) return BCB_SUCCESS;
+    if (!dst || !src) return BCB_EINVAL;
+    BCB_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return BCB_SUCCESS;
+}
+
+int bcb_memcpy_d2h(bcb_stream stream, void *dst, const void *src, size_t bytes)
+{
+    if (bytes == 0) return BCB_SUCCESS;
+    if (!dst || !src) return BCB_EINVAL;
+    BCB_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return BCB_SUCCESS;
+}
+
+int bcb_memcpy_d2d(bcb_stream stream, void *dst, const void *src, size_t bytes)
+{
+    if (bytes == 0) return BCB_SUCCESS;
+    if (!dst || !src) return BCB_EINVAL;
+    BCB_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return BCB_SUCCESS;
+}
+
+int bcb_fill(bcb_stream stream, void *p, size_t n, const void *value_host, size_t w)
+{
+    if (n == 0) return BCB_SUCCESS;
+    if (!p || !value_host || w == 0) return BCB_EINVAL;
+    StreamState *st;
+    BCB_TRY(stream_state((cudaStream_t)stream, &st));
+    cudaStream_t s = (cudaStream_t)stream;
+    int grid = grid_for(n, st->sm_count);
+    switch (w) {
+    case 1: { uint8_t v; memcpy(&v, value_host, 1); fill_kernel<<<grid, 256, 0, s>>>((uint8_t *)p, n, v); break; }
+    case 2: { uint16_t v; memcpy(&v, value_host, 2); fill_kernel<<<grid, 256, 0, s>>>((uint16_t *)p, n, v); break; }
+    case 4: { uint32_t v; memcpy(&v, value_host, 4); fill_kernel<<<grid, 256, 0, s>>>((uint32_t *)p, n, v); break; }
+    case 8: { unsigned long long v; memcpy(&v, value_host, 8); fill_kernel<<<grid, 256, 0, s>>>((unsigned long long *)p, n, v); break; }
+    default: {
+        void *pat;
+        BCB_TRY(scratch_reserve(st, w, &pat));
+        BCB_CUDA_TRY(cudaMemcpyAsync(pat, value_host, w, cudaMemcpyHostToDevice, s));
+        fill_bytes_kernel<<<grid, 256, 0, s>>>((unsigned char *)p, n, (const unsigned char *)pat, w);
+        break;
+    }
+    }
+    BCB_CUDA_TRY(cudaGetLastError());
+    return BCB_SUCCESS;
+}
+
+int bcb_iota(bcb_stream stream, int dtype, void *p, size_t n, const void *start_host)
+{
+    if (n == 0) return BCB_SUCCESS;
+    if (!p || !start_host) return BCB_EINVAL;
+    StreamState *st;
+    BCB_TRY(stream_state((cudaStream_t)stream, &st));
+    cudaStream_t s = (cudaStream_t)stream;
+    int grid = grid_for(n, st->sm_count);
+#define IOTA_CASE(DT, T) \
+    case DT: { T v; memcpy(&v, start_host, sizeof(T)); iota_kernel<<<grid, 256, 0, s>>>((T *)p, n, v); break; }
+    switch (dtype) {
+        IOTA_CASE(BCB_CHAR, signed char) IOTA_CASE(BCB_UCHAR, unsigned char) IOTA_CASE(BCB_SHORT, short)
+        IOTA_CASE(BCB_USHORT, unsigned short) IOTA_CASE(BCB_INT, int) IOTA_CASE(BCB_UINT, unsigned)
+        IOTA_CASE(BCB_LONG, long long) IOTA_CASE(BCB_ULONG, unsigned long long) IOTA_CASE(BCB_FLOAT, float)
+        IOTA_CASE(BCB_DOUBLE, double)
+    default: return BCB_EINVAL;
+    }
+#undef IOTA_CASE
+    BCB_CUDA_TRY(cudaGetLastError());
+    return BCB_SUCCESS;
+}
+
+int bcb_is_sorted(bcb_stream stream, int dtype, int descending, const void *keys, size_t n, int *result_host)
+{
+    if (!result_host) return BCB_EINVAL;
+    *result_host = 1;
+    if (n < 2) return BCB_SUCCESS;
+    if (!keys) return BCB_EINVAL;
+    StreamState *st;
+    BCB_TRY(stream_state((cudaStream_t)stream, &st));
+    cudaStream_t s = (cudaStream_t)stream;
+    int *flag = (int *)st->pinned_slot_dev;
+    *(volatile int *)st->pinned_slot = 0;
+    int grid = grid_for(n, st->sm_count);
+#define SORTED_CASE(DT, T) \
+    case DT: unsorted_pairs_kernel<<<grid, 256, 0, s>>>((const T *)keys, n, descending, flag); break;
+    switch (dtype) {
+        SORTED_CASE(BCB_CHAR, signed char) SORTED_CASE(BCB_UCHAR, unsigned char) SORTED_CASE(BCB_SHORT, short)
+        SORTED_CASE(BCB_USHORT, unsigned short) SORTED_CASE(BCB_INT, int) SORTED_CASE(BCB_UINT, unsigned)
+        SORTED_CASE(BCB_LONG, long long) SORTED_CASE(BCB_ULONG, unsigned long long) SORTED_CASE(BCB_FLOAT, float)
+        SORTED_CASE(BCB_DOUBLE, double)
+    default: return BCB_EINVAL;
+    }
+#undef SORTED_CASE
+    BCB_CUDA_TRY(cudaGetLastError());
+    BCB_CUDA_TRY(cudaStreamSynchronize(s));
+    *result_host = (*(volatile int *)st->pinned_slot) ? 0 : 1;
+    return BCB_SUCCESS;
+}
+
+}  // extern "C"

@@ -1,0 +1,142 @@
+/*
+ * compute_b200.h -- C ABI of the B200-native sort / scan / reduce path.
+ *
+ * This is the drop-in boundary: plain pointers, sizes and integer codes only.  The
+ * header-only C++ layer under include/boost/compute/ (same spellings as the reference)
+ * and the Python mirror compute_b200/ both sit on top of exactly these entry points.
+ * Every entry point cites the reference interface it replaces; paths are relative to
+ * boostorg/compute include/boost/compute/.
+ *
+ * Conventions
+ *  - All device work is enqueued on `stream` (a cudaStream_t passed as void*, NULL = the
+ *    legacy default stream) and the call returns without waiting, exactly like the
+ *    reference's enqueue-and-return algorithms (perf/perf_sort.cpp:38-39); calls that
+ *    hand a value back to the host block until it is there (accumulate.hpp:178-188,
+ *    reduce.hpp:225).
+ *  - Return value: 0 on success, otherwise a cudaError_t value (< 10000) or one of the
+ *    BCB_E* codes; nothing throws or aborts.  bcb_error_string() describes either kind.
+ *    The C++ layer maps nonzero codes to boost::compute::opencl_error
+ *    (exception/opencl_error.hpp:30-61).
+ *  - Scratch memory is owned by the library, cached per stream and stream-ordered; the
+ *    caller owns keys / values / in / out.
+ *  - Element counts are size_t; sorts accept n < 2^32 (the reference narrows to uint_:
+ *    algorithm/detail/radix_sort.hpp:351), scan/reduce accept any n.
+ *  - There is no CPU fallback: every entry point needs a CUDA device.
+ */
+#ifndef COMPUTE_B200_H
+#define COMPUTE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* scalar types of types/fundamental.hpp:30-39 (char_ ... double_) */
+typedef enum bcb_dtype {
+    BCB_CHAR = 0, BCB_UCHAR = 1, BCB_SHORT = 2, BCB_USHORT = 3, BCB_INT = 4,
+    BCB_UINT = 5, BCB_LONG = 6, BCB_ULONG = 7, BCB_FLOAT = 8, BCB_DOUBLE = 9
+} bcb_dtype;
+
+/* functors of functional/operator.hpp:73-96 that the path accepts */
+typedef enum bcb_op {
+    BCB_PLUS = 0, BCB_MULTIPLIES = 1, BCB_MIN = 2, BCB_MAX = 3,
+    BCB_BIT_AND = 4, BCB_BIT_OR = 5, BCB_BIT_XOR = 6,
+    BCB_MINUS = 7, BCB_DIVIDES = 8 /* non-associative: bcb_accumulate (serial fold) only */
+} bcb_op;
+
+#define BCB_SUCCESS 0
+#define BCB_EINVAL 10001       /* bad argument (null pointer, unknown dtype/op ...) */
+#define BCB_EUNSUPPORTED 10002 /* combination outside the hot path (e.g. bit op on float) */
+#define BCB_ETOOLARGE 10003    /* n beyond the supported range of the entry point */
+#define BCB_ENODEVICE 10004    /* no CUDA device (system.hpp:238-241 no_device_found) */
+
+typedef void *bcb_stream; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define BCB_API __attribute__((visibility("default")))
+#else
+#define BCB_API
+#endif
+
+BCB_API const char *bcb_error_string(int status);
+BCB_API int bcb_version(void);
+
+/* ---- device / queue / buffer plumbing: the subset of the L1 core the path touches ---- */
+/* system::devices / device::name / compute_units / global_memory_size (system.hpp:92-196, device.hpp) */
+BCB_API int bcb_device_count(int *count);
+BCB_API int bcb_device_info(int device, char *name, size_t name_capacity, int *compute_units,
+                    size_t *global_mem_bytes, int *cc_major, int *cc_minor);
+BCB_API int bcb_set_device(int device);
+BCB_API int bcb_get_device(int *device);
+/* command_queue ctor / dtor / finish (command_queue.hpp:125-162, :1564-1572) */
+BCB_API int bcb_stream_create(int device, bcb_stream *stream);
+BCB_API int bcb_stream_destroy(bcb_stream stream);
+BCB_API int bcb_stream_synchronize(bcb_stream stream);
+/* buffer ctor / dtor (buffer.hpp:74-89); pinned host staging for copies */
+BCB_API int bcb_malloc(void **device_ptr, size_t bytes);
+BCB_API int bcb_free(void *device_ptr);
+BCB_API int bcb_host_alloc(void **host_ptr, size_t bytes);
+BCB_API int bcb_host_free(void *host_ptr);
+/* enqueue_write_buffer / enqueue_read_buffer / enqueue_copy_buffer (command_queue.hpp:297-675); async on stream */
+BCB_API int bcb_memcpy_h2d(bcb_stream stream, void *device_dst, const void *host_src, size_t bytes);
+BCB_API int bcb_memcpy_d2h(bcb_stream stream, void *host_dst, const void *device_src, size_t bytes);
+BCB_API int bcb_memcpy_d2d(bcb_stream stream, void *device_dst, const void *device_src, size_t bytes);
+/* fill / iota / is_sorted (algorithm/fill.hpp, iota.hpp, is_sorted.hpp:39-68) -- the helpers either side of the path */
+BCB_API int bcb_fill(bcb_stream stream, void *device_ptr, size_t n, const void *value_host, size_t value_bytes);
+BCB_API int bcb_iota(bcb_stream stream, int dtype, void *device_ptr, size_t n, const void *start_host);
+BCB_API int bcb_is_sorted(bcb_stream stream, int dtype, int descending, const void *keys, size_t n, int *result_host);
+/* per-kernel device timing for benchmarks: when enabled, launchers bracket each kernel with CUDA events on the
+ * stream.  bcb_timing_read waits for the stream, returns the summed duration and launch count of one kernel kind
+ * since the last read of that kind, and forgets them. */
+typedef enum bcb_kernel_kind {
+    BCB_K_RADIX_HISTOGRAM = 0, BCB_K_DIGIT_SCAN = 1, BCB_K_ONESWEEP_PASS = 2, BCB_K_SCAN = 3, BCB_K_REDUCE = 4,
+    BCB_K_OTHER = 5, BCB_K_COUNT = 6
+} bcb_kernel_kind;
+BCB_API int bcb_timing_enable(bcb_stream stream, int enable);
+BCB_API int bcb_timing_read(bcb_stream stream, int kind, double *total_ms, unsigned long long *launches);
+/* scratch cache of a stream */
+BCB_API int bcb_workspace_bytes(bcb_stream stream, size_t *bytes);
+BCB_API int bcb_workspace_release(bcb_stream stream);
+
+/* ---- sort ---- */
+/* detail::radix_sort / radix_sort_by_key (algorithm/detail/radix_sort.hpp:428-462 -> radix_sort_impl :252-426).
+ * Stable LSD radix sort by the reference's key transform (:100-127), in place.  values == NULL for keys only;
+ * value_bytes is sizeof(T2), any size >= 1.  ascending != 0 sorts by less<T>, 0 by greater<T>. */
+BCB_API int bcb_radix_sort(bcb_stream stream, int key_dtype, int ascending, void *keys, size_t n,
+                   void *values, size_t value_bytes);
+/* detail::serial_insertion_sort / _by_key (algorithm/detail/insertion_sort.hpp:25-159): one thread, native compare.
+ * greater != 0 uses ">" (descending).  n <= 4096. */
+BCB_API int bcb_insertion_sort(bcb_stream stream, int key_dtype, int greater, void *keys, size_t n,
+                       void *values, size_t value_bytes);
+/* sort() on a host range (algorithm/sort.hpp:125-148: maps the range, sorts, unmaps): copies host_keys to the
+ * device, applies the sort() dispatch of sort.hpp:34-81, copies back, and waits. */
+BCB_API int bcb_sort_host(bcb_stream stream, int key_dtype, int descending, void *host_keys, size_t n);
+
+/* ---- scan ---- */
+/* detail::scan (algorithm/detail/scan.hpp:22-39) with the operator-generic semantics of serial_scan.hpp:26-97:
+ * inclusive: out[i] = x0 op ... op xi;  exclusive: out[i] = init op x0 op ... op x(i-1).  Arithmetic in out_dtype
+ * (exclusive_scan.hpp:80-85).  in == out (in place) is allowed.  init_host points at one out_dtype value
+ * (NULL = 0); it is ignored for inclusive scans. */
+BCB_API int bcb_scan(bcb_stream stream, int in_dtype, int out_dtype, int op, int exclusive,
+             const void *in, void *out, size_t n, const void *init_host);
+
+/* ---- reduce / accumulate ---- */
+/* reduce (algorithm/reduce.hpp:275-305): result = x0 op ... op x(n-1) in result_dtype (= result_of<F(T,T)>,
+ * the functor's type).  n == 0 leaves *result untouched (:283-285).  result_is_device selects a device
+ * destination (enqueue-and-return) or a host destination (blocks until written). */
+BCB_API int bcb_reduce(bcb_stream stream, int in_dtype, int result_dtype, int op, const void *in, size_t n,
+               void *result, int result_is_device);
+/* accumulate (algorithm/accumulate.hpp:102-188): returns init op x0 op ... as a host value of acc_dtype (the type
+ * of init); op_dtype is the functor's argument type.  Associative (op, type) pairs run the parallel reduce
+ * kernel and fold init in afterwards (exact for integers; float sums differ from the reference's serial fold
+ * only by summation order); MINUS / DIVIDES and mixed acc/op types run the single-thread left fold of
+ * detail/serial_accumulate.hpp:22-50.  Always blocks. */
+BCB_API int bcb_accumulate(bcb_stream stream, int in_dtype, int op_dtype, int acc_dtype, int op, const void *in,
+                   size_t n, const void *init_host, void *result_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COMPUTE_B200_H */

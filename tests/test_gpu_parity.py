@@ -1,0 +1,276 @@
+"""GPU parity tests: the CUDA path (through the C ABI) vs the CPU oracle and the reference's golden vectors.
+
+Bar: bit-exact (byte comparison) for every sort and for integer scan / reduce / accumulate; float sums within
+|gpu - S| <= 4 * ceil(log2 N) * 2^-24 * sum|x_i| of a float64 left fold S (2^-53 for double), per element for
+scans."""
+import math
+
+import numpy as np
+import pytest
+
+import oracle
+from golden_util import case_id, check_case, load_cases
+
+pytestmark = pytest.mark.gpu
+
+CASES = load_cases()
+ALL = oracle.DTYPES
+NPD = oracle.NP_DTYPES
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import gpu_api
+    return gpu_api
+
+
+def test_native_library_is_loaded(gpu):
+    import compute_b200
+    assert compute_b200.lib().bcb_version() >= 100
+    with open("/proc/self/maps") as f:
+        assert "libcompute_b200.so" in f.read()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[case_id(c) for c in CASES])
+def test_gpu_matches_reference_golden(case, gpu):
+    check_case(case, gpu)
+
+
+def random_keys(dtype, n, seed, mode="bits"):
+    rng = np.random.default_rng(seed)
+    npdt = np.dtype(NPD[dtype])
+    w = npdt.itemsize
+    if mode == "bits":  # every bit pattern incl. NaN payloads, +-0, +-inf, denormals
+        k = rng.integers(0, 256, size=n * w, dtype=np.uint8).view(npdt).copy()
+        if npdt.kind == "f" and n >= 16:
+            specials = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, -np.nan, np.finfo(npdt).tiny, -np.finfo(npdt).tiny,
+                                 np.finfo(npdt).smallest_subnormal, -np.finfo(npdt).smallest_subnormal], dtype=npdt)
+            pos = rng.integers(0, n, size=4 * len(specials))
+            k[pos] = np.tile(specials, 4)
+        return k
+    if mode == "few":  # heavy duplicates: exercises stability and digit skew
+        vals = rng.integers(0, 256, size=5 * w, dtype=np.uint8).view(npdt)
+        return vals[rng.integers(0, 5, size=n)].copy()
+    if mode == "equal":
+        return np.full(n, rng.integers(0, 256, size=w, dtype=np.uint8).view(npdt)[0], dtype=npdt)
+    if mode == "sorted":
+        return np.sort(rng.integers(0, 256, size=n * w, dtype=np.uint8).view({1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[w])).view(npdt).copy()
+    raise ValueError(mode)
+
+
+SORT_SIZES = [2, 31, 32, 33, 100, 1000, 7679, 7680, 7681, 50_000, 300_001]
+
+
+@pytest.mark.parametrize("dtype", ALL)
+@pytest.mark.parametrize("descending", [False, True], ids=["asc", "desc"])
+def test_radix_sort_keys_bit_exact(dtype, descending, gpu):
+    for n in SORT_SIZES:
+        for mode in (["bits"] if n not in (1000, 50_000) else ["bits", "few", "equal", "sorted"]):
+            k = random_keys(dtype, n, seed=n * 7 + len(mode), mode=mode)
+            got = gpu.radix_sort(k, descending)
+            exp = oracle.radix_sort(k, descending)
+            assert got.tobytes() == exp.tobytes(), (dtype, descending, n, mode)
+
+
+@pytest.mark.parametrize("dtype", ALL)
+def test_public_sort_dispatch_bit_exact(dtype, gpu):
+    """sort(): n<=32 insertion sort (native compare: +-0 ties keep input order), else radix."""
+    for n in (0, 1, 2, 17, 32, 33, 500):
+        for desc in (False, True):
+            k = random_keys(dtype, n, seed=n + 99, mode="bits") if n else np.empty(0, NPD[dtype])
+            if np.dtype(NPD[dtype]).kind == "f" and n:
+                k[np.isnan(k)] = 1.5  # insertion sort with NaN is order-dependent garbage in both; keep it defined
+                k[: min(n, 4)] = [0.0, -0.0, 0.0, -0.0][: min(n, 4)]
+            assert gpu.sort(k, desc).tobytes() == oracle.sort(k, desc).tobytes(), (dtype, n, desc)
+            assert gpu.stable_sort(k, desc).tobytes() == oracle.stable_sort(k, desc).tobytes(), (dtype, n, desc)
+
+
+@pytest.mark.parametrize("key_dtype", ["uchar", "short", "int", "uint", "float", "long", "ulong", "double"])
+@pytest.mark.parametrize("value_bytes", [1, 2, 4, 8, 16, 12, 3])
+def test_radix_sort_pairs_bit_exact_and_stable(key_dtype, value_bytes, gpu):
+    for n, mode in ((40, "few"), (5000, "few"), (7681, "bits"), (100_003, "few")):
+        for desc in (False, True):
+            k = random_keys(key_dtype, n, seed=n + value_bytes, mode=mode)
+            rng = np.random.default_rng(n)
+            v = rng.integers(0, 256, size=(n, value_bytes), dtype=np.uint8)
+            v[:, :min(3, value_bytes)] = (np.arange(n)[:, None] >> (8 * np.arange(min(3, value_bytes)))) & 0xFF  # original index
+            gk, gv = gpu.radix_sort(k, desc, v)
+            ek, ev = oracle.radix_sort(k, desc, v)
+            assert gk.tobytes() == ek.tobytes(), (key_dtype, value_bytes, n, desc)
+            assert gv.tobytes() == ev.tobytes(), (key_dtype, value_bytes, n, desc)
+
+
+def test_sort_by_key_dispatch(gpu):
+    for n in (0, 1, 5, 31, 32, 64):
+        k = random_keys("int", n, seed=n, mode="few") if n else np.empty(0, np.int32)
+        v = np.arange(n, dtype=np.uint32)
+        for desc in (False, True):
+            gk, gv = gpu.sort_by_key(k, v, desc)
+            ek, ev = oracle.sort_by_key(k, v, desc)
+            assert gk.tobytes() == ek.tobytes() and gv.tobytes() == ev.tobytes(), (n, desc)
+
+
+@pytest.mark.parametrize("dtype", ["uchar", "ushort", "uint", "float", "ulong"])
+def test_sort_unaligned_sub_range(dtype, gpu):
+    """buffer_iterator offsets are arbitrary: sort [lo, hi) and leave the rest untouched."""
+    n = 20_011
+    k = random_keys(dtype, n, seed=5, mode="bits")
+    for lo, hi in ((1, n - 1), (3, 10_000), (7, 7 + 7680), (13, 13 + 40)):
+        got = gpu.sort_sub_range("radix_sort", k, lo, hi, False)
+        exp = k.copy()
+        exp[lo:hi] = oracle.radix_sort(k[lo:hi], False)
+        assert got.tobytes() == exp.tobytes(), (dtype, lo, hi)
+
+
+def test_sort_host_range(gpu):
+    for n in (1, 20, 33, 100_000):
+        k = random_keys("uint", n, seed=n, mode="bits")
+        assert gpu.sort_host(k).tobytes() == oracle.sort(k).tobytes()
+        assert gpu.sort_host(k, True).tobytes() == oracle.sort(k, True).tobytes()
+
+
+def test_repeat_calls_reuse_workspace(gpu):
+    """program-cache style repeat (test_radix_sort.cpp:194-201) + shrinking / growing sizes on one stream."""
+    for n in (100_000, 50, 7681, 1_000_000, 33, 100_000):
+        k = random_keys("uint", n, seed=n, mode="bits")
+        assert gpu.radix_sort(k).tobytes() == oracle.radix_sort(k).tobytes()
+        x = np.random.default_rng(n).integers(-100, 100, size=n).astype(np.int32)
+        np.testing.assert_array_equal(gpu.scan(x, "plus", True, 3), oracle.scan(x, "plus", True, 3))
+
+
+# ------------------------------------------------------------------------------------------ scan
+SCAN_SIZES = [1, 2, 31, 255, 256, 257, 4095, 4096, 4097, 12_289, 100_000, 1_000_003]
+INT_TYPES = ["char", "uchar", "short", "ushort", "int", "uint", "long", "ulong"]
+
+
+def scan_input(dtype, n, seed):
+    rng = np.random.default_rng(seed)
+    npdt = np.dtype(NPD[dtype])
+    if npdt.kind == "f":
+        return rng.uniform(-1.0, 1.0, size=n).astype(npdt)
+    w = npdt.itemsize
+    return rng.integers(0, 256, size=n * w, dtype=np.uint8).view(npdt).copy()  # full range -> wrap-around matters
+
+
+@pytest.mark.parametrize("dtype", INT_TYPES)
+@pytest.mark.parametrize("op", ["plus", "multiplies", "min", "max", "bit_and", "bit_or", "bit_xor"])
+def test_scan_integer_bit_exact(dtype, op, gpu):
+    for n in SCAN_SIZES:
+        x = scan_input(dtype, n, seed=n)
+        if op == "multiplies":
+            x = (x | 1).astype(x.dtype)  # keep products from collapsing to 0
+        for excl, init in ((False, 0), (True, 0), (True, 7)):
+            for in_place in (False, True):
+                got = gpu.scan(x, op, excl, init, in_place=in_place)
+                exp = oracle.scan(x, op, excl, init)
+                assert got.tobytes() == exp.tobytes(), (dtype, op, n, excl, init, in_place)
+
+
+@pytest.mark.parametrize("dtype", ["float", "double"])
+def test_scan_float_plus_within_tolerance_and_deterministic(dtype, gpu):
+    eps = 2.0 ** -24 if dtype == "float" else 2.0 ** -53
+    for n in SCAN_SIZES + [5_000_000]:
+        x = scan_input(dtype, n, seed=n)
+        for excl in (False, True):
+            got = gpu.scan(x, "plus", excl, 0.25 if excl else 0).astype(np.float64)
+            pref, apref = oracle.prefix_f64(x)
+            if excl:
+                ref = np.concatenate([[0.25], 0.25 + pref[:-1]])
+                aref = np.concatenate([[0.25], 0.25 + apref[:-1]])
+            else:
+                ref, aref = pref, apref
+            tol = 4 * max(1, math.ceil(math.log2(max(n, 2)))) * eps * aref + 1e-300
+            assert np.all(np.abs(got - ref) <= tol), (dtype, n, excl, float(np.max(np.abs(got - ref) / tol)))
+            again = gpu.scan(x, "plus", excl, 0.25 if excl else 0)
+            assert again.astype(np.float64).tobytes() == got.tobytes(), "float scan must be run-to-run deterministic"
+
+
+@pytest.mark.parametrize("dtype", ["float", "double"])
+@pytest.mark.parametrize("op", ["min", "max"])
+def test_scan_float_minmax_exact(dtype, op, gpu):
+    for n in (1, 1000, 4097, 100_000):
+        x = scan_input(dtype, n, seed=n)
+        for excl, init in ((False, 0), (True, 0.5)):
+            assert gpu.scan(x, op, excl, init).tobytes() == oracle.scan(x, op, excl, init).tobytes()
+
+
+def test_scan_mixed_types(gpu):
+    """arithmetic in the OUTPUT type (exclusive_scan.hpp:80-85)."""
+    x = scan_input("uchar", 10_000, 3)
+    for out in ("int", "float", "long"):
+        got = gpu.scan(x, "plus", True, 1, out_dtype=NPD[out])
+        exp = oracle.scan(x, "plus", True, 1, out_dtype=NPD[out])
+        assert got.tobytes() == exp.tobytes(), out  # uchar sums < 2^24: exact in float too
+
+
+# ------------------------------------------------------------------------------------------ reduce / accumulate
+RED_SIZES = [1, 2, 3, 33, 1023, 1024, 1025, 4099, 65_537, 1_000_003, 5_000_011]
+
+
+@pytest.mark.parametrize("dtype", INT_TYPES)
+@pytest.mark.parametrize("op", ["plus", "multiplies", "min", "max", "bit_and", "bit_or", "bit_xor"])
+def test_reduce_integer_bit_exact(dtype, op, gpu):
+    for n in RED_SIZES:
+        x = scan_input(dtype, n, seed=n + 1)
+        if op == "multiplies":
+            x = (x | 1).astype(x.dtype)
+        got = gpu.reduce(x, op)
+        exp = oracle.reduce(x, op)
+        assert NPD[dtype](got).tobytes() == NPD[dtype](exp).tobytes(), (dtype, op, n)
+
+
+def test_reduce_unaligned_sub_range(gpu):
+    import torch
+    import compute_b200 as cb
+    x = scan_input("int", 100_001, 9)
+    d = gpu.to_dev(x)
+    for lo, hi in ((1, 100_001), (3, 77_777), (5, 6), (2, 2)):
+        got = cb.reduce(d[lo:hi], None, "plus")
+        if lo == hi:
+            assert got is None
+        else:
+            assert np.int32(got) == oracle.reduce(x[lo:hi], "plus")
+    for dt in ("uchar", "short", "double"):
+        y = scan_input(dt, 50_001, 4)
+        dy = gpu.to_dev(y)
+        got = cb.reduce(dy[1:], None, "max")
+        assert NPD[dt](got) == oracle.reduce(y[1:], "max")
+
+
+@pytest.mark.parametrize("dtype", ["float", "double"])
+def test_reduce_float_within_tolerance_and_deterministic(dtype, gpu):
+    eps = 2.0 ** -24 if dtype == "float" else 2.0 ** -53
+    for n in RED_SIZES:
+        x = np.random.default_rng(n).uniform(0, 1, size=n).astype(NPD[dtype])
+        got = float(gpu.reduce(x, "plus"))
+        s, a = oracle.sum_f64(x)
+        tol = 4 * max(1, math.ceil(math.log2(max(n, 2)))) * eps * a
+        assert abs(got - s) <= tol, (dtype, n, got, s, tol)
+        assert float(gpu.reduce(x, "plus")) == got
+        assert NPD[dtype](gpu.reduce(x, "min")) == oracle.reduce(x, "min")
+        assert NPD[dtype](gpu.reduce(x, "max")) == oracle.reduce(x, "max")
+        acc = float(gpu.accumulate(x, NPD[dtype](1.5), "plus"))
+        assert abs(acc - (s + 1.5)) <= tol + eps * 4
+
+
+def test_reduce_mixed_result_type(gpu):
+    x = scan_input("uchar", 100_000, 2)
+    assert gpu.reduce(x, "plus", np.float32) == oracle.reduce(x, "plus", np.float32)  # < 2^24: exact
+    assert gpu.reduce(x, "plus", np.int64) == oracle.reduce(x, "plus", np.int64)
+    assert gpu.reduce(x, "plus", np.uint8) == oracle.reduce(x, "plus", np.uint8)
+
+
+def test_accumulate_paths(gpu):
+    x = scan_input("int", 100_003, 11)
+    for init in (0, 5, -7):
+        for op in ("plus", "multiplies", "min", "max", "bit_xor"):
+            xx = (x | 1) if op == "multiplies" else x
+            assert np.int32(gpu.accumulate(xx, np.int32(init), op)) == oracle.accumulate(xx, np.int32(init), op), (init, op)
+    small = np.array([2, 8, 16], np.int32)
+    assert gpu.accumulate(small, np.int32(1024), "divides") == 4
+    assert gpu.accumulate(small, np.int32(100), "minus") == 74
+    f = np.random.default_rng(0).uniform(0, 3, size=2000).astype(np.float32)
+    # int-typed init over float data: strict serial fold with truncation each step (test_accumulate.cpp:258-268)
+    assert gpu.accumulate(f, np.int32(0), "plus", op_dtype=np.float32, acc_dtype=np.int32) == \
+        oracle.accumulate(f, np.int32(0), "plus", op_dtype=np.float32, acc_dtype=np.int32)
+    assert gpu.accumulate(np.empty(0, np.int32), np.int32(9), "plus") == 9
