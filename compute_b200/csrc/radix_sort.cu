@@ -28,6 +28,7 @@ namespace bcb {
 constexpr int kRadixBits = 8;
 constexpr int kRadixSize = 1 << kRadixBits;
 constexpr int kHistThreads = 512;
+constexpr int kLookbackBatch = 8;  // default look-back batch
 
 enum : unsigned { kLbInvalid = 0u, kLbPartial = 1u, kLbInclusive = 2u };
 
@@ -144,6 +145,19 @@ __global__ void __launch_bounds__(kRadixSize) digit_scan(const unsigned *__restr
 }
 
 // ---- 3. one onesweep pass ---------------------------------------------------------------------------
+// Ranking modes.  Measured on B200 (bench/microbench.cu, cycles per warp-instruction per SM): hardware match.any
+// with ~30 distinct values costs 62, an 8-ballot software match 27, shared-memory atomics / loads about 1.5-1.8.
+// At HBM speed an SM must retire 32 keys every ~11 cycles, so both match flavours are out; ranking is built from
+// shared-memory atomics instead:
+//   kRankAtomicOr     (default): every lane ORs its lane bit into a per-warp {mask, count} entry of its digit;
+//                     after a warp barrier the entry holds the full peer mask (order independent), the rank inside
+//                     the round is popc(mask & lanes below), the highest peer clears the mask and bumps the count.
+//                     Deterministic by construction: 3 shared-memory instructions per key.
+//   kRankOrderedAtoms (experimental, BCB_SORT_RANK=ordered): rank = atomicAdd(count, 1).  One instruction per key, but
+//                     stable only if same-address atomics of one warp instruction are applied in lane order, which
+//                     CUDA does not promise; never selected by default.
+enum { kRankAtomicOr = 0, kRankOrderedAtoms = 1 };
+
 template <int VB> struct value_type;
 template <> struct value_type<0> { typedef unsigned char type; };
 template <> struct value_type<1> { typedef unsigned char type; };
@@ -152,92 +166,95 @@ template <> struct value_type<4> { typedef unsigned type; };
 template <> struct value_type<8> { typedef unsigned long long type; };
 template <> struct value_type<16> { typedef uint4 type; };
 
-template <typename K, int VB, int THREADS, int ITEMS>
+template <typename K, int VB, int THREADS, int ITEMS, int RANK>
 struct PassSmem {
     static constexpr int WARPS = THREADS / 32;
     static constexpr int TILE = THREADS * ITEMS;
+    static constexpr size_t kEntry = (RANK == kRankAtomicOr) ? 8 : 4;   // {mask, count} or count
     static constexpr size_t kElem = (sizeof(K) > (size_t)VB) ? sizeof(K) : (size_t)VB;
-    static constexpr size_t kWarpHist = (size_t)WARPS * kRadixSize * sizeof(unsigned);
-    static constexpr size_t kSmall = 2 * kRadixSize * sizeof(unsigned) + 64;  // digit_start, out_base, misc
-    static constexpr size_t kBytes = kWarpHist + kSmall + (size_t)TILE * kElem + 16;
+    static constexpr size_t kWarpTab = (size_t)WARPS * kRadixSize * kEntry;
+    static constexpr size_t kSmall = kRadixSize * sizeof(unsigned) + 64;  // out_base + misc
+    static constexpr size_t kBytes = kWarpTab + kSmall + (size_t)TILE * kElem + 16;
 };
 
-template <typename K, int VB, int THREADS, int ITEMS>
-__global__ void __launch_bounds__(THREADS)
-onesweep_pass(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *__restrict__ vals_in_v,
-              void *__restrict__ vals_out_v, const unsigned *__restrict__ digit_base, unsigned long long *lookback,
-              unsigned epoch, unsigned long long *ticket, unsigned long long ticket_base, size_t n, int shift, Transform tf)
+template <typename K, bool IDENT>
+__device__ __forceinline__ unsigned pass_digit(K raw, int shift, const Transform &tf)
 {
-    typedef PassSmem<K, VB, THREADS, ITEMS> L;
+    if constexpr (IDENT) return (unsigned)(raw >> shift) & (kRadixSize - 1);  // unsigned ascending: no transform
+    else return digit_of<K>(raw, shift, tf);
+}
+
+template <typename K, int VB, int THREADS, int ITEMS, int LBATCH, int RANK, bool IDENT, bool FULL>
+__device__ __forceinline__ void
+pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *__restrict__ vals_in_v,
+          void *__restrict__ vals_out_v, const unsigned *__restrict__ digit_base, unsigned long long *lookback,
+          unsigned epoch, size_t n, int shift, const Transform &tf, size_t tile, unsigned char *smem_raw)
+{
+    typedef PassSmem<K, VB, THREADS, ITEMS, RANK> L;
     typedef typename value_type<VB>::type V;
     constexpr int WARPS = L::WARPS, TILE = L::TILE;
-    static_assert(THREADS >= kRadixSize && THREADS % 32 == 0, "one look-back thread per digit value");
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned(*warp_hist)[kRadixSize] = reinterpret_cast<unsigned(*)[kRadixSize]>(smem_raw);
-    unsigned *digit_start = reinterpret_cast<unsigned *>(smem_raw + L::kWarpHist);
-    unsigned *out_base = digit_start + kRadixSize;
-    unsigned *misc = out_base + kRadixSize;  // [0..1] tile id (u64), [2..9] warp sums of the digit scan
-    unsigned char *elem_buf = smem_raw + L::kWarpHist + L::kSmall;
+    unsigned *out_base = reinterpret_cast<unsigned *>(smem_raw + L::kWarpTab);
+    unsigned *misc = out_base + kRadixSize;  // [0..1] tile id, [2..9] warp sums of the digit scan
+    unsigned char *elem_buf = smem_raw + L::kWarpTab + L::kSmall;
     K *keys_sorted = reinterpret_cast<K *>(elem_buf);
+    // per-warp digit table: count (and peer mask) per digit value
+    uint2 *tab2 = reinterpret_cast<uint2 *>(smem_raw);        // kRankAtomicOr: [WARPS][256] {mask, count}
+    unsigned *tab1 = reinterpret_cast<unsigned *>(smem_raw);  // kRankOrderedAtoms: [WARPS][256] count
+    auto count_ref = [&](int w, unsigned d) -> unsigned & {
+        if constexpr (RANK == kRankAtomicOr) return tab2[w * kRadixSize + d].y;
+        else return tab1[w * kRadixSize + d];
+    };
 
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-
-    if (tid == 0) *reinterpret_cast<unsigned long long *>(misc) = atomicAdd(ticket, 1ull) - ticket_base;
-    // zero this warp's histogram row while the ticket is in flight
-#pragma unroll
-    for (int j = lane; j < kRadixSize; j += 32) warp_hist[warp][j] = 0;
-    __syncthreads();
-    const size_t tile = (size_t)*reinterpret_cast<unsigned long long *>(misc);
     const size_t tile_base = tile * (size_t)TILE;
-    const bool full = tile_base + TILE <= n;
-    const unsigned valid = full ? (unsigned)TILE : (unsigned)(n - tile_base);
+    const unsigned valid = FULL ? (unsigned)TILE : (unsigned)(n - tile_base);
     const unsigned warp_off = warp * (ITEMS * 32) + lane;  // in-tile index of this thread's item 0
 
     // ---- load keys, warp-striped: item i of lane l = tile_base + warp*ITEMS*32 + i*32 + l ----
     K key[ITEMS];
-    if (full) {
-#pragma unroll
-        for (int i = 0; i < ITEMS; i++) key[i] = keys_in[tile_base + warp_off + i * 32];
-    } else {
-#pragma unroll
-        for (int i = 0; i < ITEMS; i++) {
-            const unsigned t = warp_off + i * 32;
-            key[i] = t < valid ? keys_in[tile_base + t] : (K)0;
-        }
-    }
-
-    // ---- rank: warp-level multi-split against this warp's histogram row (stable: item-major, lane-minor) ----
-    unsigned short rank[ITEMS];
-    const unsigned lt_mask = lanemask_lt();
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
-        unsigned d = digit_of<K>(key[i], shift, tf);
-        if (!full && warp_off + i * 32 >= valid) d = kRadixSize - 1;  // padding sorts last within the tile
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
-        const int leader = __ffs(peers) - 1;
-        unsigned before = 0;
-        if ((int)lane == leader) {
-            before = warp_hist[warp][d];
-            warp_hist[warp][d] = before + __popc(peers);
+        const unsigned t = warp_off + i * 32;
+        if (FULL || t < valid) key[i] = __ldg(keys_in + tile_base + t);
+        else key[i] = (K)0;
+    }
+
+    // ---- rank inside the warp (stable: item-major, lane-minor == memory order) ----
+    unsigned short rank[ITEMS];
+    if constexpr (RANK == kRankAtomicOr) {
+        uint2 *wt = tab2 + warp * kRadixSize;
+        const unsigned lane_bit = 1u << lane;
+        const unsigned lt_mask = lane_bit - 1u;
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            unsigned d = pass_digit<K, IDENT>(key[i], shift, tf);
+            if (!FULL && warp_off + i * 32 >= valid) d = kRadixSize - 1;  // padding sorts last within the tile
+            atomicOr(&wt[d].x, lane_bit);
+            __syncwarp();
+            const uint2 mc = wt[d];  // {peer mask of this round, keys of digit d in earlier rounds}
+            const unsigned below = __popc(mc.x & lt_mask);
+            rank[i] = (unsigned short)(mc.y + below);
+            __syncwarp();
+            if ((mc.x >> lane) == 1u) wt[d] = make_uint2(0u, mc.y + below + 1u);  // highest peer: clear mask, bump count
+            __syncwarp();
         }
-        __syncwarp();
-        before = __shfl_sync(0xffffffffu, before, leader);
-        rank[i] = (unsigned short)(before + __popc(peers & lt_mask));
+    } else {
+        unsigned *wt = tab1 + warp * kRadixSize;
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            unsigned d = pass_digit<K, IDENT>(key[i], shift, tf);
+            if (!FULL && warp_off + i * 32 >= valid) d = kRadixSize - 1;
+            rank[i] = (unsigned short)atomicAdd(&wt[d], 1u);
+        }
     }
     __syncthreads();
 
-    // ---- per digit: exclusive prefix over warps (in place), tile count, then scan over the 256 digits ----
+    // ---- per digit: exclusive prefix over warps, tile count, exclusive scan over the 256 digit values ----
     unsigned count = 0;
     if (tid < kRadixSize) {
-        unsigned run = 0;
 #pragma unroll
-        for (int w = 0; w < WARPS; w++) {
-            const unsigned c = warp_hist[w][tid];
-            warp_hist[w][tid] = run;
-            run += c;
-        }
-        count = run;
+        for (int w = 0; w < WARPS; w++) count += count_ref(w, tid);
     }
     unsigned incl = count;
 #pragma unroll
@@ -250,55 +267,79 @@ onesweep_pass(const K *__restrict__ keys_in, K *__restrict__ keys_out, const voi
     unsigned my_start = 0;
     if (tid < kRadixSize) {
         unsigned add = 0;
-        for (unsigned w = 0; w < warp; w++) add += misc[2 + w];
+#pragma unroll
+        for (int w = 0; w < kRadixSize / 32; w++) add += (w < (int)warp) ? misc[2 + w] : 0u;
         my_start = incl - count + add;
-        digit_start[tid] = my_start;
-        if (!full && tid == kRadixSize - 1) count -= (unsigned)TILE - valid;  // drop the padding from the published count
-        // publish this tile's count for digit `tid`
+        // position of a key in the sorted tile = entry of (its warp, its digit) + its rank inside the warp
+        unsigned run = my_start;
+#pragma unroll
+        for (int w = 0; w < WARPS; w++) {
+            const unsigned c = count_ref(w, tid);
+            count_ref(w, tid) = run;
+            run += c;
+        }
+        if (!FULL && tid == kRadixSize - 1) count -= (unsigned)TILE - valid;  // drop the padding from the published count
         const unsigned status = (tile == 0) ? kLbInclusive : kLbPartial;
         st_relaxed_u64(lookback + tile * kRadixSize + tid, ((unsigned long long)((epoch << 2) | status) << 32) | count);
     }
     __syncthreads();
 
-    // ---- decoupled look-back (threads 0..255, one digit each); the other warps start reordering meanwhile ----
+    // ---- reorder the tile through shared memory ----
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) {
+        unsigned d = pass_digit<K, IDENT>(key[i], shift, tf);
+        if (!FULL && warp_off + i * 32 >= valid) d = kRadixSize - 1;
+        const unsigned pos = count_ref(warp, d) + rank[i];
+        rank[i] = (unsigned short)pos;
+        keys_sorted[pos] = key[i];
+    }
+
+    // ---- decoupled look-back (threads 0..255, one digit each).  The keys already sit in shared memory, so
+    // the key registers are dead here and the batched descriptor loads do not raise register pressure ----
     if (tid < kRadixSize) {
         unsigned excl = 0;
         if (tile > 0) {
-            size_t j = tile - 1;
-            while (true) {
-                const unsigned long long w = ld_relaxed_u64(lookback + j * kRadixSize + tid);
-                const unsigned tag = (unsigned)(w >> 32);
-                if ((tag >> 2) != epoch) continue;  // not published yet
-                excl += (unsigned)w;
-                if ((tag & 3u) == kLbInclusive) break;
-                --j;
+            constexpr int LB = LBATCH;  // independent descriptor loads in flight per step of the walk
+            long long j = (long long)tile - 1;
+            bool done = false;
+            while (!done) {
+                unsigned long long w[LB];
+#pragma unroll
+                for (int b = 0; b < LB; b++) {
+                    const long long idx = j - b;
+                    w[b] = idx >= 0 ? ld_relaxed_u64(lookback + (size_t)idx * kRadixSize + tid)
+                                    : ((unsigned long long)((epoch << 2) | kLbInclusive) << 32);
+                }
+                int consumed = 0;
+#pragma unroll
+                for (int b = 0; b < LB; b++) {
+                    if (!done && consumed == b) {
+                        const unsigned tag = (unsigned)(w[b] >> 32);
+                        if ((tag >> 2) == epoch) {  // published
+                            excl += (unsigned)w[b];
+                            consumed = b + 1;
+                            done = (tag & 3u) == kLbInclusive;
+                        }
+                    }
+                }
+                j -= consumed;
             }
             st_relaxed_u64(lookback + tile * kRadixSize + tid,
                            ((unsigned long long)((epoch << 2) | kLbInclusive) << 32) | (unsigned)(excl + count));
         }
-        out_base[tid] = digit_base[tid] + excl - my_start;  // global index = out_base[d] + position in the sorted tile
-    }
-
-    // ---- reorder the tile through shared memory ----
-#pragma unroll
-    for (int i = 0; i < ITEMS; i++) {
-        unsigned d = digit_of<K>(key[i], shift, tf);
-        if (!full && warp_off + i * 32 >= valid) d = kRadixSize - 1;
-        const unsigned pos = digit_start[d] + warp_hist[warp][d] + rank[i];
-        rank[i] = (unsigned short)pos;
-        keys_sorted[pos] = key[i];
+        out_base[tid] = __ldg(digit_base + tid) + excl - my_start;  // global index = out_base[d] + position in the sorted tile
     }
     __syncthreads();
 
     // ---- write keys: consecutive threads -> consecutive addresses inside each digit run ----
-    unsigned char dig[ITEMS];
+    unsigned char dig[VB > 0 ? ITEMS : 1];
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
         const unsigned p = i * THREADS + tid;
-        if (p < valid) {
+        if (FULL || p < valid) {
             const K k = keys_sorted[p];
-            const unsigned d = digit_of<K>(k, shift, tf);
-            dig[i] = (unsigned char)d;
+            const unsigned d = pass_digit<K, IDENT>(k, shift, tf);
+            if constexpr (VB > 0) dig[i] = (unsigned char)d;
             keys_out[(size_t)(out_base[d] + p)] = k;
         }
     }
@@ -311,21 +352,48 @@ onesweep_pass(const K *__restrict__ keys_in, K *__restrict__ keys_out, const voi
 #pragma unroll
         for (int i = 0; i < ITEMS; i++) {
             const unsigned t = warp_off + i * 32;
-            if (t < valid) val[i] = vals_in[tile_base + t];
+            if (FULL || t < valid) val[i] = vals_in[tile_base + t];
         }
         __syncthreads();  // everyone is done reading keys_sorted
 #pragma unroll
         for (int i = 0; i < ITEMS; i++) {
             const unsigned t = warp_off + i * 32;
-            if (t < valid) vals_sorted[rank[i]] = val[i];
+            if (FULL || t < valid) vals_sorted[rank[i]] = val[i];
         }
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < ITEMS; i++) {
             const unsigned p = i * THREADS + tid;
-            if (p < valid) vals_out[(size_t)(out_base[dig[i]] + p)] = vals_sorted[p];
+            if (FULL || p < valid) vals_out[(size_t)(out_base[dig[i]] + p)] = vals_sorted[p];
         }
     }
+}
+
+template <typename K, int VB, int THREADS, int ITEMS, int LBATCH, int RANK, bool IDENT>
+__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 3 : (THREADS <= 512 ? 2 : 1)))
+onesweep_pass(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *__restrict__ vals_in_v,
+              void *__restrict__ vals_out_v, const unsigned *__restrict__ digit_base, unsigned long long *lookback,
+              unsigned epoch, unsigned long long *ticket, unsigned long long ticket_base, size_t n, int shift, Transform tf)
+{
+    typedef PassSmem<K, VB, THREADS, ITEMS, RANK> L;
+    static_assert(THREADS >= kRadixSize && THREADS % 32 == 0, "one look-back thread per digit value");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned *misc = reinterpret_cast<unsigned *>(smem_raw + L::kWarpTab) + kRadixSize;
+
+    if (threadIdx.x == 0) *reinterpret_cast<unsigned long long *>(misc) = atomicAdd(ticket, 1ull) - ticket_base;
+    // zero the per-warp digit tables while the ticket is in flight
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(smem_raw);
+        for (unsigned i = threadIdx.x; i < L::kWarpTab / 16; i += THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    const size_t tile = (size_t)*reinterpret_cast<unsigned long long *>(misc);
+    if ((tile + 1) * (size_t)L::TILE <= n)
+        pass_tile<K, VB, THREADS, ITEMS, LBATCH, RANK, IDENT, true>(keys_in, keys_out, vals_in_v, vals_out_v, digit_base, lookback,
+                                                                     epoch, n, shift, tf, tile, smem_raw);
+    else
+        pass_tile<K, VB, THREADS, ITEMS, LBATCH, RANK, IDENT, false>(keys_in, keys_out, vals_in_v, vals_out_v, digit_base, lookback,
+                                                                      epoch, n, shift, tf, tile, smem_raw);
 }
 
 // ---- helpers for payloads whose size is not 1/2/4/8/16 bytes: sort (key, index), then gather ----
@@ -366,13 +434,13 @@ __global__ void insertion_sort_kernel(T *keys, size_t n, int greater, unsigned c
 }
 
 // ---- launch plumbing -----------------------------------------------------------------------------------
-template <typename K, int VB, int THREADS, int ITEMS>
-static int launch_pass(StreamState *st, const void *kin, void *kout, const void *vin, void *vout, const unsigned *base,
+template <typename K, int VB, int THREADS, int ITEMS, int LBATCH, int RANK, bool IDENT>
+static int launch_pass_impl(StreamState *st, const void *kin, void *kout, const void *vin, void *vout, const unsigned *base,
                        unsigned long long *lookback, size_t n, int shift, const Transform &tf)
 {
-    typedef PassSmem<K, VB, THREADS, ITEMS> L;
+    typedef PassSmem<K, VB, THREADS, ITEMS, RANK> L;
     static bool configured[64] = {};  // per instantiation and device: opt in to > 48 KB dynamic shared memory once
-    auto kernel = onesweep_pass<K, VB, THREADS, ITEMS>;
+    auto kernel = onesweep_pass<K, VB, THREADS, ITEMS, LBATCH, RANK, IDENT>;
     if (st->device >= 64 || !configured[st->device]) {
         BCB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kBytes));
         if (st->device < 64) configured[st->device] = true;
@@ -387,6 +455,31 @@ static int launch_pass(StreamState *st, const void *kin, void *kout, const void 
                                                                 st->control + kControlTicket, tbase, n, shift, tf);
     BCB_CUDA_TRY(cudaGetLastError());
     return BCB_SUCCESS;
+}
+
+static int g_rank_mode = -1;  // BCB_SORT_RANK=ordered selects the experimental ordered-atomics ranking (u32 keys only)
+static int rank_mode()
+{
+    if (g_rank_mode < 0) {
+        const char *e = std::getenv("BCB_SORT_RANK");
+        g_rank_mode = (e && std::strcmp(e, "ordered") == 0) ? kRankOrderedAtoms : kRankAtomicOr;
+    }
+    return g_rank_mode;
+}
+
+template <typename K, int VB, int THREADS, int ITEMS, int LBATCH = kLookbackBatch>
+static int launch_pass(StreamState *st, const void *kin, void *kout, const void *vin, void *vout, const unsigned *base,
+                       unsigned long long *lookback, size_t n, int shift, const Transform &tf)
+{
+    const bool ident = (tf.nm | tf.xc | tf.fa) == 0;  // unsigned ascending keys: the digit is a plain bit field
+    if constexpr (sizeof(K) == 4 && VB == 0) {
+        if (rank_mode() == kRankOrderedAtoms) {
+            return ident ? launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankOrderedAtoms, true>(st, kin, kout, vin, vout, base, lookback, n, shift, tf)
+                         : launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankOrderedAtoms, false>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
+        }
+    }
+    return ident ? launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankAtomicOr, true>(st, kin, kout, vin, vout, base, lookback, n, shift, tf)
+                 : launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankAtomicOr, false>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
 }
 
 // tile shapes: (key bytes, value bytes) -> THREADS x ITEMS
@@ -409,15 +502,17 @@ static int sort_variant()
     return g_sort_variant;
 }
 
+// BCB_SORT_VARIANT selects tuning variants of the u32 keys-only pass: {threads, items, look-back batch}
+#define BCB_U32_VARIANTS(X) X(1, 512, 16, 8) X(2, 512, 12, 8) X(3, 256, 24, 8) X(4, 384, 16, 8) X(5, 1024, 8, 8) X(6, 256, 16, 8)
+
 template <typename K, int VB>
 static int tile_size_for()
 {
     if constexpr (sizeof(K) == 4 && VB == 0) {
         switch (sort_variant()) {
-        case 1: return 512 * 16;
-        case 2: return 256 * 24;
-        case 3: return 512 * 12;
-        case 4: return 384 * 16;
+#define X(ID, T, I, LBV) case ID: return T * I;
+            BCB_U32_VARIANTS(X)
+#undef X
         default: break;
         }
     }
@@ -430,10 +525,9 @@ static int run_pass(StreamState *st, const void *kin, void *kout, const void *vi
 {
     if constexpr (sizeof(K) == 4 && VB == 0) {
         switch (sort_variant()) {
-        case 1: return launch_pass<K, VB, 512, 16>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
-        case 2: return launch_pass<K, VB, 256, 24>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
-        case 3: return launch_pass<K, VB, 512, 12>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
-        case 4: return launch_pass<K, VB, 384, 16>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
+#define X(ID, T, I, LBV) case ID: return launch_pass<K, VB, T, I, LBV>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
+            BCB_U32_VARIANTS(X)
+#undef X
         default: break;
         }
     }

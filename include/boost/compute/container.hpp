@@ -1,0 +1,4 @@
+#ifndef BOOST_COMPUTE_CONTAINER_HPP
+#define BOOST_COMPUTE_CONTAINER_HPP
+#include <boost/compute/container/vector.hpp>
+#endif

@@ -1,0 +1,380 @@
+// Exercises the header-only boost::compute layer (include/boost/compute) end to end on a CUDA device, the way the
+// reference's Boost.Test files use it: vectors from host ranges, algorithms on begin()/end() with a queue, results
+// checked against the reference's golden vectors (file:line cited per case) and against std:: algorithms.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <functional>
+#include <numeric>
+#include <random>
+#include <string>
+#include <vector>
+
+#include <boost/compute.hpp>
+
+namespace compute = boost::compute;
+
+static int g_failures = 0;
+static int g_checks = 0;
+
+#define CHECK(cond)                                                                     \
+    do {                                                                                \
+        ++g_checks;                                                                     \
+        if(!(cond)){                                                                    \
+            ++g_failures;                                                               \
+            std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond);               \
+        }                                                                               \
+    } while(0)
+
+template<class T>
+static std::vector<T> to_host(const compute::vector<T> &v, compute::command_queue &queue)
+{
+    std::vector<T> h(v.size());
+    compute::copy(v.begin(), v.end(), h.begin(), queue);
+    return h;
+}
+
+template<class T, size_t N>
+static bool equals(const std::vector<T> &got, const T (&expected)[N])
+{
+    return got.size() == N && std::equal(got.begin(), got.end(), expected);
+}
+
+static void test_core(compute::command_queue &queue)
+{
+    compute::device device = compute::system::default_device();
+    CHECK(compute::system::device_count() >= 1);
+    CHECK(!device.name().empty());
+    CHECK(device.type() & compute::device::gpu);
+    CHECK(device.compute_units() > 0);
+    CHECK(queue.get_device() == device);
+    CHECK(queue.get_context() == compute::system::default_context());
+    CHECK(compute::system::find_device(device.name()) == device);
+    bool threw = false;
+    try { compute::system::find_device("no such device"); } catch(compute::no_device_found &) { threw = true; }
+    CHECK(threw);
+    compute::opencl_error err(BCB_EINVAL);
+    CHECK(err.error_code() == BCB_EINVAL);
+    CHECK(std::string(err.what()).find("invalid") != std::string::npos);
+}
+
+static void test_vector(compute::command_queue &queue)
+{
+    // test_vector.cpp:42-167 style checks
+    compute::vector<int> v(compute::system::default_context());
+    CHECK(v.size() == 0 && v.empty());
+    v.push_back(1, queue);
+    v.push_back(3, queue);
+    v.push_back(5, queue);
+    v.push_back(7, queue);
+    v.push_back(9, queue);
+    CHECK(v.size() == 5);
+    CHECK(int(v[0]) == 1 && int(v[4]) == 9 && int(v.front()) == 1 && int(v.back()) == 9);
+    v.resize(3, queue);
+    CHECK(v.size() == 3 && int(v.back()) == 5);
+    v.resize(1000, queue);
+    CHECK(v.size() == 1000 && v.capacity() >= 1000 && int(v[2]) == 5);
+    v[2] = 42;
+    CHECK(int(v[2]) == 42);
+    compute::vector<float> f(size_t(10), 9.f, queue);
+    CHECK(float(f[0]) == 9.f && float(f[9]) == 9.f);
+    compute::fill(f.begin(), f.end(), 2.5f, queue);
+    CHECK(float(f[5]) == 2.5f);
+    compute::vector<int> io(8, compute::system::default_context());
+    compute::iota(io.begin(), io.end(), 3, queue);
+    const int expected_iota[] = {3, 4, 5, 6, 7, 8, 9, 10};
+    CHECK(equals(to_host(io, queue), expected_iota));
+    compute::vector<int> copy_of(io);
+    CHECK(equals(to_host(copy_of, queue), expected_iota));
+    compute::vector<int> dst(8, compute::system::default_context());
+    compute::copy(io.begin() + 2, io.end(), dst.begin(), queue);   // device -> device
+    CHECK(int(dst[0]) == 5 && int(dst[5]) == 10);
+    CHECK((io.begin() + 3).read(queue) == 6);
+    CHECK(io.end() - io.begin() == 8);
+}
+
+static void test_sort(compute::command_queue &queue)
+{
+    {   // test_sort.cpp:135-145
+        int data[] = {-4, 152, -5000, 963, 75321, -456, 0, 1112};
+        compute::vector<int> v(data, data + 8, queue);
+        CHECK(!compute::is_sorted(v.begin(), v.end(), queue));
+        compute::sort(v.begin(), v.end(), queue);
+        CHECK(compute::is_sorted(v.begin(), v.end(), queue));
+        const int expected[] = {-5000, -456, -4, 0, 152, 963, 1112, 75321};
+        CHECK(equals(to_host(v, queue), expected));
+        // test_sort.cpp:227-236
+        compute::copy(data, data + 8, v.begin(), queue);
+        compute::sort(v.begin(), v.end(), compute::greater<int>(), queue);
+        const int expected_desc[] = {75321, 1112, 963, 152, 0, -4, -456, -5000};
+        CHECK(equals(to_host(v, queue), expected_desc));
+        CHECK(compute::is_sorted(v.begin(), v.end(), compute::greater<int>(), queue));
+    }
+    {   // test_radix_sort.cpp:175-202 float keys incl. +-0
+        float data[] = {-6023.0f, 152.5f, -63.0f, 1234567.0f, 11.2f, -5000.1f, 0.0f, 14.0f, -8.25f, -0.0f};
+        compute::vector<float> v(data, data + 10, queue);
+        compute::detail::radix_sort(v.begin(), v.end(), queue);
+        const float expected[] = {-6023.0f, -5000.1f, -63.0f, -8.25f, -0.0f, 0.0f, 11.2f, 14.0f, 152.5f, 1234567.0f};
+        std::vector<float> got = to_host(v, queue);
+        CHECK(equals(got, expected));
+        CHECK(std::signbit(got[4]) && !std::signbit(got[5]));  // -0.0 before +0.0 under the radix transform
+    }
+    {   // test_radix_sort.cpp:530-541 sub-range
+        int data[] = {9, 8, 7, 6, 5, 4, 3, 2, 1, 0};
+        compute::vector<int> v(data, data + 10, queue);
+        compute::detail::radix_sort(v.begin() + 2, v.end() - 2, queue);
+        const int expected[] = {9, 8, 2, 3, 4, 5, 6, 7, 1, 0};
+        CHECK(equals(to_host(v, queue), expected));
+    }
+    {   // test_sort.cpp:286-292 host range
+        int data[] = {5, 2, 3, 6, 7, 4, 0, 1};
+        std::vector<int> host(data, data + 8);
+        compute::sort(host.begin(), host.end(), queue);
+        const int expected[] = {0, 1, 2, 3, 4, 5, 6, 7};
+        CHECK(equals(host, expected));
+    }
+    {   // large random sort vs std::sort, all key widths (perf_sort.cpp:84-130 style self-check)
+        std::mt19937_64 rng(12345);
+        const size_t n = 1000003;
+        std::vector<compute::uint_> a(n);
+        std::vector<compute::ulong_> b(n);
+        std::vector<compute::short_> c(n);
+        std::vector<double> d(n);
+        for(size_t i = 0; i < n; i++){
+            a[i] = compute::uint_(rng()); b[i] = rng(); c[i] = compute::short_(rng());
+            d[i] = (double(rng() >> 11) / 9007199254740992.0 - 0.5) * 1e5;
+        }
+        compute::vector<compute::uint_> da(a.begin(), a.end(), queue);
+        compute::vector<compute::ulong_> db(b.begin(), b.end(), queue);
+        compute::vector<compute::short_> dc(c.begin(), c.end(), queue);
+        compute::vector<double> dd(d.begin(), d.end(), queue);
+        compute::sort(da.begin(), da.end(), queue);
+        compute::sort(db.begin(), db.end(), compute::greater<compute::ulong_>(), queue);
+        compute::stable_sort(dc.begin(), dc.end(), queue);
+        compute::sort(dd.begin(), dd.end(), queue);
+        queue.finish();
+        std::sort(a.begin(), a.end());
+        std::sort(b.begin(), b.end(), std::greater<compute::ulong_>());
+        std::sort(c.begin(), c.end());
+        std::sort(d.begin(), d.end());
+        CHECK(to_host(da, queue) == a);
+        CHECK(to_host(db, queue) == b);
+        CHECK(to_host(dc, queue) == c);
+        CHECK(to_host(dd, queue) == d);
+    }
+}
+
+struct payload16 { int x; int y; float z; float w; };
+
+static void test_sort_by_key(compute::command_queue &queue)
+{
+    {   // test_radix_sort_by_key.cpp:30-61 stability
+        int keys_data[] = {10, 9, 2, 7, 6, -1, 4, 2, 2, 10};
+        int values_data[] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10};
+        compute::vector<int> keys(keys_data, keys_data + 10, queue);
+        compute::vector<int> values(values_data, values_data + 10, queue);
+        compute::detail::radix_sort_by_key(keys.begin(), keys.end(), values.begin(), queue);
+        const int ek[] = {-1, 2, 2, 2, 4, 6, 7, 9, 10, 10};
+        const int ev[] = {6, 3, 8, 9, 7, 5, 4, 2, 1, 10};
+        CHECK(equals(to_host(keys, queue), ek));
+        CHECK(equals(to_host(values, queue), ev));
+        // :63-100 descending
+        compute::copy(keys_data, keys_data + 10, keys.begin(), queue);
+        compute::copy(values_data, values_data + 10, values.begin(), queue);
+        compute::stable_sort_by_key(keys.begin(), keys.end(), values.begin(), compute::greater<int>(), queue);
+        const int dk[] = {10, 10, 9, 7, 6, 4, 2, 2, 2, -1};
+        const int dv[] = {1, 10, 2, 4, 5, 7, 3, 8, 9, 6};
+        CHECK(equals(to_host(keys, queue), dk));
+        CHECK(equals(to_host(values, queue), dv));
+    }
+    {   // test_sort_by_key.cpp:79-91 char payload (small-n insertion path)
+        int keys_data[] = {6, 2, 1, 3, 4, 7, 5, 0};
+        compute::char_ values_data[] = {'g', 'c', 'b', 'd', 'e', 'h', 'f', 'a'};
+        compute::vector<int> keys(keys_data, keys_data + 8, queue);
+        compute::vector<compute::char_> values(values_data, values_data + 8, queue);
+        compute::sort_by_key(keys.begin(), keys.end(), values.begin(), queue);
+        const compute::char_ ev[] = {'a', 'b', 'c', 'd', 'e', 'f', 'g', 'h'};
+        CHECK(equals(to_host(values, queue), ev));
+    }
+    {   // test_sort_by_key.cpp:175-205 16-byte struct payload, n = 1024 reversed keys
+        const int n = 1024;
+        std::vector<int> hk(n);
+        std::vector<payload16> hv(n);
+        for(int i = 0; i < n; i++){
+            hk[i] = n - i;
+            hv[i].x = n - i; hv[i].y = n - i; hv[i].z = hv[i].w = (n - i) / 0.5f;
+        }
+        compute::vector<int> keys(hk.begin(), hk.end(), queue);
+        compute::vector<payload16> values(n, compute::system::default_context());
+        compute::copy(&hv[0], &hv[0] + n, values.begin(), queue);
+        compute::sort_by_key(keys.begin(), keys.end(), values.begin(), queue);
+        std::vector<payload16> out(n);
+        compute::copy(values.begin(), values.end(), &out[0], queue);
+        bool ok = compute::is_sorted(keys.begin(), keys.end(), queue);
+        for(int i = 0; i < n; i++) ok = ok && out[i].x == i + 1 && out[i].w == (i + 1) / 0.5f;
+        CHECK(ok);
+    }
+    {   // perf_sort_by_key.cpp:39-46: int keys + 8-byte values, checked against a stable host sort
+        std::mt19937 rng(7);
+        const size_t n = 300007;
+        std::vector<int> hk(n);
+        std::vector<compute::long_> hv(n);
+        for(size_t i = 0; i < n; i++){ hk[i] = int(rng() % 1000) - 500; hv[i] = compute::long_(i); }
+        compute::vector<int> keys(hk.begin(), hk.end(), queue);
+        compute::vector<compute::long_> values(hv.begin(), hv.end(), queue);
+        compute::sort_by_key(keys.begin(), keys.end(), values.begin(), queue);
+        std::vector<size_t> order(n);
+        std::iota(order.begin(), order.end(), size_t(0));
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b){ return hk[a] < hk[b]; });
+        std::vector<compute::long_> got = to_host(values, queue);
+        bool ok = true;
+        for(size_t i = 0; i < n; i++) ok = ok && got[i] == compute::long_(order[i]);
+        CHECK(ok);
+    }
+}
+
+static void test_scan(compute::command_queue &queue)
+{
+    compute::context context = queue.get_context();
+    {   // test_scan.cpp:41-138
+        int data[] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11};
+        compute::vector<int> v(data, data + 12, queue);
+        compute::vector<int> r(12, context);
+        compute::vector<int>::iterator end = compute::inclusive_scan(v.begin(), v.end(), r.begin(), queue);
+        CHECK(end == r.end());
+        const int inc[] = {0, 1, 3, 6, 10, 15, 21, 28, 36, 45, 55, 66};
+        CHECK(equals(to_host(r, queue), inc));
+        compute::exclusive_scan(v.begin(), v.end(), r.begin(), queue);
+        const int exc[] = {0, 0, 1, 3, 6, 10, 15, 21, 28, 36, 45, 55};
+        CHECK(equals(to_host(r, queue), exc));
+        compute::exclusive_scan(v.begin(), v.end(), v.begin(), queue);  // in place
+        CHECK(equals(to_host(v, queue), exc));
+    }
+    {   // test_scan.cpp:360-390 multiplies with init
+        int data[] = {1, 2, 1, 2, 3};
+        compute::vector<int> v(data, data + 5, queue);
+        compute::vector<int> r(5, context);
+        compute::exclusive_scan(v.begin(), v.end(), r.begin(), int(10), compute::multiplies<int>(), queue);
+        const int e[] = {10, 10, 20, 20, 40};
+        CHECK(equals(to_host(r, queue), e));
+        compute::inclusive_scan(v.begin(), v.end(), r.begin(), compute::multiplies<int>(), queue);
+        const int i[] = {1, 2, 2, 4, 12};
+        CHECK(equals(to_host(r, queue), i));
+    }
+    {   // test_partial_sum.cpp:28-41
+        int data[] = {1, 2, 5, 3, 9, 1, 4, 2};
+        compute::vector<int> a(data, data + 8, queue);
+        compute::vector<int> b(8, context);
+        CHECK(compute::partial_sum(a.begin(), a.end(), b.begin(), queue) == b.end());
+        const int e[] = {1, 3, 8, 11, 20, 21, 25, 27};
+        CHECK(equals(to_host(b, queue), e));
+    }
+    {   // perf_exclusive_scan.cpp:54-94: ints in [0,25), checked against std::partial_sum
+        std::mt19937 rng(3);
+        const size_t n = 5000011;
+        std::vector<int> h(n);
+        for(size_t i = 0; i < n; i++) h[i] = int(rng() % 25);
+        compute::vector<int> v(h.begin(), h.end(), queue);
+        compute::vector<int> r(n, context);
+        compute::exclusive_scan(v.begin(), v.end(), r.begin(), queue);
+        std::vector<int> ref(n);
+        std::partial_sum(h.begin(), h.end() - 1, ref.begin() + 1);
+        ref[0] = 0;
+        CHECK(to_host(r, queue) == ref);
+    }
+}
+
+static void test_reduce_accumulate(compute::command_queue &queue)
+{
+    compute::context context = queue.get_context();
+    {   // test_reduce.cpp:29-40
+        int data[] = {1, 5, 9, 13, 17};
+        compute::vector<int> v(data, data + 5, queue);
+        int sum = 0, product = 0;
+        compute::reduce(v.begin(), v.end(), &sum, compute::plus<int>(), queue);
+        compute::reduce(v.begin(), v.end(), &product, compute::multiplies<int>(), queue);
+        CHECK(sum == 45 && product == 9945);
+        int mn = 0, mx = 0;
+        compute::reduce(v.begin(), v.end(), &mn, compute::min<int>(), queue);
+        compute::reduce(v.begin(), v.end(), &mx, compute::max<int>(), queue);
+        CHECK(mn == 1 && mx == 17);
+    }
+    {   // test_reduce.cpp:42-49 empty range leaves the result untouched
+        compute::vector<short> v(context);
+        short sum = 7;
+        compute::reduce(v.begin(), v.end(), &sum, queue);
+        CHECK(sum == 7);
+    }
+    {   // test_reduce.cpp:80-88 device result iterators
+        int data[] = {1, 2, 3, 4, 5, 6, 7, 8};
+        compute::vector<int> in(data, data + 8, queue);
+        compute::vector<int> res(2, context);
+        compute::reduce(in.begin(), in.begin() + 4, res.begin(), queue);
+        compute::reduce(in.begin() + 4, in.end(), res.end() - 1, queue);
+        const int e[] = {10, 26};
+        CHECK(equals(to_host(res, queue), e));
+    }
+    {   // test_reduce.cpp:269-277 uchar range accumulated in float
+        compute::vector<compute::uchar_> v(context);
+        v.push_back(250, queue);
+        v.push_back(250, queue);
+        float sum = 0;
+        compute::reduce(v.begin(), v.end(), &sum, compute::plus<float>(), queue);
+        CHECK(sum == 500.f);
+    }
+    {   // test_accumulate.cpp:25-85,150-206
+        int data[] = {2, 4, 6, 8};
+        compute::vector<int> v(data, data + 4, queue);
+        CHECK(compute::accumulate(v.begin(), v.end(), 0, queue) == 20);
+        CHECK(compute::accumulate(v.begin(), v.end(), -10, queue) == 10);
+        CHECK(compute::accumulate(v.begin(), v.end(), 2, compute::multiplies<int>(), queue) == 768);
+        int q[] = {2, 8, 16};
+        compute::vector<int> dq(q, q + 3, queue);
+        CHECK(compute::accumulate(dq.begin(), dq.end(), 1024, compute::divides<int>(), queue) == 4);
+        compute::vector<int> io(1025, context);
+        compute::iota(io.begin(), io.end(), 0, queue);
+        CHECK(compute::accumulate(io.begin(), io.end(), 2, queue) == 524802);
+        compute::vector<int> empty(context);
+        CHECK(compute::accumulate(empty.begin(), empty.end(), 4, queue) == 4);
+    }
+    {   // test_accumulate.cpp:258-300: int-typed init over float data == std::accumulate
+        std::vector<float> h(10000, 1.01f);
+        compute::vector<float> v(h.begin(), h.end(), queue);
+        CHECK(compute::accumulate(v.begin(), v.end(), 0, queue) == std::accumulate(h.begin(), h.end(), 0));
+    }
+    {   // perf_accumulate.cpp:27-45 + float reduce tolerance
+        std::mt19937 rng(5);
+        const size_t n = 4000037;
+        std::vector<int> h(n);
+        std::vector<float> f(n);
+        for(size_t i = 0; i < n; i++){ h[i] = int(rng() % 25); f[i] = float(rng() % 1000) / 1000.f; }
+        compute::vector<int> v(h.begin(), h.end(), queue);
+        CHECK(compute::accumulate(v.begin(), v.end(), 0, queue) == std::accumulate(h.begin(), h.end(), 0));
+        compute::vector<float> df(f.begin(), f.end(), queue);
+        float s = 0;
+        compute::reduce(df.begin(), df.end(), &s, queue);
+        double ref = std::accumulate(f.begin(), f.end(), 0.0);
+        CHECK(std::fabs(double(s) - ref) <= 4 * 22 * std::ldexp(1.0, -24) * ref);
+    }
+}
+
+int main()
+{
+    try {
+        compute::command_queue &queue = compute::system::default_queue();
+        std::printf("device: %s\n", queue.get_device().name().c_str());
+        test_core(queue);
+        test_vector(queue);
+        test_sort(queue);
+        test_sort_by_key(queue);
+        test_scan(queue);
+        test_reduce_accumulate(queue);
+        queue.finish();
+    } catch(std::exception &e) {
+        std::printf("EXCEPTION: %s\n", e.what());
+        return 2;
+    }
+    std::printf("%d checks, %d failures\n", g_checks, g_failures);
+    return g_failures ? 1 : 0;
+}
