@@ -75,6 +75,37 @@ __device__ __forceinline__ unsigned digit_of(K raw, int shift, const Transform &
     return (unsigned)(t >> shift) & (kRadixSize - 1);
 }
 
+// full transformed key (all digits), for comparisons in the common unsigned order
+template <typename K>
+__device__ __forceinline__ unsigned long long transformed_key(K raw, const Transform &tf)
+{
+    typedef typename key_traits<K>::U U;
+    typedef typename key_traits<K>::S S;
+    const U x = (U)raw;
+    const U nm = (U)tf.nm;
+    const U neg = (U)((S)x >> (sizeof(U) * 8 - 1));
+    const U t = ((x ^ nm) - nm) ^ (U)tf.xc ^ (neg & (U)tf.fa);
+    const unsigned long long ones = sizeof(K) == 8 ? ~0ull : ((1ull << (sizeof(K) * 8 % 64)) - 1);
+    return (unsigned long long)t & ones;
+}
+
+// one thread per splitter: lower bound of the splitter in a sorted range, compared in the transformed space
+template <typename K>
+__global__ void partition_points_kernel(const K *__restrict__ keys, size_t n, const unsigned long long *__restrict__ splitters,
+                                        unsigned num, unsigned long long *__restrict__ points, Transform tf)
+{
+    const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= num) return;
+    const unsigned long long s = splitters[j];
+    size_t lo = 0, hi = n;
+    while (lo < hi) {
+        const size_t mid = lo + (hi - lo) / 2;
+        if (transformed_key<K>(keys[mid], tf) < s) lo = mid + 1;
+        else hi = mid;
+    }
+    points[j] = lo;
+}
+
 // ---- 1. histogram of all digit positions in one read ------------------------------------------
 template <typename K>
 __global__ void __launch_bounds__(kHistThreads)
@@ -184,11 +215,32 @@ __device__ __forceinline__ unsigned pass_digit(K raw, int shift, const Transform
     else return digit_of<K>(raw, shift, tf);
 }
 
+// warp-striped tile load: item i of lane l of warp w = tile_base + w*ITEMS*32 + i*32 + l (128 B per warp instruction)
+template <typename K, int THREADS, int ITEMS>
+__device__ __forceinline__ void load_tile_keys(const K *__restrict__ keys_in, size_t n, size_t tile, K (&key)[ITEMS])
+{
+    constexpr int TILE = THREADS * ITEMS;
+    const size_t tile_base = tile * (size_t)TILE;
+    const unsigned warp_off = (threadIdx.x >> 5) * (ITEMS * 32) + (threadIdx.x & 31u);
+    if (tile_base + TILE <= n) {
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) key[i] = __ldg(keys_in + tile_base + warp_off + i * 32);
+    } else {
+        const unsigned valid = (unsigned)(n - tile_base);
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            const unsigned t = warp_off + i * 32;
+            key[i] = t < valid ? __ldg(keys_in + tile_base + t) : (K)0;
+        }
+    }
+}
+
 template <typename K, int VB, int THREADS, int ITEMS, int LBATCH, int RANK, bool IDENT, bool FULL>
 __device__ __forceinline__ void
 pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *__restrict__ vals_in_v,
           void *__restrict__ vals_out_v, const unsigned *__restrict__ digit_base, unsigned long long *lookback,
-          unsigned epoch, size_t n, int shift, const Transform &tf, size_t tile, unsigned char *smem_raw)
+          unsigned epoch, size_t n, int shift, const Transform &tf, size_t tile, unsigned char *smem_raw,
+          K (&key)[ITEMS], unsigned long long *ticket, unsigned long long ticket_base, size_t num_tiles)
 {
     typedef PassSmem<K, VB, THREADS, ITEMS, RANK> L;
     typedef typename value_type<VB>::type V;
@@ -211,14 +263,9 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
     const unsigned valid = FULL ? (unsigned)TILE : (unsigned)(n - tile_base);
     const unsigned warp_off = warp * (ITEMS * 32) + lane;  // in-tile index of this thread's item 0
 
-    // ---- load keys, warp-striped: item i of lane l = tile_base + warp*ITEMS*32 + i*32 + l ----
-    K key[ITEMS];
-#pragma unroll
-    for (int i = 0; i < ITEMS; i++) {
-        const unsigned t = warp_off + i * 32;
-        if (FULL || t < valid) key[i] = __ldg(keys_in + tile_base + t);
-        else key[i] = (K)0;
-    }
+    // key[] already holds this tile's keys (loaded by the caller / prefetched during the previous tile).
+    // Draw the NEXT tile id now; it is published through shared memory and used for the prefetch below.
+    if (tid == 0) *reinterpret_cast<unsigned long long *>(misc) = atomicAdd(ticket, 1ull) - ticket_base;
 
     // ---- rank inside the warp (stable: item-major, lane-minor == memory order) ----
     unsigned short rank[ITEMS];
@@ -292,6 +339,13 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
         const unsigned pos = count_ref(warp, d) + rank[i];
         rank[i] = (unsigned short)pos;
         keys_sorted[pos] = key[i];
+    }
+
+    // ---- prefetch the next tile's keys into the (now dead) key registers: the loads fly during the look-back and
+    // the store phase of this tile, so a tile never waits for its own input ----
+    {
+        const size_t next = (size_t)*reinterpret_cast<volatile unsigned long long *>(misc);  // written before 2 barriers
+        if (next < num_tiles) load_tile_keys<K, THREADS, ITEMS>(keys_in, n, next, key);
     }
 
     // ---- decoupled look-back (threads 0..255, one digit each).  The keys already sit in shared memory, so
@@ -369,31 +423,45 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
     }
 }
 
-template <typename K, int VB, int THREADS, int ITEMS, int LBATCH, int RANK, bool IDENT>
-__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 3 : (THREADS <= 512 ? 2 : 1)))
+template <typename K, int VB, int THREADS, int ITEMS, int LBATCH, int RANK, bool IDENT, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 onesweep_pass(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *__restrict__ vals_in_v,
               void *__restrict__ vals_out_v, const unsigned *__restrict__ digit_base, unsigned long long *lookback,
-              unsigned epoch, unsigned long long *ticket, unsigned long long ticket_base, size_t n, int shift, Transform tf)
+              unsigned epoch, unsigned long long *ticket, unsigned long long ticket_base, size_t n, size_t num_tiles, int shift,
+              Transform tf)
 {
+    // Persistent CTAs: the grid is sized to the number of resident CTAs; each CTA keeps drawing tile ids from the
+    // ticket until they run out.  Tile ids are therefore handed out in the order CTAs actually run, which is what
+    // makes the look-back deadlock free, and the next tile's id and keys are fetched while the current tile is
+    // still being processed.
     typedef PassSmem<K, VB, THREADS, ITEMS, RANK> L;
     static_assert(THREADS >= kRadixSize && THREADS % 32 == 0, "one look-back thread per digit value");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned *misc = reinterpret_cast<unsigned *>(smem_raw + L::kWarpTab) + kRadixSize;
 
     if (threadIdx.x == 0) *reinterpret_cast<unsigned long long *>(misc) = atomicAdd(ticket, 1ull) - ticket_base;
-    // zero the per-warp digit tables while the ticket is in flight
-    {
-        uint4 *z = reinterpret_cast<uint4 *>(smem_raw);
-        for (unsigned i = threadIdx.x; i < L::kWarpTab / 16; i += THREADS) z[i] = make_uint4(0, 0, 0, 0);
-    }
     __syncthreads();
-    const size_t tile = (size_t)*reinterpret_cast<unsigned long long *>(misc);
-    if ((tile + 1) * (size_t)L::TILE <= n)
-        pass_tile<K, VB, THREADS, ITEMS, LBATCH, RANK, IDENT, true>(keys_in, keys_out, vals_in_v, vals_out_v, digit_base, lookback,
-                                                                     epoch, n, shift, tf, tile, smem_raw);
-    else
-        pass_tile<K, VB, THREADS, ITEMS, LBATCH, RANK, IDENT, false>(keys_in, keys_out, vals_in_v, vals_out_v, digit_base, lookback,
-                                                                      epoch, n, shift, tf, tile, smem_raw);
+    size_t tile = (size_t)*reinterpret_cast<volatile unsigned long long *>(misc);
+    K key[ITEMS];
+    if (tile < num_tiles) load_tile_keys<K, THREADS, ITEMS>(keys_in, n, tile, key);
+    while (tile < num_tiles) {
+        // zero the per-warp digit tables (the previous tile left offsets in them)
+        {
+            uint4 *z = reinterpret_cast<uint4 *>(smem_raw);
+            for (unsigned i = threadIdx.x; i < L::kWarpTab / 16; i += THREADS) z[i] = make_uint4(0, 0, 0, 0);
+        }
+        __syncthreads();  // tables zeroed; everyone has read the current tile id
+        if ((tile + 1) * (size_t)L::TILE <= n)
+            pass_tile<K, VB, THREADS, ITEMS, LBATCH, RANK, IDENT, true>(keys_in, keys_out, vals_in_v, vals_out_v, digit_base, lookback,
+                                                                         epoch, n, shift, tf, tile, smem_raw, key, ticket, ticket_base,
+                                                                         num_tiles);
+        else
+            pass_tile<K, VB, THREADS, ITEMS, LBATCH, RANK, IDENT, false>(keys_in, keys_out, vals_in_v, vals_out_v, digit_base, lookback,
+                                                                          epoch, n, shift, tf, tile, smem_raw, key, ticket, ticket_base,
+                                                                          num_tiles);
+        tile = (size_t)*reinterpret_cast<volatile unsigned long long *>(misc);  // next tile id (its keys are already in flight)
+        __syncthreads();  // all stores of this tile issued, shared memory free for the next one
+    }
 }
 
 // ---- helpers for payloads whose size is not 1/2/4/8/16 bytes: sort (key, index), then gather ----
@@ -434,25 +502,36 @@ __global__ void insertion_sort_kernel(T *keys, size_t n, int greater, unsigned c
 }
 
 // ---- launch plumbing -----------------------------------------------------------------------------------
-template <typename K, int VB, int THREADS, int ITEMS, int LBATCH, int RANK, bool IDENT>
+constexpr int default_min_blocks(int threads) { return threads <= 256 ? 3 : (threads <= 512 ? 2 : 1); }
+
+template <typename K, int VB, int THREADS, int ITEMS, int LBATCH, int RANK, bool IDENT, int MINB = default_min_blocks(THREADS)>
 static int launch_pass_impl(StreamState *st, const void *kin, void *kout, const void *vin, void *vout, const unsigned *base,
                        unsigned long long *lookback, size_t n, int shift, const Transform &tf)
 {
     typedef PassSmem<K, VB, THREADS, ITEMS, RANK> L;
     static bool configured[64] = {};  // per instantiation and device: opt in to > 48 KB dynamic shared memory once
-    auto kernel = onesweep_pass<K, VB, THREADS, ITEMS, LBATCH, RANK, IDENT>;
+    auto kernel = onesweep_pass<K, VB, THREADS, ITEMS, LBATCH, RANK, IDENT, MINB>;
     if (st->device >= 64 || !configured[st->device]) {
         BCB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kBytes));
         if (st->device < 64) configured[st->device] = true;
     }
     const size_t tiles = (n + L::TILE - 1) / L::TILE;
+    static int resident[64] = {};  // CTAs of this kernel that fit one SM
+    int per_sm = (st->device < 64) ? resident[st->device] : 0;
+    if (per_sm == 0) {
+        BCB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, L::kBytes));
+        if (per_sm < 1) per_sm = 1;
+        if (st->device < 64) resident[st->device] = per_sm;
+    }
+    size_t grid = (size_t)st->sm_count * (size_t)per_sm;
+    if (grid > tiles) grid = tiles;
     unsigned epoch;
     BCB_TRY(next_epoch(st, &epoch));
     const unsigned long long tbase = st->ticket_base;
-    st->ticket_base += tiles;
+    st->ticket_base += tiles + grid;  // every CTA draws one id per tile it processes plus one that tells it to stop
     LaunchTimer timer(st, BCB_K_ONESWEEP_PASS);
-    kernel<<<(unsigned)tiles, THREADS, L::kBytes, st->stream>>>((const K *)kin, (K *)kout, vin, vout, base, lookback, epoch,
-                                                                st->control + kControlTicket, tbase, n, shift, tf);
+    kernel<<<(unsigned)grid, THREADS, L::kBytes, st->stream>>>((const K *)kin, (K *)kout, vin, vout, base, lookback, epoch,
+                                                               st->control + kControlTicket, tbase, n, tiles, shift, tf);
     BCB_CUDA_TRY(cudaGetLastError());
     return BCB_SUCCESS;
 }
@@ -467,19 +546,19 @@ static int rank_mode()
     return g_rank_mode;
 }
 
-template <typename K, int VB, int THREADS, int ITEMS, int LBATCH = kLookbackBatch>
+template <typename K, int VB, int THREADS, int ITEMS, int LBATCH = kLookbackBatch, int MINB = default_min_blocks(THREADS)>
 static int launch_pass(StreamState *st, const void *kin, void *kout, const void *vin, void *vout, const unsigned *base,
                        unsigned long long *lookback, size_t n, int shift, const Transform &tf)
 {
     const bool ident = (tf.nm | tf.xc | tf.fa) == 0;  // unsigned ascending keys: the digit is a plain bit field
     if constexpr (sizeof(K) == 4 && VB == 0) {
         if (rank_mode() == kRankOrderedAtoms) {
-            return ident ? launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankOrderedAtoms, true>(st, kin, kout, vin, vout, base, lookback, n, shift, tf)
-                         : launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankOrderedAtoms, false>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
+            return ident ? launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankOrderedAtoms, true, MINB>(st, kin, kout, vin, vout, base, lookback, n, shift, tf)
+                         : launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankOrderedAtoms, false, MINB>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
         }
     }
-    return ident ? launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankAtomicOr, true>(st, kin, kout, vin, vout, base, lookback, n, shift, tf)
-                 : launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankAtomicOr, false>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
+    return ident ? launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankAtomicOr, true, MINB>(st, kin, kout, vin, vout, base, lookback, n, shift, tf)
+                 : launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankAtomicOr, false, MINB>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
 }
 
 // tile shapes: (key bytes, value bytes) -> THREADS x ITEMS
@@ -503,14 +582,14 @@ static int sort_variant()
 }
 
 // BCB_SORT_VARIANT selects tuning variants of the u32 keys-only pass: {threads, items, look-back batch}
-#define BCB_U32_VARIANTS(X) X(1, 512, 16, 8) X(2, 512, 12, 8) X(3, 256, 24, 8) X(4, 384, 16, 8) X(5, 1024, 8, 8) X(6, 256, 16, 8)
+#define BCB_U32_VARIANTS(X) X(1, 512, 16, 8, 2) X(2, 384, 16, 8, 3) X(3, 256, 24, 8, 3) X(4, 384, 16, 8, 2) X(5, 256, 16, 8, 4) X(6, 256, 16, 8, 3) X(7, 512, 12, 8, 2) X(8, 256, 20, 8, 3)
 
 template <typename K, int VB>
 static int tile_size_for()
 {
     if constexpr (sizeof(K) == 4 && VB == 0) {
         switch (sort_variant()) {
-#define X(ID, T, I, LBV) case ID: return T * I;
+#define X(ID, T, I, LBV, MB) case ID: return T * I;
             BCB_U32_VARIANTS(X)
 #undef X
         default: break;
@@ -525,7 +604,7 @@ static int run_pass(StreamState *st, const void *kin, void *kout, const void *vi
 {
     if constexpr (sizeof(K) == 4 && VB == 0) {
         switch (sort_variant()) {
-#define X(ID, T, I, LBV) case ID: return launch_pass<K, VB, T, I, LBV>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
+#define X(ID, T, I, LBV, MB) case ID: return launch_pass<K, VB, T, I, LBV, MB>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
             BCB_U32_VARIANTS(X)
 #undef X
         default: break;
@@ -675,6 +754,38 @@ int bcb_insertion_sort(bcb_stream stream, int key_dtype, int greater, void *keys
     StreamState *st;
     BCB_TRY(stream_state((cudaStream_t)stream, &st));
     return insertion_sort_impl(st, key_dtype, greater, keys, n, values, value_bytes);
+}
+
+int bcb_partition_points(bcb_stream stream, int key_dtype, int ascending, const void *sorted_keys, size_t n,
+                         const unsigned long long *splitters_host, size_t num_splitters, unsigned long long *points_host)
+{
+    if (!dtype_size(key_dtype)) return BCB_EINVAL;
+    if (num_splitters == 0) return BCB_SUCCESS;
+    if (!splitters_host || !points_host || (n && !sorted_keys)) return BCB_EINVAL;
+    StreamState *st;
+    BCB_TRY(stream_state((cudaStream_t)stream, &st));
+    const Transform tf = make_transform(key_dtype, ascending != 0);
+    unsigned long long *dev;
+    BCB_CUDA_TRY(cudaMallocAsync((void **)&dev, 2 * num_splitters * sizeof(unsigned long long), st->stream));
+    int rc = BCB_SUCCESS;
+    cudaError_t e = cudaMemcpyAsync(dev, splitters_host, num_splitters * sizeof(unsigned long long), cudaMemcpyHostToDevice, st->stream);
+    if (e == cudaSuccess) {
+        const unsigned blocks = (unsigned)((num_splitters + 63) / 64);
+        switch (dtype_size(key_dtype)) {
+        case 1: partition_points_kernel<unsigned char><<<blocks, 64, 0, st->stream>>>((const unsigned char *)sorted_keys, n, dev, (unsigned)num_splitters, dev + num_splitters, tf); break;
+        case 2: partition_points_kernel<unsigned short><<<blocks, 64, 0, st->stream>>>((const unsigned short *)sorted_keys, n, dev, (unsigned)num_splitters, dev + num_splitters, tf); break;
+        case 4: partition_points_kernel<unsigned><<<blocks, 64, 0, st->stream>>>((const unsigned *)sorted_keys, n, dev, (unsigned)num_splitters, dev + num_splitters, tf); break;
+        default: partition_points_kernel<unsigned long long><<<blocks, 64, 0, st->stream>>>((const unsigned long long *)sorted_keys, n, dev, (unsigned)num_splitters, dev + num_splitters, tf); break;
+        }
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(points_host, dev + num_splitters, num_splitters * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st->stream);
+    if (e != cudaSuccess) rc = (int)e;
+    (void)cudaFreeAsync(dev, st->stream);
+    e = cudaStreamSynchronize(st->stream);
+    if (rc == BCB_SUCCESS && e != cudaSuccess) rc = (int)e;
+    if (rc != BCB_SUCCESS) (void)cudaGetLastError();
+    return rc;
 }
 
 int bcb_sort_host(bcb_stream stream, int key_dtype, int descending, void *host_keys, size_t n)

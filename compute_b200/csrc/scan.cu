@@ -239,7 +239,7 @@ scan_kernel(const T *in, T *out, size_t n, int exclusive, T init, TileState<T> t
     if (warp == 0) {
         T prefix;
         if (tile == 0) {
-            prefix = exclusive ? init : O::identity();
+            prefix = exclusive ? init : O::identity();  // modes 1 (exclusive) and 2 (seeded inclusive) start from init
             if (lane == 0) ts.post(0, epoch, kInclusive, exclusive ? O::apply(init, aggregate) : aggregate);
         } else {
             if (lane == 0) ts.post(tile, epoch, kPartial, aggregate);
@@ -257,7 +257,7 @@ scan_kernel(const T *in, T *out, size_t n, int exclusive, T init, TileState<T> t
     for (int j = 0; j < NV; j++) {
         const T p = O::apply(base, vexcl[j]);
         T y[VEC];
-        if (exclusive) {
+        if (exclusive == 1) {
             y[0] = p;
 #pragma unroll
             for (int k = 1; k < VEC; k++) y[k] = O::apply(p, x[j][k - 1]);

@@ -1,0 +1,283 @@
+"""Multi-GPU sort / scan / reduce: one process per GPU, ``torch.distributed`` (NCCL over NVLink / NVSwitch) for
+the exchange steps, the single-GPU CUDA kernels for all local work (SURVEY.md section 8e -- the reference itself has
+no multi-device path, so this is new functionality with the single-GPU results as its parity target).
+
+Data model: a range is block-distributed -- rank r holds the r-th contiguous block of the global range.
+
+* ``sort`` / ``sort_by_key`` (sample sort): local stable radix sort -> regular samples of the transformed keys ->
+  all-gather, common splitters -> partition points by binary search on the sorted shard -> all-to-all of contiguous
+  slices (keys, then values) -> local stable radix sort of the received runs (they arrive in source-rank order, so
+  equal keys keep their global input order).  The concatenation of the per-rank outputs in rank order is
+  bit-identical to the single-GPU sort.
+* scans: local reduce -> all-gather of P partials -> carry = init op partial_0 op ... op partial_(r-1), folded in
+  rank order -> local single-pass scan seeded with the carry.  Integer results are bit-exact; float results are
+  deterministic (fixed fold order).
+* ``reduce`` / ``accumulate``: local reduce -> all-gather of P partials -> fold in rank order.
+
+The local primitives are reached through a small ``LocalOps`` object so that the host-side protocol (sampling,
+splitters, exchange plan, carries) can be exercised on CPU with the gloo backend by the tests, which plug in the
+CPU oracle there.  The product only ever uses ``CudaLocalOps`` (C ABI -> sm_100a kernels); there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .core import NP_OF_CODE, dtype_code, op_code
+
+_BITS_VIEW = {1: torch.int8, 2: torch.int16, 4: torch.int32, 8: torch.int64}
+_NP_UINT = {1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# host-side protocol helpers (pure numpy; unit-tested on CPU)
+# ------------------------------------------------------------------------------------------------------------
+def transformed_keys(raw_bits: np.ndarray, dtype_c: int, ascending: bool) -> np.ndarray:
+    """The reference's order-preserving key transform (algorithm/detail/radix_sort.hpp:100-127) on raw key bit
+    patterns (unsigned ints of the key width); returns uint64 keys whose unsigned order is the sort order."""
+    w = raw_bits.dtype.itemsize * 8
+    x = raw_bits.astype(np.uint64)
+    ones = np.uint64((1 << w) - 1)
+    sign = np.uint64(1 << (w - 1))
+    is_float = dtype_c in (8, 9)
+    is_signed = dtype_c in (0, 2, 4, 6)
+    with np.errstate(over="ignore"):
+        if ascending:
+            if is_float:
+                mask = (((np.uint64(0) - (x >> np.uint64(w - 1))) & ones) | sign)
+                return (x ^ mask) & ones
+            if is_signed:
+                return (x ^ sign) & ones
+            return x
+        neg = (np.uint64(0) - x) & ones
+        if is_float:
+            mask = (((np.uint64(0) - (x >> np.uint64(w - 1))) & ones) | sign)
+            return (neg ^ mask) & ones
+        if is_signed:
+            return (neg ^ sign) & ones
+        return (ones - x) & ones
+
+
+def select_splitters(all_samples: np.ndarray, world: int) -> np.ndarray:
+    """P-1 splitters from the gathered, transformed samples (regular sampling: every rank contributes the same
+    number of evenly spaced samples of its sorted shard).  Returns uint64[world-1], non-decreasing."""
+    s = np.sort(all_samples.astype(np.uint64).reshape(-1))
+    if world <= 1 or s.size == 0:
+        return np.empty(0, dtype=np.uint64)
+    pos = (np.arange(1, world, dtype=np.int64) * s.size) // world
+    return s[np.minimum(pos, s.size - 1)]
+
+
+def exchange_plan(points: np.ndarray, n_local: int):
+    """Send counts per destination from the partition points of the sorted shard (points[j] = first index whose
+    transformed key is >= splitter j)."""
+    edges = np.concatenate([[0], np.asarray(points, dtype=np.int64), [n_local]])
+    return np.diff(edges).astype(np.int64)
+
+
+def fold_carry(partials: np.ndarray, rank: int, op: str, init=None):
+    """init op partial_0 op ... op partial_(rank-1) in rank order, in the partials' dtype (wrap-around integers)."""
+    dt = partials.dtype
+    fn = _NP_OPS[op]
+    acc = None if init is None else dt.type(init)
+    with np.errstate(over="ignore"):
+        for r in range(rank):
+            acc = partials[r] if acc is None else dt.type(fn(acc, partials[r]))
+    return acc
+
+
+_NP_OPS = {
+    "plus": lambda a, b: a + b, "multiplies": lambda a, b: a * b,
+    "min": lambda a, b: b if b < a else a, "max": lambda a, b: b if a < b else a,
+    "bit_and": lambda a, b: a & b, "bit_or": lambda a, b: a | b, "bit_xor": lambda a, b: a ^ b,
+}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# local primitives
+# ------------------------------------------------------------------------------------------------------------
+class CudaLocalOps:
+    """Local work on this rank's GPU through the C ABI (the only implementation the product ships)."""
+
+    device_type = "cuda"
+
+    def __init__(self):
+        from . import algorithm, core
+        from ._capi import check, lib
+        self._alg, self._check, self._lib = algorithm, check, lib()
+        self.queue = core.command_queue()
+
+    def sort(self, keys, values, descending):
+        if values is None:
+            self._alg.radix_sort(keys, not descending, self.queue)
+        else:
+            self._alg.radix_sort_by_key(keys, values, not descending, self.queue)
+
+    def partition_points(self, sorted_keys, splitters: np.ndarray, descending: bool) -> np.ndarray:
+        out = np.zeros(max(1, splitters.size), dtype=np.uint64)
+        sp = np.ascontiguousarray(splitters, dtype=np.uint64)
+        self._check(self._lib.bcb_partition_points(self.queue.handle, dtype_code(sorted_keys.dtype), int(not descending),
+                                                   sorted_keys.data_ptr(), sorted_keys.numel(), sp.ctypes.data, sp.size,
+                                                   out.ctypes.data))
+        return out[: splitters.size].astype(np.int64)
+
+    def gather_bits(self, keys, positions: np.ndarray) -> np.ndarray:
+        """Raw bit patterns of keys[positions] as unsigned ints on the host."""
+        w = keys.element_size()
+        idx = torch.from_numpy(positions.astype(np.int64)).to(keys.device)
+        picked = keys.view(_BITS_VIEW[w]).index_select(0, idx)
+        return picked.cpu().numpy().view(_NP_UINT[w])
+
+    def reduce_to(self, x, op, result_dtype):
+        """Local reduction as a 1-element tensor of result_dtype on this device."""
+        out = torch.empty(1, dtype=result_dtype, device=x.device)
+        self._alg.reduce(x, out, op, queue=self.queue)
+        return out
+
+    def scan(self, x, out, mode: int, init, op):
+        out_code = dtype_code(out.dtype)
+        init_arr = np.array([0 if init is None else init]).astype(NP_OF_CODE[out_code])
+        self._check(self._lib.bcb_scan(self.queue.handle, dtype_code(x.dtype), out_code, op_code(op), mode, x.data_ptr(),
+                                       out.data_ptr(), x.numel(), init_arr.ctypes.data))
+
+    def empty(self, n, like):
+        return torch.empty((n,) + tuple(like.shape[1:]), dtype=like.dtype, device=like.device)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the distributed algorithms
+# ------------------------------------------------------------------------------------------------------------
+class Context:
+    def __init__(self, group=None, local_ops=None, samples_per_rank: int = 1024):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.ops = local_ops if local_ops is not None else CudaLocalOps()
+        self.samples_per_rank = samples_per_rank
+        self.last_stats = {}
+
+    # -- helpers ----------------------------------------------------------------------------------------
+    def _all_gather_np(self, arr: np.ndarray) -> np.ndarray:
+        """all-gather a small host array (same shape on every rank) -> [world, ...]."""
+        if self.world == 1:
+            return arr[None]
+        dev = "cuda" if self.ops.device_type == "cuda" else "cpu"
+        t = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1).copy()).to(dev)
+        outs = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(outs, t, group=self.group)
+        return np.stack([o.cpu().numpy().view(arr.dtype).reshape(arr.shape) for o in outs])
+
+    def _all_to_all(self, src: torch.Tensor, send_counts: np.ndarray, recv_counts: np.ndarray) -> torch.Tensor:
+        """variable-size all-to-all of contiguous row slices (bitwise; rows may be wider than one element)."""
+        out = self.ops.empty(int(recv_counts.sum()), src)
+        if self.world == 1:
+            out.copy_(src)
+            return out
+        row = src.element_size() * (src.numel() // src.shape[0] if src.shape[0] else 1)
+        s8 = src.contiguous().view(torch.uint8).reshape(-1)
+        o8 = out.view(torch.uint8).reshape(-1)
+        dist.all_to_all_single(o8, s8, output_split_sizes=[int(c) * row for c in recv_counts],
+                               input_split_sizes=[int(c) * row for c in send_counts], group=self.group)
+        return out
+
+    # -- sort -------------------------------------------------------------------------------------------
+    def sort(self, keys: torch.Tensor, values: torch.Tensor | None = None, descending: bool = False):
+        """Globally sorts the block-distributed range.  ``keys`` (and ``values``) are this rank's shard and are used
+        as scratch; returns this rank's slice of the sorted range (sizes differ slightly between ranks)."""
+        P = self.world
+        n_local = keys.shape[0]
+        if P == 1:
+            self.ops.sort(keys, values, descending)
+            return keys if values is None else (keys, values)
+        code = dtype_code(keys.dtype)
+        # 1. local stable sort
+        self.ops.sort(keys, values, descending)
+        # 2. regular samples of the sorted shard, transformed to the common unsigned order
+        s = self.samples_per_rank
+        pos = (np.arange(s, dtype=np.int64) * max(n_local, 1)) // s if n_local else np.zeros(0, np.int64)
+        bits = self.ops.gather_bits(keys, pos) if n_local else np.zeros(0, _NP_UINT[keys.element_size()])
+        tk = transformed_keys(bits, code, not descending)
+        if tk.size < s:  # empty shard: pad with the maximum so it does not pull splitters down
+            tk = np.concatenate([tk, np.full(s - tk.size, np.iinfo(np.uint64).max, np.uint64)])
+        splitters = select_splitters(self._all_gather_np(tk), P)
+        # 3. partition points and the P x P count matrix
+        points = self.ops.partition_points(keys, splitters, descending) if n_local else np.zeros(P - 1, np.int64)
+        send = exchange_plan(points, n_local)
+        counts = self._all_gather_np(send)          # counts[src][dst]
+        recv = counts[:, self.rank].copy()
+        # 4. exchange: contiguous slices, received in source-rank order
+        out_keys = self._all_to_all(keys, send, recv)
+        out_vals = self._all_to_all(values, send, recv) if values is not None else None
+        # 5. final local stable sort of the P received runs
+        self.ops.sort(out_keys, out_vals, descending)
+        self.last_stats = {"sent": int(send.sum() - send[self.rank]), "received": int(recv.sum()),
+                           "imbalance": float(counts.sum(axis=0).max() * P / max(1, counts.sum()))}
+        return out_keys if values is None else (out_keys, out_vals)
+
+    # -- scan -------------------------------------------------------------------------------------------
+    def _scan(self, x, out, exclusive, init, op):
+        if self.world == 1:
+            self.ops.scan(x, out, 1 if exclusive else 0, init, op)
+            return out
+        part = self.ops.reduce_to(x, op, out.dtype) if x.numel() else None
+        np_dt = NP_OF_CODE[dtype_code(out.dtype)].type
+        w = np.dtype(np_dt).itemsize
+        local = (part.view(_BITS_VIEW[w]).cpu().numpy().view(np_dt) if part is not None else np.zeros(1, np_dt))
+        has = np.array([1 if x.numel() else 0], dtype=np.int32)
+        partials = self._all_gather_np(local).reshape(-1)
+        present = self._all_gather_np(has).reshape(-1)
+        carry = None if not exclusive else np_dt(0 if init is None else init)
+        fn = _NP_OPS[op]
+        with np.errstate(over="ignore"):
+            for r in range(self.rank):
+                if present[r]:
+                    carry = partials[r] if carry is None else np_dt(fn(carry, partials[r]))
+        if x.numel():
+            if carry is None:
+                self.ops.scan(x, out, 0, None, op)      # inclusive, nothing before this rank
+            else:
+                self.ops.scan(x, out, 1 if exclusive else 2, carry, op)  # 2 = inclusive scan seeded with a carry
+        return out
+
+    def exclusive_scan(self, x, out, init=0, op="plus"):
+        return self._scan(x, out, True, init, op)
+
+    def inclusive_scan(self, x, out, op="plus"):
+        return self._scan(x, out, False, None, op)
+
+    # -- reduce -----------------------------------------------------------------------------------------
+    def reduce(self, x, op="plus", result_dtype=None):
+        """Global reduction; every rank returns the same host scalar (None if the global range is empty)."""
+        rdt = result_dtype if result_dtype is not None else x.dtype
+        np_dt = NP_OF_CODE[dtype_code(rdt)].type
+        w = np.dtype(np_dt).itemsize
+        if x.numel():
+            part = self.ops.reduce_to(x, op, rdt)
+            local = part.view(_BITS_VIEW[w]).cpu().numpy().view(np_dt)
+        else:
+            local = np.zeros(1, np_dt)
+        if self.world == 1:
+            return local[0] if x.numel() else None
+        partials = self._all_gather_np(local).reshape(-1)
+        present = self._all_gather_np(np.array([1 if x.numel() else 0], dtype=np.int32)).reshape(-1)
+        acc = None
+        fn = _NP_OPS[op]
+        with np.errstate(over="ignore"):
+            for r in range(self.world):
+                if present[r]:
+                    acc = partials[r] if acc is None else np_dt(fn(acc, partials[r]))
+        return acc
+
+    def accumulate(self, x, init, op="plus"):
+        r = self.reduce(x, op)
+        np_dt = NP_OF_CODE[dtype_code(x.dtype)].type
+        if r is None:
+            return np_dt(init)
+        with np.errstate(over="ignore"):
+            return np_dt(_NP_OPS[op](np_dt(init), r))
+
+
+_ = ctypes

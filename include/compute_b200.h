@@ -114,11 +114,20 @@ BCB_API int bcb_insertion_sort(bcb_stream stream, int key_dtype, int greater, vo
  * device, applies the sort() dispatch of sort.hpp:34-81, copies back, and waits. */
 BCB_API int bcb_sort_host(bcb_stream stream, int key_dtype, int descending, void *host_keys, size_t n);
 
+/* Partition points of an already sorted range against splitters given in the transformed key space of
+ * radix_sort.hpp:100-127 (uint64, non-decreasing): points_host[j] = first index whose transformed key is
+ * >= splitters_host[j].  Used by the multi-GPU sample sort to cut a sorted shard into per-destination slices
+ * (new functionality: the reference has no multi-device path).  Blocks. */
+BCB_API int bcb_partition_points(bcb_stream stream, int key_dtype, int ascending, const void *sorted_keys, size_t n,
+                                 const unsigned long long *splitters_host, size_t num_splitters,
+                                 unsigned long long *points_host);
+
 /* ---- scan ---- */
 /* detail::scan (algorithm/detail/scan.hpp:22-39) with the operator-generic semantics of serial_scan.hpp:26-97:
  * inclusive: out[i] = x0 op ... op xi;  exclusive: out[i] = init op x0 op ... op x(i-1).  Arithmetic in out_dtype
  * (exclusive_scan.hpp:80-85).  in == out (in place) is allowed.  init_host points at one out_dtype value
- * (NULL = 0); it is ignored for inclusive scans. */
+ * (NULL = 0); it is ignored for inclusive scans.  exclusive == 2 is an inclusive scan seeded with init
+ * (out[i] = init op x0 op ... op xi), the per-rank step of the multi-GPU inclusive scan. */
 BCB_API int bcb_scan(bcb_stream stream, int in_dtype, int out_dtype, int op, int exclusive,
              const void *in, void *out, size_t n, const void *init_host);
 

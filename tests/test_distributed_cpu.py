@@ -1,0 +1,170 @@
+"""Host-side protocol of the multi-GPU path (compute_b200/distributed.py) on CPU: unit tests of the numpy helpers
+and a world_size-2 gloo run in which the local GPU primitives are replaced by the CPU oracle (test infrastructure
+only -- the product ships CudaLocalOps alone).  The distributed result must equal the single-device oracle result
+bit for bit (sorts, integer scans / reductions)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from compute_b200 import distributed as cbd
+from compute_b200.core import dtype_code
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_transformed_keys_match_oracle():
+    rng = np.random.default_rng(1)
+    for name in oracle.DTYPES:
+        npdt = np.dtype(oracle.NP_DTYPES[name])
+        w = npdt.itemsize
+        bits = rng.integers(0, 256, size=200 * w, dtype=np.uint8).view({1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[w])
+        for asc in (True, False):
+            got = cbd.transformed_keys(bits, dtype_code(npdt), asc)
+            exp = np.array([oracle.radix_key(name, asc, int(b)) for b in bits], dtype=np.uint64)
+            np.testing.assert_array_equal(got, exp, err_msg=f"{name} asc={asc}")
+
+
+def test_splitters_and_plan():
+    s = np.arange(4000, dtype=np.uint64)[::-1].copy()
+    sp = cbd.select_splitters(s, 4)
+    np.testing.assert_array_equal(sp, [1000, 2000, 3000])
+    assert cbd.select_splitters(s, 1).size == 0
+    np.testing.assert_array_equal(cbd.exchange_plan(np.array([3, 3, 10]), 12), [3, 0, 7, 2])
+    p = np.array([5, 7, 250], dtype=np.uint8)
+    assert cbd.fold_carry(p, 3, "plus", 10) == np.uint8((10 + 5 + 7 + 250) % 256)
+    assert cbd.fold_carry(p, 0, "plus", None) is None
+    assert cbd.fold_carry(p, 2, "max", None) == 7
+
+
+class OracleLocalOps:
+    """CPU stand-in for CudaLocalOps used ONLY by this test: same interface, oracle semantics, CPU tensors."""
+    device_type = "cpu"
+    _T = {torch.int8: np.int8, torch.uint8: np.uint8, torch.int16: np.int16, torch.int32: np.int32, torch.int64: np.int64,
+          torch.float32: np.float32, torch.float64: np.float64}
+
+    def _np(self, t):
+        return t.numpy()
+
+    def sort(self, keys, values, descending):
+        k = self._np(keys)
+        if values is None:
+            k[:] = oracle.radix_sort(k, descending)
+        else:
+            v = self._np(values)
+            sk, sv = oracle.radix_sort(k, descending, v)
+            k[:] = sk
+            v[:] = sv
+
+    def partition_points(self, sorted_keys, splitters, descending):
+        k = self._np(sorted_keys)
+        w = k.dtype.itemsize
+        bits = k.view({1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[w])
+        tk = cbd.transformed_keys(bits, dtype_code(k.dtype), not descending)
+        return np.searchsorted(tk, splitters, side="left").astype(np.int64)
+
+    def gather_bits(self, keys, positions):
+        k = self._np(keys)
+        return k.view({1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[k.dtype.itemsize])[positions]
+
+    def reduce_to(self, x, op, result_dtype):
+        r = oracle.reduce(self._np(x), op, self._T[result_dtype])
+        return torch.from_numpy(np.array([r], dtype=self._T[result_dtype]))
+
+    def scan(self, x, out, mode, init, op):
+        xs = self._np(x)
+        o = self._np(out)
+        if mode == 1:
+            o[:] = oracle.scan(xs, op, True, init, out_dtype=o.dtype)
+        elif mode == 0:
+            o[:] = oracle.scan(xs, op, False, 0, out_dtype=o.dtype)
+        else:  # inclusive seeded with a carry == exclusive scan of x with init, shifted by one, plus the last element
+            ex = oracle.scan(xs, op, True, init, out_dtype=o.dtype)
+            o[:-1] = ex[1:]
+            o[-1:] = oracle.scan(np.concatenate([ex[-1:], xs[-1:].astype(o.dtype)]), op, False, 0)[-1:]
+
+    def empty(self, n, like):
+        return torch.empty((n,) + tuple(like.shape[1:]), dtype=like.dtype)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, results):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ctx = cbd.Context(local_ops=OracleLocalOps(), samples_per_rank=64)
+        rng = np.random.default_rng(42)
+        out = {}
+        # --- sort: keys only (float with duplicates, descending) and by key (int keys, 8-byte payload rows) ---
+        n_total = 20_000
+        allk = rng.integers(-50, 50, size=n_total).astype(np.float32)
+        allk[::97] = -0.0
+        lo, hi = rank * n_total // world, (rank + 1) * n_total // world
+        shard = torch.from_numpy(allk[lo:hi].copy())
+        out["sort_f32_desc"] = ctx.sort(shard, None, descending=True).numpy().copy()
+        keys = rng.integers(-1000, 1000, size=n_total).astype(np.int32)
+        vals = np.stack([np.arange(n_total, dtype=np.int32), -np.arange(n_total, dtype=np.int32)], axis=1)
+        k, v = ctx.sort(torch.from_numpy(keys[lo:hi].copy()), torch.from_numpy(vals[lo:hi].copy()))
+        out["pairs_k"], out["pairs_v"] = k.numpy().copy(), v.numpy().copy()
+        out["stats"] = dict(ctx.last_stats)
+        # --- scans and reductions on unequal blocks (rank 0 gets 1/3) ---
+        x = rng.integers(-2**31, 2**31 - 1, size=9001).astype(np.int32)
+        cut = 3000
+        mine = torch.from_numpy((x[:cut] if rank == 0 else x[cut:]).copy())
+        o = torch.empty_like(mine)
+        ctx.exclusive_scan(mine, o, 11)
+        out["excl"] = o.numpy().copy()
+        ctx.inclusive_scan(mine, o, "plus")
+        out["incl"] = o.numpy().copy()
+        ctx.inclusive_scan(mine, o, "max")
+        out["incl_max"] = o.numpy().copy()
+        out["sum"] = ctx.reduce(mine)
+        out["min"] = ctx.reduce(mine, "min")
+        out["acc"] = ctx.accumulate(mine, 5)
+        results[rank] = out
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_gloo_matches_single_device_oracle():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker, args=(world, port, results), nprocs=world, join=True)
+    res = [results[r] for r in range(world)]
+    rng = np.random.default_rng(42)
+    n_total = 20_000
+    allk = rng.integers(-50, 50, size=n_total).astype(np.float32)
+    allk[::97] = -0.0
+    got = np.concatenate([r["sort_f32_desc"] for r in res])
+    assert got.tobytes() == oracle.radix_sort(allk, True).tobytes()
+    keys = rng.integers(-1000, 1000, size=n_total).astype(np.int32)
+    vals = np.stack([np.arange(n_total, dtype=np.int32), -np.arange(n_total, dtype=np.int32)], axis=1)
+    ek, ev = oracle.radix_sort(keys, False, vals)
+    assert np.concatenate([r["pairs_k"] for r in res]).tobytes() == ek.tobytes()
+    assert np.concatenate([r["pairs_v"] for r in res]).tobytes() == ev.tobytes()
+    assert res[0]["stats"]["imbalance"] < 1.5
+    x = rng.integers(-2**31, 2**31 - 1, size=9001).astype(np.int32)
+    np.testing.assert_array_equal(np.concatenate([r["excl"] for r in res]), oracle.scan(x, "plus", True, 11))
+    np.testing.assert_array_equal(np.concatenate([r["incl"] for r in res]), oracle.scan(x, "plus", False, 0))
+    np.testing.assert_array_equal(np.concatenate([r["incl_max"] for r in res]), oracle.scan(x, "max", False, 0))
+    for r in res:
+        assert r["sum"] == oracle.reduce(x, "plus")
+        assert r["min"] == oracle.reduce(x, "min")
+        assert r["acc"] == oracle.accumulate(x, np.int32(5), "plus")
