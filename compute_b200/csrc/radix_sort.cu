@@ -200,10 +200,10 @@ template <> struct value_type<16> { typedef uint4 type; };
 template <typename K, int VB, int THREADS, int ITEMS, int RANK>
 struct PassSmem {
     static constexpr int WARPS = THREADS / 32;
+    static constexpr int VWARPS = THREADS / 16;  // 16-lane "virtual warps": one digit table and one key segment each
     static constexpr int TILE = THREADS * ITEMS;
-    static constexpr size_t kEntry = (RANK == kRankAtomicOr) ? 8 : 4;   // {mask, count} or count
     static constexpr size_t kElem = (sizeof(K) > (size_t)VB) ? sizeof(K) : (size_t)VB;
-    static constexpr size_t kWarpTab = (size_t)WARPS * kRadixSize * kEntry;
+    static constexpr size_t kWarpTab = (size_t)VWARPS * kRadixSize * sizeof(unsigned);
     static constexpr size_t kSmall = kRadixSize * sizeof(unsigned) + 64;  // out_base + misc
     static constexpr size_t kBytes = kWarpTab + kSmall + (size_t)TILE * kElem + 16;
 };
@@ -215,21 +215,28 @@ __device__ __forceinline__ unsigned pass_digit(K raw, int shift, const Transform
     else return digit_of<K>(raw, shift, tf);
 }
 
-// warp-striped tile load: item i of lane l of warp w = tile_base + w*ITEMS*32 + i*32 + l (128 B per warp instruction)
+// Tile layout: 16-lane virtual warp v = tid/16 owns the contiguous segment [v*ITEMS*16, (v+1)*ITEMS*16) of the tile;
+// its lane h holds items i*16 + h.  One warp instruction therefore reads two 64-byte pieces (full 32-byte sectors).
+template <int ITEMS>
+__device__ __forceinline__ unsigned tile_offset_of_item0()
+{
+    return (threadIdx.x >> 4) * (ITEMS * 16) + (threadIdx.x & 15u);
+}
+
 template <typename K, int THREADS, int ITEMS>
 __device__ __forceinline__ void load_tile_keys(const K *__restrict__ keys_in, size_t n, size_t tile, K (&key)[ITEMS])
 {
     constexpr int TILE = THREADS * ITEMS;
     const size_t tile_base = tile * (size_t)TILE;
-    const unsigned warp_off = (threadIdx.x >> 5) * (ITEMS * 32) + (threadIdx.x & 31u);
+    const unsigned off0 = tile_offset_of_item0<ITEMS>();
     if (tile_base + TILE <= n) {
 #pragma unroll
-        for (int i = 0; i < ITEMS; i++) key[i] = __ldg(keys_in + tile_base + warp_off + i * 32);
+        for (int i = 0; i < ITEMS; i++) key[i] = __ldg(keys_in + tile_base + off0 + i * 16);
     } else {
         const unsigned valid = (unsigned)(n - tile_base);
 #pragma unroll
         for (int i = 0; i < ITEMS; i++) {
-            const unsigned t = warp_off + i * 32;
+            const unsigned t = off0 + i * 16;
             key[i] = t < valid ? __ldg(keys_in + tile_base + t) : (K)0;
         }
     }
@@ -250,48 +257,43 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
     unsigned *misc = out_base + kRadixSize;  // [0..1] tile id, [2..9] warp sums of the digit scan
     unsigned char *elem_buf = smem_raw + L::kWarpTab + L::kSmall;
     K *keys_sorted = reinterpret_cast<K *>(elem_buf);
-    // per-warp digit table: count (and peer mask) per digit value
-    uint2 *tab2 = reinterpret_cast<uint2 *>(smem_raw);        // kRankAtomicOr: [WARPS][256] {mask, count}
-    unsigned *tab1 = reinterpret_cast<unsigned *>(smem_raw);  // kRankOrderedAtoms: [WARPS][256] count
-    auto count_ref = [&](int w, unsigned d) -> unsigned & {
-        if constexpr (RANK == kRankAtomicOr) return tab2[w * kRadixSize + d].y;
-        else return tab1[w * kRadixSize + d];
-    };
-
-    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    // digit table of each 16-lane virtual warp.  kRankAtomicOr packs {count : 16 | peer mask : 16} into one word
+    // (a 32-bit entry keeps every access a single-wavefront-per-bank operation); kRankOrderedAtoms stores the count.
+    unsigned *tab = reinterpret_cast<unsigned *>(smem_raw);  // [VWARPS][256]
+    constexpr int CSHIFT = (RANK == kRankAtomicOr) ? 16 : 0;
+    constexpr int VWARPS = L::VWARPS;
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, vwarp = tid >> 4;
     const size_t tile_base = tile * (size_t)TILE;
     const unsigned valid = FULL ? (unsigned)TILE : (unsigned)(n - tile_base);
-    const unsigned warp_off = warp * (ITEMS * 32) + lane;  // in-tile index of this thread's item 0
+    const unsigned off0 = tile_offset_of_item0<ITEMS>();  // in-tile index of this thread's item 0; item i is off0 + 16*i
+    unsigned *wt = tab + vwarp * kRadixSize;
 
     // key[] already holds this tile's keys (loaded by the caller / prefetched during the previous tile).
-    // Draw the NEXT tile id now; it is published through shared memory and used for the prefetch below.
-    if (tid == 0) *reinterpret_cast<unsigned long long *>(misc) = atomicAdd(ticket, 1ull) - ticket_base;
+    (void)ticket; (void)ticket_base;
 
     // ---- rank inside the warp (stable: item-major, lane-minor == memory order) ----
     unsigned short rank[ITEMS];
     if constexpr (RANK == kRankAtomicOr) {
-        uint2 *wt = tab2 + warp * kRadixSize;
-        const unsigned lane_bit = 1u << lane;
-        const unsigned lt_mask = lane_bit - 1u;
+        const unsigned hbit = 1u << (lane & 15u);
+        const unsigned hlt = hbit - 1u;
 #pragma unroll
         for (int i = 0; i < ITEMS; i++) {
             unsigned d = pass_digit<K, IDENT>(key[i], shift, tf);
-            if (!FULL && warp_off + i * 32 >= valid) d = kRadixSize - 1;  // padding sorts last within the tile
-            atomicOr(&wt[d].x, lane_bit);
+            if (!FULL && off0 + i * 16 >= valid) d = kRadixSize - 1;  // padding sorts last within the tile
+            atomicOr(&wt[d], hbit);
             __syncwarp();
-            const uint2 mc = wt[d];  // {peer mask of this round, keys of digit d in earlier rounds}
-            const unsigned below = __popc(mc.x & lt_mask);
-            rank[i] = (unsigned short)(mc.y + below);
+            const unsigned e = wt[d];  // {keys of digit d in earlier rounds : 16 | peers in this round : 16}
+            const unsigned below = __popc(e & hlt);
+            rank[i] = (unsigned short)((e >> 16) + below);
             __syncwarp();
-            if ((mc.x >> lane) == 1u) wt[d] = make_uint2(0u, mc.y + below + 1u);  // highest peer: clear mask, bump count
+            if (((e & 0xffffu) >> (lane & 15u)) == 1u) wt[d] = (e & 0xffff0000u) + ((below + 1u) << 16);  // highest peer
             __syncwarp();
         }
     } else {
-        unsigned *wt = tab1 + warp * kRadixSize;
 #pragma unroll
         for (int i = 0; i < ITEMS; i++) {
             unsigned d = pass_digit<K, IDENT>(key[i], shift, tf);
-            if (!FULL && warp_off + i * 32 >= valid) d = kRadixSize - 1;
+            if (!FULL && off0 + i * 16 >= valid) d = kRadixSize - 1;
             rank[i] = (unsigned short)atomicAdd(&wt[d], 1u);
         }
     }
@@ -301,7 +303,7 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
     unsigned count = 0;
     if (tid < kRadixSize) {
 #pragma unroll
-        for (int w = 0; w < WARPS; w++) count += count_ref(w, tid);
+        for (int v = 0; v < VWARPS; v++) count += tab[v * kRadixSize + tid] >> CSHIFT;
     }
     unsigned incl = count;
 #pragma unroll
@@ -320,9 +322,9 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
         // position of a key in the sorted tile = entry of (its warp, its digit) + its rank inside the warp
         unsigned run = my_start;
 #pragma unroll
-        for (int w = 0; w < WARPS; w++) {
-            const unsigned c = count_ref(w, tid);
-            count_ref(w, tid) = run;
+        for (int v = 0; v < VWARPS; v++) {
+            const unsigned c = tab[v * kRadixSize + tid] >> CSHIFT;
+            tab[v * kRadixSize + tid] = run << CSHIFT;
             run += c;
         }
         if (!FULL && tid == kRadixSize - 1) count -= (unsigned)TILE - valid;  // drop the padding from the published count
@@ -335,8 +337,8 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
         unsigned d = pass_digit<K, IDENT>(key[i], shift, tf);
-        if (!FULL && warp_off + i * 32 >= valid) d = kRadixSize - 1;
-        const unsigned pos = count_ref(warp, d) + rank[i];
+        if (!FULL && off0 + i * 16 >= valid) d = kRadixSize - 1;
+        const unsigned pos = (wt[d] >> CSHIFT) + rank[i];
         rank[i] = (unsigned short)pos;
         keys_sorted[pos] = key[i];
     }
@@ -344,7 +346,7 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
     // ---- prefetch the next tile's keys into the (now dead) key registers: the loads fly during the look-back and
     // the store phase of this tile, so a tile never waits for its own input ----
     {
-        const size_t next = (size_t)*reinterpret_cast<volatile unsigned long long *>(misc);  // written before 2 barriers
+        const size_t next = tile + gridDim.x;  // round-robin tile assignment (see onesweep_pass)
         if (next < num_tiles) load_tile_keys<K, THREADS, ITEMS>(keys_in, n, next, key);
     }
 
@@ -405,13 +407,13 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
         V val[ITEMS];
 #pragma unroll
         for (int i = 0; i < ITEMS; i++) {
-            const unsigned t = warp_off + i * 32;
+            const unsigned t = off0 + i * 16;
             if (FULL || t < valid) val[i] = vals_in[tile_base + t];
         }
         __syncthreads();  // everyone is done reading keys_sorted
 #pragma unroll
         for (int i = 0; i < ITEMS; i++) {
-            const unsigned t = warp_off + i * 32;
+            const unsigned t = off0 + i * 16;
             if (FULL || t < valid) vals_sorted[rank[i]] = val[i];
         }
         __syncthreads();
@@ -430,27 +432,24 @@ onesweep_pass(const K *__restrict__ keys_in, K *__restrict__ keys_out, const voi
               unsigned epoch, unsigned long long *ticket, unsigned long long ticket_base, size_t n, size_t num_tiles, int shift,
               Transform tf)
 {
-    // Persistent CTAs: the grid is sized to the number of resident CTAs; each CTA keeps drawing tile ids from the
-    // ticket until they run out.  Tile ids are therefore handed out in the order CTAs actually run, which is what
-    // makes the look-back deadlock free, and the next tile's id and keys are fetched while the current tile is
-    // still being processed.
+    // Persistent CTAs: the grid is sized to the number of resident CTAs and tiles are dealt round-robin (CTA b takes
+    // tiles b, b + G, b + 2G ...).  All CTAs are co-resident, so every tile a look-back can wait for is being worked
+    // on, the tiles in flight form one contiguous window of the input (their scattered writes merge in L2), and the
+    // next tile's keys are fetched while the current tile is still being processed.
     typedef PassSmem<K, VB, THREADS, ITEMS, RANK> L;
     static_assert(THREADS >= kRadixSize && THREADS % 32 == 0, "one look-back thread per digit value");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned *misc = reinterpret_cast<unsigned *>(smem_raw + L::kWarpTab) + kRadixSize;
 
-    if (threadIdx.x == 0) *reinterpret_cast<unsigned long long *>(misc) = atomicAdd(ticket, 1ull) - ticket_base;
-    __syncthreads();
-    size_t tile = (size_t)*reinterpret_cast<volatile unsigned long long *>(misc);
+    size_t tile = blockIdx.x;
     K key[ITEMS];
     if (tile < num_tiles) load_tile_keys<K, THREADS, ITEMS>(keys_in, n, tile, key);
-    while (tile < num_tiles) {
-        // zero the per-warp digit tables (the previous tile left offsets in them)
+    for (; tile < num_tiles; tile += gridDim.x) {
+        // zero the digit tables (the previous tile left offsets in them)
         {
             uint4 *z = reinterpret_cast<uint4 *>(smem_raw);
             for (unsigned i = threadIdx.x; i < L::kWarpTab / 16; i += THREADS) z[i] = make_uint4(0, 0, 0, 0);
         }
-        __syncthreads();  // tables zeroed; everyone has read the current tile id
+        __syncthreads();
         if ((tile + 1) * (size_t)L::TILE <= n)
             pass_tile<K, VB, THREADS, ITEMS, LBATCH, RANK, IDENT, true>(keys_in, keys_out, vals_in_v, vals_out_v, digit_base, lookback,
                                                                          epoch, n, shift, tf, tile, smem_raw, key, ticket, ticket_base,
@@ -459,7 +458,6 @@ onesweep_pass(const K *__restrict__ keys_in, K *__restrict__ keys_out, const voi
             pass_tile<K, VB, THREADS, ITEMS, LBATCH, RANK, IDENT, false>(keys_in, keys_out, vals_in_v, vals_out_v, digit_base, lookback,
                                                                           epoch, n, shift, tf, tile, smem_raw, key, ticket, ticket_base,
                                                                           num_tiles);
-        tile = (size_t)*reinterpret_cast<volatile unsigned long long *>(misc);  // next tile id (its keys are already in flight)
         __syncthreads();  // all stores of this tile issued, shared memory free for the next one
     }
 }
@@ -527,8 +525,7 @@ static int launch_pass_impl(StreamState *st, const void *kin, void *kout, const 
     if (grid > tiles) grid = tiles;
     unsigned epoch;
     BCB_TRY(next_epoch(st, &epoch));
-    const unsigned long long tbase = st->ticket_base;
-    st->ticket_base += tiles + grid;  // every CTA draws one id per tile it processes plus one that tells it to stop
+    const unsigned long long tbase = st->ticket_base;  // (tickets are no longer drawn by this kernel)
     LaunchTimer timer(st, BCB_K_ONESWEEP_PASS);
     kernel<<<(unsigned)grid, THREADS, L::kBytes, st->stream>>>((const K *)kin, (K *)kout, vin, vout, base, lookback, epoch,
                                                                st->control + kControlTicket, tbase, n, tiles, shift, tf);

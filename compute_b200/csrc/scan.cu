@@ -16,6 +16,7 @@
 // Floating-point prefixes are folded strictly in tile order, so results are run-to-run deterministic.
 #include "ops.cuh"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace bcb {
@@ -276,6 +277,250 @@ scan_kernel(const T *in, T *out, size_t n, int exclusive, T init, TileState<T> t
     }
 }
 
+// ---- persistent, TMA-pipelined variant -------------------------------------------------------------------
+// The one-tile-per-CTA kernel above exposes every tile's load latency and its look-back latency to the CTA
+// (ncu: warps mostly parked at the barrier while warp 0 looks back; 37 % of HBM peak).  Here the grid is sized to
+// the resident CTAs, each CTA owns a ring of kStages shared-memory stages that the bulk-copy engine fills ahead of
+// time (cp.async.bulk global -> shared, completion on an mbarrier), scans the tile in place in shared memory and
+// hands it back to the copy engine (cp.async.bulk shared -> global).  Loads of the next tiles are therefore in
+// flight during every phase of the current one, and no registers are tied up by data in flight.
+// Tiles are dealt round-robin: CTA b processes tiles b, b + G, b + 2G ... (G = grid size = resident CTAs), so the
+// tiles in flight at any moment form one contiguous window of the input and a prefetched tile is never one that
+// another CTA is waiting for.  (Drawing tickets ahead of time was measured to be 2x slower: a CTA then HOLDS
+// tiles it is not working on yet while their successors spin in the look-back.)
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, unsigned bytes, void *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_1d(void *gmem_dst, const void *smem_src, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N> __device__ __forceinline__ void tma_store_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+constexpr int kRoundThreads = 512;                 // threads per CTA of the round-synchronous kernel
+constexpr int kRoundWarps = kRoundThreads / 32;
+
+template <typename T> struct ScanRing {
+    static constexpr int kItems = sizeof(T) == 8 ? 8 : 16;            // elements per thread
+    static constexpr int kTile = kRoundThreads * kItems;              // 8192 elements (4096 for 8-byte types)
+    static constexpr int kTileBytes = kTile * (int)sizeof(T);         // <= 32 KiB
+    static constexpr int kStages = 3;
+    static constexpr size_t kBytes = (size_t)kStages * kTileBytes + 1024;  // stages + barriers / bookkeeping
+};
+
+// Round-synchronous look-back.  With G persistent CTAs and round-robin tiles, round r processes the contiguous
+// window [rG, (r+1)G).  The prefix of tile t = rG + b is
+//     carry(r)  op  fold(aggregate(rG), ..., aggregate(rG + b - 1))
+// where carry(r) is the inclusive prefix published by the LAST tile of round r-1.  All b aggregates are fetched in
+// ONE parallel step (thread i reads the descriptor of tile rG + i) and folded with a fixed-shape block reduction, so
+// the look-back costs one L2 round trip instead of b/32 of them, every thread of the CTA takes part (no warps parked
+// at a barrier), and a tile's prefix is a pure function of its position and the data: floating-point results are
+// run-to-run deterministic.  Only the last tile of a round publishes an inclusive value.
+template <typename T, int OP>
+__global__ void __launch_bounds__(kRoundThreads)
+scan_tma_kernel(const T *in, T *out, size_t n, int exclusive, T init, TileState<T> ts, unsigned epoch, size_t num_tiles)
+{
+    typedef Op<OP, T> O;
+    typedef ScanRing<T> R;
+    constexpr int VEC = 16 / sizeof(T);
+    constexpr int NV = R::kItems / VEC;
+    constexpr int S = R::kStages;
+    constexpr int TILE = R::kTile;
+    static_assert(NV >= 1, "vector wider than the per-thread item count");
+
+    extern __shared__ __align__(128) unsigned char ring_raw[];
+    T *stage_base = reinterpret_cast<T *>(ring_raw);
+    unsigned long long *full_bar = reinterpret_cast<unsigned long long *>(ring_raw + (size_t)S * R::kTileBytes);  // [S]
+    __shared__ T s_warp_total[kRoundWarps];
+    __shared__ T s_fold[kRoundWarps];
+    __shared__ T s_carry;
+
+    const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    const unsigned G = gridDim.x, b = blockIdx.x;
+    auto tile_of = [&](unsigned it) { return (size_t)b + (size_t)it * G; };
+
+    auto issue_load = [&](int s, size_t tile) {  // thread 0 only
+        if (tile < num_tiles) {
+            const size_t base = tile * (size_t)TILE;
+            if (base + TILE <= n) {  // full tile: bulk copy; a partial last tile is loaded with guarded loads instead
+                mbar_expect_tx(&full_bar[s], (unsigned)R::kTileBytes);
+                tma_load_1d(stage_base + (size_t)s * TILE, in + base, (unsigned)R::kTileBytes, &full_bar[s]);
+            }
+        }
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < S; s++) mbar_init(&full_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int s = 0; s < S; s++) issue_load(s, tile_of((unsigned)s));
+    }
+    __syncthreads();
+
+    for (unsigned it = 0;; ++it) {
+        const size_t tile = tile_of(it);
+        if (tile >= num_tiles) break;
+        const int s = (int)(it % S);
+        const unsigned parity = (it / S) & 1u;
+        const size_t tile_base = tile * (size_t)TILE;
+        const bool full = tile_base + TILE <= n;
+        T *stage = stage_base + (size_t)s * TILE;
+        const unsigned warp_elem = warp * (32 * R::kItems);
+
+        // ---- tile -> registers (from the stage the copy engine filled, or guarded loads for the partial tile) ----
+        T x[NV][VEC];
+        if (full) {
+            mbar_wait(&full_bar[s], parity);
+#pragma unroll
+            for (int j = 0; j < NV; j++) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(stage + warp_elem + (j * 32 + lane) * VEC);
+                const T *e = reinterpret_cast<const T *>(&v);
+#pragma unroll
+                for (int k = 0; k < VEC; k++) x[j][k] = e[k];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < NV; j++) {
+#pragma unroll
+                for (int k = 0; k < VEC; k++) {
+                    const size_t i = tile_base + warp_elem + (size_t)(j * 32 + lane) * VEC + k;
+                    x[j][k] = i < n ? in[i] : O::identity();
+                }
+            }
+        }
+
+        // ---- vector-local scan, warp scans, block aggregate (same arithmetic as scan_kernel) ----
+        T vsum[NV];
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+#pragma unroll
+            for (int k = 1; k < VEC; k++) x[j][k] = O::apply(x[j][k - 1], x[j][k]);
+            vsum[j] = x[j][VEC - 1];
+        }
+        T vexcl[NV];
+        T carry = O::identity();
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            T sc = vsum[j];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const T o = shfl_up_t(sc, d);
+                if ((int)lane >= d) sc = O::apply(o, sc);
+            }
+            T e = shfl_up_t(sc, 1);
+            if (lane == 0) e = O::identity();
+            vexcl[j] = O::apply(carry, e);
+            carry = O::apply(carry, shfl_t(sc, 31));
+        }
+        if (lane == 0) s_warp_total[warp] = carry;
+        __syncthreads();
+        T warp_off = O::identity();
+        T aggregate = O::identity();
+#pragma unroll
+        for (int w = 0; w < kRoundWarps; w++) {
+            const T t = s_warp_total[w];
+            if (w < (int)warp) warp_off = O::apply(warp_off, t);
+            aggregate = O::apply(aggregate, t);
+        }
+        const bool last_in_round = (b == G - 1);
+        if (tid == 0 && !last_in_round) ts.post(tile, epoch, kPartial, aggregate);
+
+        // ---- round-synchronous look-back: one parallel step ----
+        T v = O::identity();
+        if (tid < b) {  // aggregate of tile it*G + tid (same round, earlier position)
+            const size_t j = (size_t)it * G + tid;
+            unsigned st;
+            do { st = ts.peek(j, epoch, v); } while (st == kInvalid);
+        }
+        if (tid == kRoundThreads - 1) {  // carry of the round: inclusive prefix of the previous round's last tile
+            T c = exclusive ? init : O::identity();
+            if (it > 0) {
+                const size_t j = (size_t)it * G - 1;
+                unsigned st;
+                do { st = ts.peek(j, epoch, c); } while (st != kInclusive);
+            }
+            s_carry = c;
+        }
+        // fixed-shape fold: shuffle tree inside each warp (order-preserving), then a left fold over the 16 warp values
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const T o = shfl_up_t(v, off);
+            if ((int)lane >= off) v = O::apply(o, v);
+        }
+        if (lane == 31) s_fold[warp] = v;
+        __syncthreads();
+        T prefix = s_carry;
+#pragma unroll
+        for (int w = 0; w < kRoundWarps; w++) prefix = O::apply(prefix, s_fold[w]);
+        if (tid == 0 && last_in_round) ts.post(tile, epoch, kInclusive, O::apply(prefix, aggregate));
+        const T base = O::apply(prefix, warp_off);
+
+        // ---- outputs: back into the stage (then bulk store), or guarded stores for the partial tile ----
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            const T p = O::apply(base, vexcl[j]);
+            T y[VEC];
+            if (exclusive == 1) {
+                y[0] = p;
+#pragma unroll
+                for (int k = 1; k < VEC; k++) y[k] = O::apply(p, x[j][k - 1]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < VEC; k++) y[k] = O::apply(p, x[j][k]);
+            }
+            if (full) {
+                *reinterpret_cast<uint4 *>(stage + warp_elem + (j * 32 + lane) * VEC) = *reinterpret_cast<const uint4 *>(y);
+            } else {
+                const size_t i0 = tile_base + warp_elem + (size_t)(j * 32 + lane) * VEC;
+#pragma unroll
+                for (int k = 0; k < VEC; k++)
+                    if (i0 + k < n) out[i0 + k] = y[k];
+            }
+        }
+        fence_proxy_async();  // make the generic-proxy writes to the stage visible to the bulk-copy engine
+        __syncthreads();
+        if (tid == 0) {
+            if (full) tma_store_1d(out + tile_base, stage, (unsigned)R::kTileBytes);
+            // the store issued one iteration ago has had a whole tile's time to drain: recycle ITS stage now
+            if (it > 0) {
+                tma_store_wait_read<1>();
+                issue_load((int)((it - 1) % S), tile_of(it - 1 + S));
+            }
+        }
+    }
+    if (tid == 0) tma_store_wait_read<0>();  // shared memory must outlive the last bulk stores
+}
+
 template <typename A>
 __global__ void convert_kernel(const void *in, int in_dtype, A *out, size_t n)
 {
@@ -297,6 +542,31 @@ static int launch_scan(StreamState *st, const void *in, void *out, size_t n, int
     BCB_TRY(next_epoch(st, &epoch));
     TileState<T> ts;
     ts.bind(mem, tiles);
+    static int use_tma = -1;  // BCB_SCAN_TMA=0 forces the one-tile-per-CTA kernel
+    if (use_tma < 0) { const char *e = std::getenv("BCB_SCAN_TMA"); use_tma = (e && e[0] == '0') ? 0 : 1; }
+    const bool aligned = (((uintptr_t)in | (uintptr_t)out) & 15) == 0;
+    if (use_tma && aligned && n >= (size_t)4 * ScanRing<T>::kTile) {
+        typedef ScanRing<T> R;
+        const size_t rtiles = (n + R::kTile - 1) / R::kTile;
+        BCB_TRY(lookback_reserve(st, TileState<T>::bytes(rtiles), &mem));
+        ts.bind(mem, rtiles);
+        auto kernel = scan_tma_kernel<T, OP>;
+        static int resident[64] = {};
+        int per_sm = (st->device < 64) ? resident[st->device] : 0;
+        if (per_sm == 0) {
+            BCB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R::kBytes));
+            BCB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kRoundThreads, R::kBytes));
+            if (per_sm < 1) per_sm = 1;
+            if (st->device < 64) resident[st->device] = per_sm;
+        }
+        size_t grid = (size_t)st->sm_count * (size_t)per_sm;
+        if (grid > (size_t)kRoundThreads) grid = kRoundThreads;  // one look-back thread per earlier tile of the round
+        if (grid > rtiles) grid = rtiles;
+        LaunchTimer timer(st, BCB_K_SCAN);
+        kernel<<<(unsigned)grid, kRoundThreads, R::kBytes, st->stream>>>((const T *)in, (T *)out, n, exclusive, init, ts, epoch, rtiles);
+        BCB_CUDA_TRY(cudaGetLastError());
+        return BCB_SUCCESS;
+    }
     const unsigned long long base = st->ticket_base;
     st->ticket_base += tiles;
     LaunchTimer timer(st, BCB_K_SCAN);
