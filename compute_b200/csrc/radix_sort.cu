@@ -379,6 +379,7 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
                     }
                 }
                 j -= consumed;
+                if (consumed == 0) __nanosleep(40);  // nothing new was published: back off before polling again
             }
             st_relaxed_u64(lookback + tile * kRadixSize + tid,
                            ((unsigned long long)((epoch << 2) | kLbInclusive) << 32) | (unsigned)(excl + count));

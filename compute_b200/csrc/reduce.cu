@@ -9,6 +9,7 @@
 // HBM-bound: 1 x sizeof(T) bytes per element.
 #include "ops.cuh"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace bcb {
@@ -59,10 +60,11 @@ __device__ __forceinline__ T fold_vec(T acc, const uint4 &v)
 }
 
 // Same-type kernel: 128-bit streaming loads over the 16-byte-aligned body, scalar head/tail.
-template <typename T, int OP>
+template <typename T, int OP, int UNROLL, bool CONTIG>
 __global__ void __launch_bounds__(kReduceThreads)
 reduce_kernel(const T *__restrict__ in, size_t n, T *partials, unsigned *done_counter, T *result)
 {
+    constexpr int kReduceUnroll = UNROLL;
     constexpr int VEC = 16 / sizeof(T);
     __shared__ T smem[32];
     __shared__ bool is_last;
@@ -76,19 +78,34 @@ reduce_kernel(const T *__restrict__ in, size_t n, T *partials, unsigned *done_co
     const size_t tail_start = head + nvec * VEC;
     const uint4 *vin = reinterpret_cast<const uint4 *>(in + head);
 
-    T acc[kReduceUnroll];
+    T acc[4];
 #pragma unroll
-    for (int u = 0; u < kReduceUnroll; u++) acc[u] = Op<OP, T>::identity();
+    for (int u = 0; u < 4; u++) acc[u] = Op<OP, T>::identity();
 
-    size_t v = gid;
-    for (; v + (kReduceUnroll - 1) * gthreads < nvec; v += kReduceUnroll * gthreads) {
-        uint4 x[kReduceUnroll];
+    if constexpr (CONTIG) {
+        // each CTA streams contiguous UNROLL x 4 KiB chunks (thread t reads vectors t, t+256, ... of the chunk)
+        const size_t chunk = (size_t)kReduceThreads * kReduceUnroll;
+        const size_t nchunks = nvec / chunk;
+        for (size_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+            const uint4 *p = vin + c * chunk + threadIdx.x;
+            uint4 x[kReduceUnroll];
 #pragma unroll
-        for (int u = 0; u < kReduceUnroll; u++) x[u] = ld_stream_v4(vin + v + u * gthreads);
+            for (int u = 0; u < kReduceUnroll; u++) x[u] = ld_stream_v4(p + u * kReduceThreads);
 #pragma unroll
-        for (int u = 0; u < kReduceUnroll; u++) acc[u] = fold_vec<T, OP, VEC>(acc[u], x[u]);
+            for (int u = 0; u < kReduceUnroll; u++) acc[u % 4] = fold_vec<T, OP, VEC>(acc[u % 4], x[u]);
+        }
+        for (size_t v = nchunks * chunk + gid; v < nvec; v += gthreads) acc[0] = fold_vec<T, OP, VEC>(acc[0], ld_stream_v4(vin + v));
+    } else {
+        size_t v = gid;
+        for (; v + (kReduceUnroll - 1) * gthreads < nvec; v += kReduceUnroll * gthreads) {
+            uint4 x[kReduceUnroll];
+#pragma unroll
+            for (int u = 0; u < kReduceUnroll; u++) x[u] = ld_stream_v4(vin + v + u * gthreads);
+#pragma unroll
+            for (int u = 0; u < kReduceUnroll; u++) acc[u % 4] = fold_vec<T, OP, VEC>(acc[u % 4], x[u]);
+        }
+        for (; v < nvec; v += gthreads) acc[0] = fold_vec<T, OP, VEC>(acc[0], ld_stream_v4(vin + v));
     }
-    for (; v < nvec; v += gthreads) acc[0] = fold_vec<T, OP, VEC>(acc[0], ld_stream_v4(vin + v));
     // scalar head and tail (< 2 * VEC elements in total)
     if (gid < head) acc[1] = Op<OP, T>::apply(acc[1], in[gid]);
     if (tail_start + gid < n) acc[2] = Op<OP, T>::apply(acc[2], in[tail_start + gid]);
@@ -206,9 +223,24 @@ static int launch_reduce_same(StreamState *st, const void *in, size_t n, void *r
     void *partials;
     BCB_TRY(scratch_reserve(st, (size_t)kMaxReduceBlocks * sizeof(T), &partials));
     unsigned *counter = reinterpret_cast<unsigned *>(st->control + 1);
+    static int variant = -1;  // BCB_REDUCE_VARIANT: tuning knob (grid multiplier / unroll / access pattern)
+    if (variant < 0) { const char *e = std::getenv("BCB_REDUCE_VARIANT"); variant = e ? std::atoi(e) : 0; }
     int grid = reduce_grid(n, sizeof(T), st->sm_count);
     LaunchTimer timer(st, BCB_K_REDUCE);
-    reduce_kernel<T, OP><<<grid, kReduceThreads, 0, st->stream>>>((const T *)in, n, (T *)partials, counter, (T *)result_dev);
+    if constexpr (sizeof(T) == 4 && OP == BCB_PLUS) {
+        const int cap4 = st->sm_count * 4, cap16 = st->sm_count * 16 < kMaxReduceBlocks ? st->sm_count * 16 : kMaxReduceBlocks;
+        switch (variant) {
+        case 1: reduce_kernel<T, OP, 4, true><<<grid, kReduceThreads, 0, st->stream>>>((const T *)in, n, (T *)partials, counter, (T *)result_dev); break;
+        case 2: reduce_kernel<T, OP, 8, true><<<grid, kReduceThreads, 0, st->stream>>>((const T *)in, n, (T *)partials, counter, (T *)result_dev); break;
+        case 3: reduce_kernel<T, OP, 8, true><<<grid < cap4 ? grid : cap4, kReduceThreads, 0, st->stream>>>((const T *)in, n, (T *)partials, counter, (T *)result_dev); break;
+        case 4: reduce_kernel<T, OP, 4, false><<<cap16, kReduceThreads, 0, st->stream>>>((const T *)in, n, (T *)partials, counter, (T *)result_dev); break;
+        case 5: reduce_kernel<T, OP, 8, false><<<grid, kReduceThreads, 0, st->stream>>>((const T *)in, n, (T *)partials, counter, (T *)result_dev); break;
+        case 6: reduce_kernel<T, OP, 2, true><<<cap16, kReduceThreads, 0, st->stream>>>((const T *)in, n, (T *)partials, counter, (T *)result_dev); break;
+        default: reduce_kernel<T, OP, 4, false><<<grid, kReduceThreads, 0, st->stream>>>((const T *)in, n, (T *)partials, counter, (T *)result_dev); break;
+        }
+    } else {
+        reduce_kernel<T, OP, 4, false><<<grid, kReduceThreads, 0, st->stream>>>((const T *)in, n, (T *)partials, counter, (T *)result_dev);
+    }
     BCB_CUDA_TRY(cudaGetLastError());
     return BCB_SUCCESS;
 }

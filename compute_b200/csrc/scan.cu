@@ -25,7 +25,8 @@ constexpr int kScanThreads = 256;
 constexpr int kScanWarps = kScanThreads / 32;
 constexpr int kScanItems = 16;                         // elements per thread
 constexpr int kScanTile = kScanThreads * kScanItems;   // 4096
-constexpr int kScanMaxWindows = 40;                    // look-back windows buffered for the ordered fp fold
+constexpr int kScanMaxWindows = 40;
+constexpr unsigned kSpinBackoffNs = 40;                // pause between polls of a descriptor that is not published yet                    // look-back windows buffered for the ordered fp fold
 
 enum : unsigned { kInvalid = 0u, kPartial = 1u, kInclusive = 2u };
 
@@ -117,7 +118,7 @@ __device__ __forceinline__ T lookback_prefix(const TileState<T> &ts, size_t tile
         T val = O::identity();
         unsigned st = kInclusive;  // tiles "before 0" behave as an inclusive identity
         if (idx >= 0) {
-            do { st = ts.peek((size_t)idx, epoch, val); } while (st == kInvalid);
+            while ((st = ts.peek((size_t)idx, epoch, val)) == kInvalid) __nanosleep(kSpinBackoffNs);
         }
         const unsigned inc = __ballot_sync(0xffffffffu, st == kInclusive);
         if constexpr (!is_fp<T>::value) {
@@ -332,21 +333,26 @@ constexpr int kRoundThreads = 512;                 // threads per CTA of the rou
 constexpr int kRoundWarps = kRoundThreads / 32;
 
 template <typename T> struct ScanRing {
-    static constexpr int kItems = sizeof(T) == 8 ? 8 : 16;            // elements per thread
-    static constexpr int kTile = kRoundThreads * kItems;              // 8192 elements (4096 for 8-byte types)
-    static constexpr int kTileBytes = kTile * (int)sizeof(T);         // <= 32 KiB
-    static constexpr int kStages = 3;
+    static constexpr int kItems = sizeof(T) == 1 ? 16 : (sizeof(T) == 8 ? 4 : 8);  // elements per thread
+    static constexpr int kTile = kRoundThreads * kItems;               // 4096 elements (8192 / 2048 for 1- / 8-byte types)
+    static constexpr int kTileBytes = kTile * (int)sizeof(T);          // 16 KiB (8 KiB for 1- and 2-byte types)
+    static constexpr int kStages = 4;
     static constexpr size_t kBytes = (size_t)kStages * kTileBytes + 1024;  // stages + barriers / bookkeeping
 };
 
-// Round-synchronous look-back.  With G persistent CTAs and round-robin tiles, round r processes the contiguous
-// window [rG, (r+1)G).  The prefix of tile t = rG + b is
-//     carry(r)  op  fold(aggregate(rG), ..., aggregate(rG + b - 1))
-// where carry(r) is the inclusive prefix published by the LAST tile of round r-1.  All b aggregates are fetched in
-// ONE parallel step (thread i reads the descriptor of tile rG + i) and folded with a fixed-shape block reduction, so
-// the look-back costs one L2 round trip instead of b/32 of them, every thread of the CTA takes part (no warps parked
-// at a barrier), and a tile's prefix is a pure function of its position and the data: floating-point results are
-// run-to-run deterministic.  Only the last tile of a round publishes an inclusive value.
+// Round-synchronous, software-pipelined look-back.
+// With G persistent CTAs and round-robin tiles, round r processes the contiguous window [rG, (r+1)G).  The prefix of
+// tile t = rG + b is
+//     carry(r)  op  fold(aggregate(rG), ..., aggregate(rG + b - 1)),
+// carry(r) being the inclusive prefix published by the LAST tile of round r-1.  All b aggregates are fetched in ONE
+// parallel step (thread i polls the descriptor of tile rG + i) and folded with a fixed-shape block reduction: one L2
+// round trip instead of b/32, every thread takes part, and a tile's prefix is a pure function of its position and the
+// data, so floating-point results are run-to-run deterministic.  Only the last tile of a round publishes an
+// inclusive value.
+// Each iteration runs phase A of tile `it` (tile -> registers, tile-local scan written back to the stage, aggregate
+// published, first poll of the round's descriptors issued) and then phase C of tile `it-1` (finish the poll, fold the
+// prefix, add it to the stage, hand the stage to the bulk-copy engine).  The descriptors a tile waits for therefore
+// have a whole phase A of slack, and the bulk loads of the next two tiles are in flight all the time.
 template <typename T, int OP>
 __global__ void __launch_bounds__(kRoundThreads)
 scan_tma_kernel(const T *in, T *out, size_t n, int exclusive, T init, TileState<T> ts, unsigned epoch, size_t num_tiles)
@@ -368,6 +374,8 @@ scan_tma_kernel(const T *in, T *out, size_t n, int exclusive, T init, TileState<
 
     const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     const unsigned G = gridDim.x, b = blockIdx.x;
+    const bool last_in_round = (b == G - 1);
+    const unsigned warp_elem = warp * (32 * R::kItems);
     auto tile_of = [&](unsigned it) { return (size_t)b + (size_t)it * G; };
 
     auto issue_load = [&](int s, size_t tile) {  // thread 0 only
@@ -387,134 +395,166 @@ scan_tma_kernel(const T *in, T *out, size_t n, int exclusive, T init, TileState<
     }
     __syncthreads();
 
-    for (unsigned it = 0;; ++it) {
-        const size_t tile = tile_of(it);
-        if (tile >= num_tiles) break;
-        const int s = (int)(it % S);
-        const unsigned parity = (it / S) & 1u;
-        const size_t tile_base = tile * (size_t)TILE;
-        const bool full = tile_base + TILE <= n;
-        T *stage = stage_base + (size_t)s * TILE;
-        const unsigned warp_elem = warp * (32 * R::kItems);
+    // state of the tile whose phase C is pending
+    bool pending = false;
+    T pend_aggregate = O::identity();
+    T poll_v = O::identity();        // threads < b: aggregate of an earlier tile of the round (if poll_ok)
+    T poll_c = O::identity();        // last thread: carry of the round (if poll_ok)
+    bool poll_ok = true;
 
-        // ---- tile -> registers (from the stage the copy engine filled, or guarded loads for the partial tile) ----
-        T x[NV][VEC];
-        if (full) {
-            mbar_wait(&full_bar[s], parity);
+    for (unsigned it = 0;; ++it) {
+        const size_t tileA = tile_of(it);
+        const bool doA = tileA < num_tiles;
+        if (!doA && !pending) break;
+
+        T aggregate = O::identity();
+        if (doA) {
+            // ================= phase A: tile `it` =================
+            const int s = (int)(it % S);
+            const size_t tile_base = tileA * (size_t)TILE;
+            const bool full = tile_base + TILE <= n;
+            T *stage = stage_base + (size_t)s * TILE;
+            T x[NV][VEC];
+            if (full) {
+                mbar_wait(&full_bar[s], (it / S) & 1u);
 #pragma unroll
-            for (int j = 0; j < NV; j++) {
-                const uint4 v = *reinterpret_cast<const uint4 *>(stage + warp_elem + (j * 32 + lane) * VEC);
-                const T *e = reinterpret_cast<const T *>(&v);
+                for (int j = 0; j < NV; j++) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(stage + warp_elem + (j * 32 + lane) * VEC);
+                    const T *e = reinterpret_cast<const T *>(&v);
 #pragma unroll
-                for (int k = 0; k < VEC; k++) x[j][k] = e[k];
-            }
-        } else {
+                    for (int k = 0; k < VEC; k++) x[j][k] = e[k];
+                }
+            } else {
 #pragma unroll
-            for (int j = 0; j < NV; j++) {
+                for (int j = 0; j < NV; j++) {
 #pragma unroll
-                for (int k = 0; k < VEC; k++) {
-                    const size_t i = tile_base + warp_elem + (size_t)(j * 32 + lane) * VEC + k;
-                    x[j][k] = i < n ? in[i] : O::identity();
+                    for (int k = 0; k < VEC; k++) {
+                        const size_t i = tile_base + warp_elem + (size_t)(j * 32 + lane) * VEC + k;
+                        x[j][k] = i < n ? in[i] : O::identity();
+                    }
                 }
             }
-        }
-
-        // ---- vector-local scan, warp scans, block aggregate (same arithmetic as scan_kernel) ----
-        T vsum[NV];
+            // vector-local scan, warp scans, block aggregate
+            T vsum[NV];
 #pragma unroll
-        for (int j = 0; j < NV; j++) {
+            for (int j = 0; j < NV; j++) {
 #pragma unroll
-            for (int k = 1; k < VEC; k++) x[j][k] = O::apply(x[j][k - 1], x[j][k]);
-            vsum[j] = x[j][VEC - 1];
-        }
-        T vexcl[NV];
-        T carry = O::identity();
-#pragma unroll
-        for (int j = 0; j < NV; j++) {
-            T sc = vsum[j];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const T o = shfl_up_t(sc, d);
-                if ((int)lane >= d) sc = O::apply(o, sc);
+                for (int k = 1; k < VEC; k++) x[j][k] = O::apply(x[j][k - 1], x[j][k]);
+                vsum[j] = x[j][VEC - 1];
             }
-            T e = shfl_up_t(sc, 1);
-            if (lane == 0) e = O::identity();
-            vexcl[j] = O::apply(carry, e);
-            carry = O::apply(carry, shfl_t(sc, 31));
-        }
-        if (lane == 0) s_warp_total[warp] = carry;
-        __syncthreads();
-        T warp_off = O::identity();
-        T aggregate = O::identity();
+            T vexcl[NV];
+            T carry = O::identity();
 #pragma unroll
-        for (int w = 0; w < kRoundWarps; w++) {
-            const T t = s_warp_total[w];
-            if (w < (int)warp) warp_off = O::apply(warp_off, t);
-            aggregate = O::apply(aggregate, t);
-        }
-        const bool last_in_round = (b == G - 1);
-        if (tid == 0 && !last_in_round) ts.post(tile, epoch, kPartial, aggregate);
-
-        // ---- round-synchronous look-back: one parallel step ----
-        T v = O::identity();
-        if (tid < b) {  // aggregate of tile it*G + tid (same round, earlier position)
-            const size_t j = (size_t)it * G + tid;
-            unsigned st;
-            do { st = ts.peek(j, epoch, v); } while (st == kInvalid);
-        }
-        if (tid == kRoundThreads - 1) {  // carry of the round: inclusive prefix of the previous round's last tile
-            T c = exclusive ? init : O::identity();
-            if (it > 0) {
-                const size_t j = (size_t)it * G - 1;
-                unsigned st;
-                do { st = ts.peek(j, epoch, c); } while (st != kInclusive);
+            for (int j = 0; j < NV; j++) {
+                T sc = vsum[j];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const T o = shfl_up_t(sc, d);
+                    if ((int)lane >= d) sc = O::apply(o, sc);
+                }
+                T e = shfl_up_t(sc, 1);
+                if (lane == 0) e = O::identity();
+                vexcl[j] = O::apply(carry, e);
+                carry = O::apply(carry, shfl_t(sc, 31));
             }
-            s_carry = c;
-        }
-        // fixed-shape fold: shuffle tree inside each warp (order-preserving), then a left fold over the 16 warp values
+            if (lane == 0) s_warp_total[warp] = carry;
+            __syncthreads();
+            T warp_off = O::identity();
 #pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const T o = shfl_up_t(v, off);
-            if ((int)lane >= off) v = O::apply(o, v);
-        }
-        if (lane == 31) s_fold[warp] = v;
-        __syncthreads();
-        T prefix = s_carry;
-#pragma unroll
-        for (int w = 0; w < kRoundWarps; w++) prefix = O::apply(prefix, s_fold[w]);
-        if (tid == 0 && last_in_round) ts.post(tile, epoch, kInclusive, O::apply(prefix, aggregate));
-        const T base = O::apply(prefix, warp_off);
-
-        // ---- outputs: back into the stage (then bulk store), or guarded stores for the partial tile ----
-#pragma unroll
-        for (int j = 0; j < NV; j++) {
-            const T p = O::apply(base, vexcl[j]);
-            T y[VEC];
-            if (exclusive == 1) {
-                y[0] = p;
-#pragma unroll
-                for (int k = 1; k < VEC; k++) y[k] = O::apply(p, x[j][k - 1]);
-            } else {
-#pragma unroll
-                for (int k = 0; k < VEC; k++) y[k] = O::apply(p, x[j][k]);
+            for (int w = 0; w < kRoundWarps; w++) {
+                const T t = s_warp_total[w];
+                if (w < (int)warp) warp_off = O::apply(warp_off, t);
+                aggregate = O::apply(aggregate, t);
             }
-            if (full) {
+            if (tid == 0 && !last_in_round) ts.post(tileA, epoch, kPartial, aggregate);
+            // tile-local scan back into the stage (phase C adds the tile prefix)
+#pragma unroll
+            for (int j = 0; j < NV; j++) {
+                const T p = O::apply(warp_off, vexcl[j]);
+                T y[VEC];
+                if (exclusive == 1) {
+                    y[0] = p;
+#pragma unroll
+                    for (int k = 1; k < VEC; k++) y[k] = O::apply(p, x[j][k - 1]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < VEC; k++) y[k] = O::apply(p, x[j][k]);
+                }
                 *reinterpret_cast<uint4 *>(stage + warp_elem + (j * 32 + lane) * VEC) = *reinterpret_cast<const uint4 *>(y);
-            } else {
-                const size_t i0 = tile_base + warp_elem + (size_t)(j * 32 + lane) * VEC;
-#pragma unroll
-                for (int k = 0; k < VEC; k++)
-                    if (i0 + k < n) out[i0 + k] = y[k];
             }
         }
-        fence_proxy_async();  // make the generic-proxy writes to the stage visible to the bulk-copy engine
-        __syncthreads();
-        if (tid == 0) {
-            if (full) tma_store_1d(out + tile_base, stage, (unsigned)R::kTileBytes);
-            // the store issued one iteration ago has had a whole tile's time to drain: recycle ITS stage now
-            if (it > 0) {
-                tma_store_wait_read<1>();
-                issue_load((int)((it - 1) % S), tile_of(it - 1 + S));
+
+        if (pending) {
+            // ================= phase C: tile `it - 1` =================
+            const unsigned pit = it - 1;
+            const size_t tileC = tile_of(pit);
+            const int s = (int)(pit % S);
+            const size_t tile_base = tileC * (size_t)TILE;
+            const bool full = tile_base + TILE <= n;
+            T *stage = stage_base + (size_t)s * TILE;
+            // finish the poll that phase A of that tile started
+            if (!poll_ok) {
+                if (tid < b) {
+                    const size_t j = (size_t)pit * G + tid;
+                    while (ts.peek(j, epoch, poll_v) == kInvalid) __nanosleep(kSpinBackoffNs);
+                } else if (tid == kRoundThreads - 1) {
+                    const size_t j = (size_t)pit * G - 1;
+                    while (ts.peek(j, epoch, poll_c) != kInclusive) __nanosleep(kSpinBackoffNs);
+                }
+            }
+            if (tid == kRoundThreads - 1) s_carry = poll_c;
+            T v = (tid < b) ? poll_v : O::identity();
+            // fixed-shape fold: ordered shuffle scan inside each warp, then a left fold over the 16 warp values
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const T o = shfl_up_t(v, off);
+                if ((int)lane >= off) v = O::apply(o, v);
+            }
+            if (lane == 31) s_fold[warp] = v;
+            __syncthreads();
+            T prefix = s_carry;
+#pragma unroll
+            for (int w = 0; w < kRoundWarps; w++) prefix = O::apply(prefix, s_fold[w]);
+            if (tid == 0 && last_in_round) ts.post(tileC, epoch, kInclusive, O::apply(prefix, pend_aggregate));
+#pragma unroll
+            for (int j = 0; j < NV; j++) {
+                T *slot = stage + warp_elem + (j * 32 + lane) * VEC;
+                uint4 raw = *reinterpret_cast<const uint4 *>(slot);
+                T *e = reinterpret_cast<T *>(&raw);
+#pragma unroll
+                for (int k = 0; k < VEC; k++) e[k] = O::apply(prefix, e[k]);
+                if (full) {
+                    *reinterpret_cast<uint4 *>(slot) = raw;
+                } else {
+                    const size_t i0 = tile_base + warp_elem + (size_t)(j * 32 + lane) * VEC;
+#pragma unroll
+                    for (int k = 0; k < VEC; k++)
+                        if (i0 + k < n) out[i0 + k] = e[k];
+                }
+            }
+            fence_proxy_async();  // make the generic-proxy writes to the stage visible to the bulk-copy engine
+            __syncthreads();
+            if (tid == 0) {
+                if (full) tma_store_1d(out + tile_base, stage, (unsigned)R::kTileBytes);
+                if (pit > 0) {  // the store issued one iteration ago has drained: recycle its stage
+                    tma_store_wait_read<1>();
+                    issue_load((int)((pit - 1) % S), tile_of(pit - 1 + S));
+                }
+            }
+        } else if (doA) {
+            __syncthreads();  // keep s_warp_total's readers and the next iteration's writers apart
+        }
+
+        // first (non-blocking) poll for the tile that just went through phase A
+        pending = doA;
+        pend_aggregate = aggregate;
+        poll_ok = true;
+        if (doA) {
+            if (tid < b) {
+                poll_ok = ts.peek((size_t)it * G + tid, epoch, poll_v) != kInvalid;
+            } else if (tid == kRoundThreads - 1) {
+                poll_c = exclusive ? init : O::identity();
+                if (it > 0) poll_ok = ts.peek((size_t)it * G - 1, epoch, poll_c) == kInclusive;
             }
         }
     }
