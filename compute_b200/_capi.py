@@ -39,6 +39,7 @@ SIGNATURES = {
     "bcb_insertion_sort": ([_vp, _i, _i, _vp, _sz, _vp, _sz], _i),
     "bcb_sort_host": ([_vp, _i, _i, _vp, _sz], _i),
     "bcb_partition_points": ([_vp, _i, _i, _vp, _sz, _vp, _sz, _vp], _i),
+    "bcb_partition_by_splitters": ([_vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _sz, _vp, _sz, _vp], _i),
     "bcb_scan": ([_vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp], _i),
     "bcb_reduce": ([_vp, _i, _i, _i, _vp, _sz, _vp, _i], _i),
     "bcb_accumulate": ([_vp, _i, _i, _i, _i, _vp, _sz, _vp, _vp], _i),

@@ -33,10 +33,14 @@ constexpr int kLookbackBatch = 8;  // default look-back batch
 enum : unsigned { kLbInvalid = 0u, kLbPartial = 1u, kLbInclusive = 2u };
 
 // order-preserving transform parameters (uniform): key' = ((x ^ nm) - nm) ^ xc ^ (asr(x) & fa)
+constexpr int kMaxSplitters = 7;  // multi-GPU partition pass: up to 8 destinations
 struct Transform {
     unsigned long long nm;  // all-ones: negate x first (descending signed / float)
     unsigned long long xc;  // xor constant: sign bit (signed, float) or all-ones (descending unsigned)
     unsigned long long fa;  // float only: bits below the sign, selected when x is negative
+    // splitter mode (digit = number of splitters <= transformed key): used by the multi-GPU partition pass
+    unsigned long long split[kMaxSplitters];
+    int nsplit;
 };
 
 static Transform make_transform(int dtype, bool ascending)
@@ -44,7 +48,7 @@ static Transform make_transform(int dtype, bool ascending)
     const unsigned w = (unsigned)dtype_size(dtype) * 8;
     const unsigned long long ones = (w == 64) ? ~0ull : ((1ull << w) - 1);
     const unsigned long long sign = 1ull << (w - 1);
-    Transform t{0, 0, 0};
+    Transform t{};
     const bool sgn = dtype_is_signed_int(dtype), flt = dtype_is_float(dtype);
     if (sgn || flt) {
         t.xc = sign;
@@ -208,11 +212,23 @@ struct PassSmem {
     static constexpr size_t kBytes = kWarpTab + kSmall + (size_t)TILE * kElem + 16;
 };
 
-template <typename K, bool IDENT>
+// digit modes of the pass kernel: plain bit field (unsigned ascending), transformed bit field, splitter bucket
+enum { kDigitIdent = 1, kDigitTransform = 0, kDigitSplit = 2 };
+
+template <typename K, int IDENT>
 __device__ __forceinline__ unsigned pass_digit(K raw, int shift, const Transform &tf)
 {
-    if constexpr (IDENT) return (unsigned)(raw >> shift) & (kRadixSize - 1);  // unsigned ascending: no transform
-    else return digit_of<K>(raw, shift, tf);
+    if constexpr (IDENT == kDigitIdent) {
+        return (unsigned)(raw >> shift) & (kRadixSize - 1);
+    } else if constexpr (IDENT == kDigitSplit) {
+        const unsigned long long t = transformed_key<K>(raw, tf);
+        unsigned d = 0;
+#pragma unroll
+        for (int j = 0; j < kMaxSplitters; j++) d += (j < tf.nsplit && t >= tf.split[j]) ? 1u : 0u;
+        return d;
+    } else {
+        return digit_of<K>(raw, shift, tf);
+    }
 }
 
 // Tile layout: 16-lane virtual warp v = tid/16 owns the contiguous segment [v*ITEMS*16, (v+1)*ITEMS*16) of the tile;
@@ -242,7 +258,7 @@ __device__ __forceinline__ void load_tile_keys(const K *__restrict__ keys_in, si
     }
 }
 
-template <typename K, int VB, int THREADS, int ITEMS, int LBATCH, int RANK, bool IDENT, bool FULL>
+template <typename K, int VB, int THREADS, int ITEMS, int LBATCH, int RANK, int IDENT, bool FULL>
 __device__ __forceinline__ void
 pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *__restrict__ vals_in_v,
           void *__restrict__ vals_out_v, const unsigned *__restrict__ digit_base, unsigned long long *lookback,
@@ -426,7 +442,7 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
     }
 }
 
-template <typename K, int VB, int THREADS, int ITEMS, int LBATCH, int RANK, bool IDENT, int MINB>
+template <typename K, int VB, int THREADS, int ITEMS, int LBATCH, int RANK, int IDENT, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 onesweep_pass(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *__restrict__ vals_in_v,
               void *__restrict__ vals_out_v, const unsigned *__restrict__ digit_base, unsigned long long *lookback,
@@ -503,7 +519,7 @@ __global__ void insertion_sort_kernel(T *keys, size_t n, int greater, unsigned c
 // ---- launch plumbing -----------------------------------------------------------------------------------
 constexpr int default_min_blocks(int threads) { return threads <= 256 ? 3 : (threads <= 512 ? 2 : 1); }
 
-template <typename K, int VB, int THREADS, int ITEMS, int LBATCH, int RANK, bool IDENT, int MINB = default_min_blocks(THREADS)>
+template <typename K, int VB, int THREADS, int ITEMS, int LBATCH, int RANK, int IDENT, int MINB = default_min_blocks(THREADS)>
 static int launch_pass_impl(StreamState *st, const void *kin, void *kout, const void *vin, void *vout, const unsigned *base,
                        unsigned long long *lookback, size_t n, int shift, const Transform &tf)
 {
@@ -551,12 +567,12 @@ static int launch_pass(StreamState *st, const void *kin, void *kout, const void 
     const bool ident = (tf.nm | tf.xc | tf.fa) == 0;  // unsigned ascending keys: the digit is a plain bit field
     if constexpr (sizeof(K) == 4 && VB == 0) {
         if (rank_mode() == kRankOrderedAtoms) {
-            return ident ? launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankOrderedAtoms, true, MINB>(st, kin, kout, vin, vout, base, lookback, n, shift, tf)
-                         : launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankOrderedAtoms, false, MINB>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
+            return ident ? launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankOrderedAtoms, kDigitIdent, MINB>(st, kin, kout, vin, vout, base, lookback, n, shift, tf)
+                         : launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankOrderedAtoms, kDigitTransform, MINB>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
         }
     }
-    return ident ? launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankAtomicOr, true, MINB>(st, kin, kout, vin, vout, base, lookback, n, shift, tf)
-                 : launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankAtomicOr, false, MINB>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
+    return ident ? launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankAtomicOr, kDigitIdent, MINB>(st, kin, kout, vin, vout, base, lookback, n, shift, tf)
+                 : launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankAtomicOr, kDigitTransform, MINB>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
 }
 
 // tile shapes: (key bytes, value bytes) -> THREADS x ITEMS
@@ -610,6 +626,72 @@ static int run_pass(StreamState *st, const void *kin, void *kout, const void *vi
     }
     return launch_pass<K, VB, PassConfig<K, VB>::THREADS, PassConfig<K, VB>::ITEMS>(st, kin, kout, vin, vout, base, lookback, n,
                                                                                      shift, tf);
+}
+
+// ---- multi-GPU partition pass: bucket histogram by splitters ---------------------------------------------
+template <typename K>
+__global__ void __launch_bounds__(256) split_histogram(const K *__restrict__ keys, size_t n, unsigned *__restrict__ hist, Transform tf)
+{
+    unsigned cnt[kMaxSplitters + 1];
+#pragma unroll
+    for (int j = 0; j <= kMaxSplitters; j++) cnt[j] = 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned d = pass_digit<K, kDigitSplit>(__ldg(keys + i), 0, tf);
+#pragma unroll
+        for (int j = 0; j <= kMaxSplitters; j++) cnt[j] += (d == (unsigned)j);
+    }
+#pragma unroll
+    for (int j = 0; j <= kMaxSplitters; j++) {
+        unsigned v = cnt[j];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        if ((threadIdx.x & 31u) == 0 && v) atomicAdd(hist + j, v);
+    }
+}
+
+template <typename K, int VB>
+static int partition_typed(StreamState *st, const void *kin, void *kout, const void *vin, void *vout, size_t n, const Transform &tf,
+                           unsigned long long *counts_host)
+{
+    constexpr int THREADS = PassConfig<K, VB>::THREADS, ITEMS = PassConfig<K, VB>::ITEMS;
+    const size_t tile = (size_t)THREADS * ITEMS;
+    const size_t tiles = (n + tile - 1) / tile;
+    void *lb;
+    BCB_TRY(lookback_reserve(st, tiles * kRadixSize * sizeof(unsigned long long), &lb));
+    unsigned *hist = st->hist;
+    unsigned *base = st->hist + 8 * kRadixSize;
+    BCB_CUDA_TRY(cudaMemsetAsync(hist, 0, kRadixSize * sizeof(unsigned), st->stream));
+    size_t blocks = (n + 256 * 16 - 1) / (256 * 16);
+    const size_t cap = (size_t)st->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    {
+        LaunchTimer timer(st, BCB_K_RADIX_HISTOGRAM);
+        split_histogram<K><<<(unsigned)blocks, 256, 0, st->stream>>>((const K *)kin, n, hist, tf);
+    }
+    BCB_CUDA_TRY(cudaGetLastError());
+    digit_scan<<<1, kRadixSize, 0, st->stream>>>(hist, base);
+    BCB_CUDA_TRY(cudaGetLastError());
+    unsigned host_counts[kMaxSplitters + 1];
+    BCB_CUDA_TRY(cudaMemcpyAsync(host_counts, hist, sizeof(host_counts), cudaMemcpyDeviceToHost, st->stream));
+    BCB_TRY((launch_pass_impl<K, VB, THREADS, ITEMS, kLookbackBatch, kRankAtomicOr, kDigitSplit>(st, kin, kout, vin, vout, base,
+                                                                                                (unsigned long long *)lb, n, 0, tf)));
+    BCB_CUDA_TRY(cudaStreamSynchronize(st->stream));
+    for (int j = 0; j <= tf.nsplit; j++) counts_host[j] = host_counts[j];
+    return BCB_SUCCESS;
+}
+
+template <typename K>
+static int partition_by_value_size(StreamState *st, const void *kin, void *kout, const void *vin, void *vout, size_t vb, size_t n,
+                                   const Transform &tf, unsigned long long *counts_host)
+{
+    if (!vin || vb == 0) return partition_typed<K, 0>(st, kin, kout, nullptr, nullptr, n, tf, counts_host);
+    switch (vb) {
+    case 4: return partition_typed<K, 4>(st, kin, kout, vin, vout, n, tf, counts_host);
+    case 8: return partition_typed<K, 8>(st, kin, kout, vin, vout, n, tf, counts_host);
+    default: return BCB_EUNSUPPORTED;  // callers fall back to sort-then-cut (bcb_partition_points)
+    }
 }
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -784,6 +866,30 @@ int bcb_partition_points(bcb_stream stream, int key_dtype, int ascending, const 
     if (rc == BCB_SUCCESS && e != cudaSuccess) rc = (int)e;
     if (rc != BCB_SUCCESS) (void)cudaGetLastError();
     return rc;
+}
+
+int bcb_partition_by_splitters(bcb_stream stream, int key_dtype, int ascending, const void *keys_in, void *keys_out,
+                               const void *values_in, void *values_out, size_t value_bytes, size_t n,
+                               const unsigned long long *splitters_host, size_t num_splitters, unsigned long long *counts_host)
+{
+    if (!dtype_size(key_dtype) || !counts_host) return BCB_EINVAL;
+    if (num_splitters > (size_t)kMaxSplitters) return BCB_EUNSUPPORTED;
+    for (size_t j = 0; j <= num_splitters; j++) counts_host[j] = 0;
+    if (n == 0) return BCB_SUCCESS;
+    if (!keys_in || !keys_out || (num_splitters && !splitters_host)) return BCB_EINVAL;
+    if (n >= 0xffff0000ull) return BCB_ETOOLARGE;
+    StreamState *st;
+    BCB_TRY(stream_state((cudaStream_t)stream, &st));
+    Transform tf = make_transform(key_dtype, ascending != 0);
+    tf.nsplit = (int)num_splitters;
+    for (size_t j = 0; j < num_splitters; j++) tf.split[j] = splitters_host[j];
+    const size_t vb = (values_in && values_out) ? value_bytes : 0;
+    switch (dtype_size(key_dtype)) {
+    case 1: return partition_by_value_size<unsigned char>(st, keys_in, keys_out, values_in, values_out, vb, n, tf, counts_host);
+    case 2: return partition_by_value_size<unsigned short>(st, keys_in, keys_out, values_in, values_out, vb, n, tf, counts_host);
+    case 4: return partition_by_value_size<unsigned>(st, keys_in, keys_out, values_in, values_out, vb, n, tf, counts_host);
+    default: return partition_by_value_size<unsigned long long>(st, keys_in, keys_out, values_in, values_out, vb, n, tf, counts_host);
+    }
 }
 
 int bcb_sort_host(bcb_stream stream, int key_dtype, int descending, void *host_keys, size_t n)

@@ -236,10 +236,18 @@ static int launch_reduce_same(StreamState *st, const void *in, size_t n, void *r
         case 4: reduce_kernel<T, OP, 4, false><<<cap16, kReduceThreads, 0, st->stream>>>((const T *)in, n, (T *)partials, counter, (T *)result_dev); break;
         case 5: reduce_kernel<T, OP, 8, false><<<grid, kReduceThreads, 0, st->stream>>>((const T *)in, n, (T *)partials, counter, (T *)result_dev); break;
         case 6: reduce_kernel<T, OP, 2, true><<<cap16, kReduceThreads, 0, st->stream>>>((const T *)in, n, (T *)partials, counter, (T *)result_dev); break;
-        default: reduce_kernel<T, OP, 4, false><<<grid, kReduceThreads, 0, st->stream>>>((const T *)in, n, (T *)partials, counter, (T *)result_dev); break;
+        case 7: reduce_kernel<T, OP, 4, false><<<grid, kReduceThreads, 0, st->stream>>>((const T *)in, n, (T *)partials, counter, (T *)result_dev); break;
+        default: break;
         }
-    } else {
-        reduce_kernel<T, OP, 4, false><<<grid, kReduceThreads, 0, st->stream>>>((const T *)in, n, (T *)partials, counter, (T *)result_dev);
+        if (variant >= 1 && variant <= 7) { BCB_CUDA_TRY(cudaGetLastError()); return BCB_SUCCESS; }
+    }
+    {
+        // default (measured best of the variants on B200): contiguous 8 KiB chunks per CTA, 2 vectors in flight per
+        // thread, 16 CTAs per SM
+        int g = st->sm_count * 16 < kMaxReduceBlocks ? st->sm_count * 16 : kMaxReduceBlocks;
+        const size_t chunks = (n * sizeof(T) + (size_t)kReduceThreads * 32 - 1) / ((size_t)kReduceThreads * 32);
+        if ((size_t)g > chunks) g = (int)(chunks ? chunks : 1);
+        reduce_kernel<T, OP, 2, true><<<g, kReduceThreads, 0, st->stream>>>((const T *)in, n, (T *)partials, counter, (T *)result_dev);
     }
     BCB_CUDA_TRY(cudaGetLastError());
     return BCB_SUCCESS;

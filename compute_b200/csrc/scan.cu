@@ -402,6 +402,20 @@ scan_tma_kernel(const T *in, T *out, size_t n, int exclusive, T init, TileState<
     T poll_c = O::identity();        // last thread: carry of the round (if poll_ok)
     bool poll_ok = true;
 
+    // ordered fold of the 16 per-warp values in shared memory, done by every warp with shuffles:
+    // before = fold of vals[0 .. upto), all = fold of all 16
+    auto fold16 = [&](const T *vals, unsigned upto, T &before, T &all) {
+        T t = (lane < (unsigned)kRoundWarps) ? vals[lane] : O::identity();
+#pragma unroll
+        for (int d = 1; d < kRoundWarps; d <<= 1) {
+            const T o = shfl_up_t(t, d);
+            if ((int)lane >= d) t = O::apply(o, t);
+        }
+        all = shfl_t(t, kRoundWarps - 1);
+        const T prev = shfl_t(t, upto == 0 ? 0 : (int)upto - 1);
+        before = upto == 0 ? O::identity() : prev;
+    };
+
     for (unsigned it = 0;; ++it) {
         const size_t tileA = tile_of(it);
         const bool doA = tileA < num_tiles;
@@ -459,13 +473,8 @@ scan_tma_kernel(const T *in, T *out, size_t n, int exclusive, T init, TileState<
             }
             if (lane == 0) s_warp_total[warp] = carry;
             __syncthreads();
-            T warp_off = O::identity();
-#pragma unroll
-            for (int w = 0; w < kRoundWarps; w++) {
-                const T t = s_warp_total[w];
-                if (w < (int)warp) warp_off = O::apply(warp_off, t);
-                aggregate = O::apply(aggregate, t);
-            }
+            T warp_off;
+            fold16(s_warp_total, warp, warp_off, aggregate);
             if (tid == 0 && !last_in_round) ts.post(tileA, epoch, kPartial, aggregate);
             // tile-local scan back into the stage (phase C adds the tile prefix)
 #pragma unroll
@@ -512,9 +521,9 @@ scan_tma_kernel(const T *in, T *out, size_t n, int exclusive, T init, TileState<
             }
             if (lane == 31) s_fold[warp] = v;
             __syncthreads();
-            T prefix = s_carry;
-#pragma unroll
-            for (int w = 0; w < kRoundWarps; w++) prefix = O::apply(prefix, s_fold[w]);
+            T unused, folded;
+            fold16(s_fold, 0, unused, folded);
+            const T prefix = O::apply(s_carry, folded);
             if (tid == 0 && last_in_round) ts.post(tileC, epoch, kInclusive, O::apply(prefix, pend_aggregate));
 #pragma unroll
             for (int j = 0; j < NV; j++) {

@@ -124,6 +124,28 @@ class CudaLocalOps:
                                                    out.ctypes.data))
         return out[: splitters.size].astype(np.int64)
 
+    def partition(self, keys, values, splitters: np.ndarray, descending: bool):
+        """Stable partition of the unsorted shard into len(splitters)+1 buckets in one pass.  Returns
+        (keys_out, values_out, counts) or None when the C ABI does not support the shape (then sort-and-cut is used)."""
+        nb = splitters.size + 1
+        vb = 0 if values is None else values.element_size() * (values.numel() // max(1, values.shape[0]))
+        if splitters.size > 7 or vb not in (0, 4, 8):
+            return None  # same decision on every rank (it depends on shapes only)
+        if keys.shape[0] == 0:
+            return keys, values, np.zeros(nb, dtype=np.int64)
+        out_k = torch.empty_like(keys)
+        out_v = torch.empty_like(values) if values is not None else None
+        counts = np.zeros(nb, dtype=np.uint64)
+        sp = np.ascontiguousarray(splitters, dtype=np.uint64)
+        rc = self._lib.bcb_partition_by_splitters(self.queue.handle, dtype_code(keys.dtype), int(not descending), keys.data_ptr(),
+                                                  out_k.data_ptr(), None if values is None else values.data_ptr(),
+                                                  None if values is None else out_v.data_ptr(), vb, keys.shape[0],
+                                                  sp.ctypes.data, sp.size, counts.ctypes.data)
+        if rc == 10002:  # BCB_EUNSUPPORTED
+            return None
+        self._check(rc)
+        return out_k, out_v, counts.astype(np.int64)
+
     def gather_bits(self, keys, positions: np.ndarray) -> np.ndarray:
         """Raw bit patterns of keys[positions] as unsigned ints on the host."""
         w = keys.element_size()
@@ -193,27 +215,42 @@ class Context:
             self.ops.sort(keys, values, descending)
             return keys if values is None else (keys, values)
         code = dtype_code(keys.dtype)
-        # 1. local stable sort
-        self.ops.sort(keys, values, descending)
-        # 2. regular samples of the sorted shard, transformed to the common unsigned order
         s = self.samples_per_rank
-        pos = (np.arange(s, dtype=np.int64) * max(n_local, 1)) // s if n_local else np.zeros(0, np.int64)
-        bits = self.ops.gather_bits(keys, pos) if n_local else np.zeros(0, _NP_UINT[keys.element_size()])
-        tk = transformed_keys(bits, code, not descending)
-        if tk.size < s:  # empty shard: pad with the maximum so it does not pull splitters down
-            tk = np.concatenate([tk, np.full(s - tk.size, np.iinfo(np.uint64).max, np.uint64)])
-        splitters = select_splitters(self._all_gather_np(tk), P)
-        # 3. partition points and the P x P count matrix
-        points = self.ops.partition_points(keys, splitters, descending) if n_local else np.zeros(P - 1, np.int64)
-        send = exchange_plan(points, n_local)
-        counts = self._all_gather_np(send)          # counts[src][dst]
+
+        def sample_splitters(src):
+            pos = (np.arange(s, dtype=np.int64) * max(n_local, 1)) // s if n_local else np.zeros(0, np.int64)
+            bits = self.ops.gather_bits(src, pos) if n_local else np.zeros(0, _NP_UINT[src.element_size()])
+            tk = transformed_keys(bits, code, not descending)
+            if tk.size < s:  # empty shard: pad with the maximum so it does not pull splitters down
+                tk = np.concatenate([tk, np.full(s - tk.size, np.iinfo(np.uint64).max, np.uint64)])
+            return select_splitters(self._all_gather_np(tk), P)
+
+        # Preferred plan: evenly spaced samples of the UNSORTED shard -> splitters -> ONE stable partition pass
+        # (bucket = number of splitters <= transformed key) -> all-to-all -> one local sort.
+        splitters = sample_splitters(keys)
+        part = self.ops.partition(keys, values, splitters, descending) if hasattr(self.ops, "partition") else None
+        if part is not None:
+            src_keys, src_vals, send = part
+            plan = "partition"
+        else:
+            # Fallback (payload sizes / rank counts the partition kernel does not cover): local stable sort, then
+            # cut the sorted shard at the splitters by binary search.
+            self.ops.sort(keys, values, descending)
+            splitters = sample_splitters(keys)
+            points = self.ops.partition_points(keys, splitters, descending) if n_local else np.zeros(P - 1, np.int64)
+            send = exchange_plan(points, n_local)
+            src_keys, src_vals = keys, values
+            plan = "sort-and-cut"
+        plans = self._all_gather_np(np.array([1 if plan == "partition" else 0], dtype=np.int32)).reshape(-1)
+        counts = self._all_gather_np(np.asarray(send, dtype=np.int64))          # counts[src][dst]
         recv = counts[:, self.rank].copy()
-        # 4. exchange: contiguous slices, received in source-rank order
-        out_keys = self._all_to_all(keys, send, recv)
-        out_vals = self._all_to_all(values, send, recv) if values is not None else None
+        # exchange: contiguous slices, received in source-rank order
+        out_keys = self._all_to_all(src_keys, send, recv)
+        out_vals = self._all_to_all(src_vals, send, recv) if values is not None else None
+        _ = plans
         # 5. final local stable sort of the P received runs
         self.ops.sort(out_keys, out_vals, descending)
-        self.last_stats = {"sent": int(send.sum() - send[self.rank]), "received": int(recv.sum()),
+        self.last_stats = {"plan": plan, "sent": int(send.sum() - send[self.rank]), "received": int(recv.sum()),
                            "imbalance": float(counts.sum(axis=0).max() * P / max(1, counts.sum()))}
         return out_keys if values is None else (out_keys, out_vals)
 

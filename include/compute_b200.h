@@ -122,6 +122,15 @@ BCB_API int bcb_partition_points(bcb_stream stream, int key_dtype, int ascending
                                  const unsigned long long *splitters_host, size_t num_splitters,
                                  unsigned long long *points_host);
 
+/* Stable partition of an UNSORTED range into num_splitters + 1 buckets (bucket of a key = number of splitters <= its
+ * transformed key; splitters as for bcb_partition_points, at most 7): one onesweep-style pass, out of place
+ * (keys_in -> keys_out, values likewise; value_bytes 0, 4 or 8).  counts_host receives the bucket sizes.  This is the
+ * first step of the multi-GPU sample sort: the buckets are the per-destination slices of the all-to-all.  Blocks. */
+BCB_API int bcb_partition_by_splitters(bcb_stream stream, int key_dtype, int ascending, const void *keys_in, void *keys_out,
+                                       const void *values_in, void *values_out, size_t value_bytes, size_t n,
+                                       const unsigned long long *splitters_host, size_t num_splitters,
+                                       unsigned long long *counts_host);
+
 /* ---- scan ---- */
 /* detail::scan (algorithm/detail/scan.hpp:22-39) with the operator-generic semantics of serial_scan.hpp:26-97:
  * inclusive: out[i] = x0 op ... op xi;  exclusive: out[i] = init op x0 op ... op x(i-1).  Arithmetic in out_dtype

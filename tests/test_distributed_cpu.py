@@ -69,6 +69,19 @@ class OracleLocalOps:
         tk = cbd.transformed_keys(bits, dtype_code(k.dtype), not descending)
         return np.searchsorted(tk, splitters, side="left").astype(np.int64)
 
+    def partition(self, keys, values, splitters, descending):
+        if getattr(self, "force_sort_and_cut", False):
+            return None
+        k = self._np(keys)
+        bits = k.view({1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[k.dtype.itemsize])
+        tk = cbd.transformed_keys(bits, dtype_code(k.dtype), not descending)
+        bucket = np.searchsorted(splitters, tk, side="right")
+        order = np.argsort(bucket, kind="stable")
+        counts = np.bincount(bucket, minlength=splitters.size + 1).astype(np.int64)
+        ok = torch.from_numpy(k[order].copy())
+        ov = torch.from_numpy(self._np(values)[order].copy()) if values is not None else None
+        return ok, ov, counts
+
     def gather_bits(self, keys, positions):
         k = self._np(keys)
         return k.view({1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[k.dtype.itemsize])[positions]
@@ -106,7 +119,8 @@ def _worker(rank, world, port, results):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        ctx = cbd.Context(local_ops=OracleLocalOps(), samples_per_rank=64)
+        ops = OracleLocalOps()
+        ctx = cbd.Context(local_ops=ops, samples_per_rank=64)
         rng = np.random.default_rng(42)
         out = {}
         # --- sort: keys only (float with duplicates, descending) and by key (int keys, 8-byte payload rows) ---
@@ -121,6 +135,11 @@ def _worker(rank, world, port, results):
         k, v = ctx.sort(torch.from_numpy(keys[lo:hi].copy()), torch.from_numpy(vals[lo:hi].copy()))
         out["pairs_k"], out["pairs_v"] = k.numpy().copy(), v.numpy().copy()
         out["stats"] = dict(ctx.last_stats)
+        ops.force_sort_and_cut = True   # the fallback plan must give the same bytes
+        k2, v2 = ctx.sort(torch.from_numpy(keys[lo:hi].copy()), torch.from_numpy(vals[lo:hi].copy()))
+        out["pairs_k2"], out["pairs_v2"] = k2.numpy().copy(), v2.numpy().copy()
+        out["stats2"] = dict(ctx.last_stats)
+        ops.force_sort_and_cut = False
         # --- scans and reductions on unequal blocks (rank 0 gets 1/3) ---
         x = rng.integers(-2**31, 2**31 - 1, size=9001).astype(np.int32)
         cut = 3000
@@ -159,6 +178,9 @@ def test_two_rank_gloo_matches_single_device_oracle():
     ek, ev = oracle.radix_sort(keys, False, vals)
     assert np.concatenate([r["pairs_k"] for r in res]).tobytes() == ek.tobytes()
     assert np.concatenate([r["pairs_v"] for r in res]).tobytes() == ev.tobytes()
+    assert np.concatenate([r["pairs_k2"] for r in res]).tobytes() == ek.tobytes()
+    assert np.concatenate([r["pairs_v2"] for r in res]).tobytes() == ev.tobytes()
+    assert res[0]["stats"]["plan"] == "partition" and res[0]["stats2"]["plan"] == "sort-and-cut"
     assert res[0]["stats"]["imbalance"] < 1.5
     x = rng.integers(-2**31, 2**31 - 1, size=9001).astype(np.int32)
     np.testing.assert_array_equal(np.concatenate([r["excl"] for r in res]), oracle.scan(x, "plus", True, 11))
