@@ -1,0 +1,118 @@
+// radix_common.cuh -- pieces shared by the radix-sort translation units (radix_sort.cu, radix_sort_ns.cu)
+#pragma once
+
+#include "ops.cuh"
+
+namespace bcb {
+
+constexpr int kRadixBits = 8;
+constexpr int kRadixSize = 1 << kRadixBits;
+constexpr int kHistThreads = 512;
+constexpr int kLookbackBatch = 8;  // default look-back batch
+
+enum : unsigned { kLbInvalid = 0u, kLbPartial = 1u, kLbInclusive = 2u };
+
+// order-preserving transform parameters (uniform): key' = ((x ^ nm) - nm) ^ xc ^ (asr(x) & fa)
+constexpr int kMaxSplitters = 7;  // multi-GPU partition pass: up to 8 destinations
+struct Transform {
+    unsigned long long nm;  // all-ones: negate x first (descending signed / float)
+    unsigned long long xc;  // xor constant: sign bit (signed, float) or all-ones (descending unsigned)
+    unsigned long long fa;  // float only: bits below the sign, selected when x is negative
+    // splitter mode (digit = number of splitters <= transformed key): used by the multi-GPU partition pass
+    unsigned long long split[kMaxSplitters];
+    int nsplit;
+};
+
+inline Transform make_transform(int dtype, bool ascending)
+{
+    const unsigned w = (unsigned)dtype_size(dtype) * 8;
+    const unsigned long long ones = (w == 64) ? ~0ull : ((1ull << w) - 1);
+    const unsigned long long sign = 1ull << (w - 1);
+    Transform t{};
+    const bool sgn = dtype_is_signed_int(dtype), flt = dtype_is_float(dtype);
+    if (sgn || flt) {
+        t.xc = sign;
+        if (!ascending) t.nm = ~0ull;
+        if (flt) t.fa = ones & ~sign;
+    } else if (!ascending) {
+        t.xc = ones;
+    }
+    return t;
+}
+
+template <typename K> struct key_traits;
+template <> struct key_traits<unsigned char> { typedef unsigned U; typedef int S; };
+template <> struct key_traits<unsigned short> { typedef unsigned U; typedef int S; };
+template <> struct key_traits<unsigned> { typedef unsigned U; typedef int S; };
+template <> struct key_traits<unsigned long long> { typedef unsigned long long U; typedef long long S; };
+
+template <typename K>
+__device__ __forceinline__ unsigned digit_of(K raw, int shift, const Transform &tf)
+{
+    typedef typename key_traits<K>::U U;
+    typedef typename key_traits<K>::S S;
+    const U x = (U)raw;
+    const U nm = (U)tf.nm;
+    // asr over the compute width: only meaningful (fa != 0) for float / double keys, whose width IS the compute width
+    const U neg = (U)((S)x >> (sizeof(U) * 8 - 1));
+    const U t = ((x ^ nm) - nm) ^ (U)tf.xc ^ (neg & (U)tf.fa);
+    return (unsigned)(t >> shift) & (kRadixSize - 1);
+}
+
+// full transformed key (all digits), for comparisons in the common unsigned order
+template <typename K>
+__device__ __forceinline__ unsigned long long transformed_key(K raw, const Transform &tf)
+{
+    typedef typename key_traits<K>::U U;
+    typedef typename key_traits<K>::S S;
+    const U x = (U)raw;
+    const U nm = (U)tf.nm;
+    const U neg = (U)((S)x >> (sizeof(U) * 8 - 1));
+    const U t = ((x ^ nm) - nm) ^ (U)tf.xc ^ (neg & (U)tf.fa);
+    const unsigned long long ones = sizeof(K) == 8 ? ~0ull : ((1ull << (sizeof(K) * 8 % 64)) - 1);
+    return (unsigned long long)t & ones;
+}
+
+// one thread per splitter: lower bound of the splitter in a sorted range, compared in the transformed space
+template <typename K>
+__global__ void partition_points_kernel(const K *__restrict__ keys, size_t n, const unsigned long long *__restrict__ splitters,
+                                        unsigned num, unsigned long long *__restrict__ points, Transform tf)
+{
+    const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= num) return;
+    const unsigned long long s = splitters[j];
+    size_t lo = 0, hi = n;
+    while (lo < hi) {
+        const size_t mid = lo + (hi - lo) / 2;
+        if (transformed_key<K>(keys[mid], tf) < s) lo = mid + 1;
+        else hi = mid;
+    }
+    points[j] = lo;
+}
+
+// digit modes of the pass kernel: plain bit field (unsigned ascending), transformed bit field, splitter bucket
+enum { kDigitIdent = 1, kDigitTransform = 0, kDigitSplit = 2 };
+
+template <typename K, int IDENT>
+__device__ __forceinline__ unsigned pass_digit(K raw, int shift, const Transform &tf)
+{
+    if constexpr (IDENT == kDigitIdent) {
+        return (unsigned)(raw >> shift) & (kRadixSize - 1);
+    } else if constexpr (IDENT == kDigitSplit) {
+        const unsigned long long t = transformed_key<K>(raw, tf);
+        unsigned d = 0;
+#pragma unroll
+        for (int j = 0; j < kMaxSplitters; j++) d += (j < tf.nsplit && t >= tf.split[j]) ? 1u : 0u;
+        return d;
+    } else {
+        return digit_of<K>(raw, shift, tf);
+    }
+}
+
+
+// nibble-split pass kernel (radix_sort_ns.cu): keys only.  Returns BCB_EUNSUPPORTED for shapes it does not cover.
+int ns_launch_pass(StreamState *st, int key_bytes, const void *kin, void *kout, const unsigned *base, unsigned long long *lookback,
+                   size_t n, int shift, const Transform &tf, int digit_mode);
+size_t ns_tile_size();
+
+}  // namespace bcb

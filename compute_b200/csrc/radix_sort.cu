@@ -18,97 +18,12 @@
 // extracted, because the descending float transform is not invertible (-0.0 and +denorm_min collide).
 // Look-back words are 64-bit {epoch<<2|status, count} so no per-pass initialisation is needed and counts up to
 // 2^32-1 fit.
-#include "ops.cuh"
+#include "radix_common.cuh"
 
 #include <cstdlib>
 #include <cstring>
 
 namespace bcb {
-
-constexpr int kRadixBits = 8;
-constexpr int kRadixSize = 1 << kRadixBits;
-constexpr int kHistThreads = 512;
-constexpr int kLookbackBatch = 8;  // default look-back batch
-
-enum : unsigned { kLbInvalid = 0u, kLbPartial = 1u, kLbInclusive = 2u };
-
-// order-preserving transform parameters (uniform): key' = ((x ^ nm) - nm) ^ xc ^ (asr(x) & fa)
-constexpr int kMaxSplitters = 7;  // multi-GPU partition pass: up to 8 destinations
-struct Transform {
-    unsigned long long nm;  // all-ones: negate x first (descending signed / float)
-    unsigned long long xc;  // xor constant: sign bit (signed, float) or all-ones (descending unsigned)
-    unsigned long long fa;  // float only: bits below the sign, selected when x is negative
-    // splitter mode (digit = number of splitters <= transformed key): used by the multi-GPU partition pass
-    unsigned long long split[kMaxSplitters];
-    int nsplit;
-};
-
-static Transform make_transform(int dtype, bool ascending)
-{
-    const unsigned w = (unsigned)dtype_size(dtype) * 8;
-    const unsigned long long ones = (w == 64) ? ~0ull : ((1ull << w) - 1);
-    const unsigned long long sign = 1ull << (w - 1);
-    Transform t{};
-    const bool sgn = dtype_is_signed_int(dtype), flt = dtype_is_float(dtype);
-    if (sgn || flt) {
-        t.xc = sign;
-        if (!ascending) t.nm = ~0ull;
-        if (flt) t.fa = ones & ~sign;
-    } else if (!ascending) {
-        t.xc = ones;
-    }
-    return t;
-}
-
-template <typename K> struct key_traits;
-template <> struct key_traits<unsigned char> { typedef unsigned U; typedef int S; };
-template <> struct key_traits<unsigned short> { typedef unsigned U; typedef int S; };
-template <> struct key_traits<unsigned> { typedef unsigned U; typedef int S; };
-template <> struct key_traits<unsigned long long> { typedef unsigned long long U; typedef long long S; };
-
-template <typename K>
-__device__ __forceinline__ unsigned digit_of(K raw, int shift, const Transform &tf)
-{
-    typedef typename key_traits<K>::U U;
-    typedef typename key_traits<K>::S S;
-    const U x = (U)raw;
-    const U nm = (U)tf.nm;
-    // asr over the compute width: only meaningful (fa != 0) for float / double keys, whose width IS the compute width
-    const U neg = (U)((S)x >> (sizeof(U) * 8 - 1));
-    const U t = ((x ^ nm) - nm) ^ (U)tf.xc ^ (neg & (U)tf.fa);
-    return (unsigned)(t >> shift) & (kRadixSize - 1);
-}
-
-// full transformed key (all digits), for comparisons in the common unsigned order
-template <typename K>
-__device__ __forceinline__ unsigned long long transformed_key(K raw, const Transform &tf)
-{
-    typedef typename key_traits<K>::U U;
-    typedef typename key_traits<K>::S S;
-    const U x = (U)raw;
-    const U nm = (U)tf.nm;
-    const U neg = (U)((S)x >> (sizeof(U) * 8 - 1));
-    const U t = ((x ^ nm) - nm) ^ (U)tf.xc ^ (neg & (U)tf.fa);
-    const unsigned long long ones = sizeof(K) == 8 ? ~0ull : ((1ull << (sizeof(K) * 8 % 64)) - 1);
-    return (unsigned long long)t & ones;
-}
-
-// one thread per splitter: lower bound of the splitter in a sorted range, compared in the transformed space
-template <typename K>
-__global__ void partition_points_kernel(const K *__restrict__ keys, size_t n, const unsigned long long *__restrict__ splitters,
-                                        unsigned num, unsigned long long *__restrict__ points, Transform tf)
-{
-    const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= num) return;
-    const unsigned long long s = splitters[j];
-    size_t lo = 0, hi = n;
-    while (lo < hi) {
-        const size_t mid = lo + (hi - lo) / 2;
-        if (transformed_key<K>(keys[mid], tf) < s) lo = mid + 1;
-        else hi = mid;
-    }
-    points[j] = lo;
-}
 
 // ---- 1. histogram of all digit positions in one read ------------------------------------------
 template <typename K>
@@ -211,25 +126,6 @@ struct PassSmem {
     static constexpr size_t kSmall = kRadixSize * sizeof(unsigned) + 64;  // out_base + misc
     static constexpr size_t kBytes = kWarpTab + kSmall + (size_t)TILE * kElem + 16;
 };
-
-// digit modes of the pass kernel: plain bit field (unsigned ascending), transformed bit field, splitter bucket
-enum { kDigitIdent = 1, kDigitTransform = 0, kDigitSplit = 2 };
-
-template <typename K, int IDENT>
-__device__ __forceinline__ unsigned pass_digit(K raw, int shift, const Transform &tf)
-{
-    if constexpr (IDENT == kDigitIdent) {
-        return (unsigned)(raw >> shift) & (kRadixSize - 1);
-    } else if constexpr (IDENT == kDigitSplit) {
-        const unsigned long long t = transformed_key<K>(raw, tf);
-        unsigned d = 0;
-#pragma unroll
-        for (int j = 0; j < kMaxSplitters; j++) d += (j < tf.nsplit && t >= tf.split[j]) ? 1u : 0u;
-        return d;
-    } else {
-        return digit_of<K>(raw, shift, tf);
-    }
-}
 
 // Tile layout: 16-lane virtual warp v = tid/16 owns the contiguous segment [v*ITEMS*16, (v+1)*ITEMS*16) of the tile;
 // its lane h holds items i*16 + h.  One warp instruction therefore reads two 64-byte pieces (full 32-byte sectors).
@@ -585,6 +481,21 @@ template <typename K> struct PassConfig<K, 8> { static constexpr int THREADS = 3
 template <typename K> struct PassConfig<K, 16> { static constexpr int THREADS = 384, ITEMS = 8; };
 template <> struct PassConfig<unsigned long long, 4> { static constexpr int THREADS = 384, ITEMS = 12; };
 
+static bool sort_variant_is_default() { const char *e = std::getenv("BCB_SORT_VARIANT"); return !e || std::atoi(e) == 0; }
+
+// BCB_SORT_KERNEL=ns selects the experimental nibble-split pass kernel (radix_sort_ns.cu) for 32/64-bit keys-only
+// sorts.  It is bit-exact but measured SLOWER on B200 (34 vs 53 Gkeys/s: 147 instructions per key make it ALU bound,
+// profiles/r01_sort_pass_ns_nibble_split.txt), so the atomic-OR kernel stays the default.
+static int g_sort_kernel = -1;
+static bool want_ns_kernel()
+{
+    if (g_sort_kernel < 0) {
+        const char *e = std::getenv("BCB_SORT_KERNEL");
+        g_sort_kernel = (e && std::strcmp(e, "ns") == 0) ? 1 : 0;
+    }
+    return g_sort_kernel == 1 && rank_mode() == kRankAtomicOr && sort_variant_is_default();
+}
+
 static int g_sort_variant = -1;  // BCB_SORT_VARIANT: tuning variants of the u32 keys-only pass
 static int sort_variant()
 {
@@ -601,6 +512,9 @@ static int sort_variant()
 template <typename K, int VB>
 static int tile_size_for()
 {
+    if constexpr (VB == 0 && (sizeof(K) == 4 || sizeof(K) == 8)) {
+        if (want_ns_kernel()) return (int)ns_tile_size();
+    }
     if constexpr (sizeof(K) == 4 && VB == 0) {
         switch (sort_variant()) {
 #define X(ID, T, I, LBV, MB) case ID: return T * I;
@@ -616,6 +530,12 @@ template <typename K, int VB>
 static int run_pass(StreamState *st, const void *kin, void *kout, const void *vin, void *vout, const unsigned *base,
                     unsigned long long *lookback, size_t n, int shift, const Transform &tf)
 {
+    if constexpr (VB == 0 && (sizeof(K) == 4 || sizeof(K) == 8)) {
+        if (want_ns_kernel()) {
+            const bool ident = (tf.nm | tf.xc | tf.fa) == 0;
+            return ns_launch_pass(st, (int)sizeof(K), kin, kout, base, lookback, n, shift, tf, ident ? kDigitIdent : kDigitTransform);
+        }
+    }
     if constexpr (sizeof(K) == 4 && VB == 0) {
         switch (sort_variant()) {
 #define X(ID, T, I, LBV, MB) case ID: return launch_pass<K, VB, T, I, LBV, MB>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
