@@ -36,6 +36,7 @@ SIGNATURES = {
     "bcb_workspace_bytes": ([_vp, ctypes.POINTER(_sz)], _i),
     "bcb_workspace_release": ([_vp], _i),
     "bcb_radix_sort": ([_vp, _i, _i, _vp, _sz, _vp, _sz], _i),
+    "bcb_sort_speculation_stats": ([_vp, ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong)], _i),
     "bcb_insertion_sort": ([_vp, _i, _i, _vp, _sz, _vp, _sz], _i),
     "bcb_sort_host": ([_vp, _i, _i, _vp, _sz], _i),
     "bcb_partition_points": ([_vp, _i, _i, _vp, _sz, _vp, _sz, _vp], _i),

@@ -58,6 +58,7 @@ struct StreamState {
     void *pinned_slot = nullptr;      // host address
     void *pinned_slot_dev = nullptr;  // device alias
     int sm_count = 0;
+    unsigned long long spec_runs = 0, spec_fallbacks = 0;  // speculative keys-only sorts: verified runs / re-sorts
     // optional per-kernel timing (bcb_timing_*): CUDA event pairs recorded around each launch
     bool timing = false;
     struct TimedLaunch { int kind; cudaEvent_t start, stop; };

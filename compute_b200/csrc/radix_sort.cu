@@ -446,23 +446,47 @@ static int launch_pass_impl(StreamState *st, const void *kin, void *kout, const 
     return BCB_SUCCESS;
 }
 
-static int g_rank_mode = -1;  // BCB_SORT_RANK=ordered selects the experimental ordered-atomics ranking (u32 keys only)
-static int rank_mode()
+// Speculative ranking for large keys-only sorts (32- and 64-bit keys).
+// The ordered-atomics pass kernel is ~25 % faster than the atomic-OR one but stable only if same-address shared
+// atomics of one warp instruction are applied in lane order (true on every B200 measured, not promised by CUDA).  For a
+// KEYS-ONLY sort that assumption can be CHECKED after the fact: every pass is a permutation whatever order the atomics
+// took, so the output is the correct result if and only if it is sorted by the transformed key.  sort_typed therefore
+// runs the fast passes, verifies sortedness in one extra read (4 B/key), and in the (never observed) failure case
+// simply sorts the buffer again with the deterministic kernel -- re-sorting a permutation of the input gives the same
+// bytes.  Key-value sorts never speculate (stability of the payload cannot be verified from the keys).
+//   BCB_SORT_SPECULATIVE=0       always use the deterministic atomic-OR kernel
+//   BCB_SORT_FORCE_FALLBACK=1    test hook: treat every verification as failed
+constexpr size_t kSpeculativeMinKeys = (size_t)1 << 22;  // below this the sort stays fully asynchronous
+static int g_speculative = -1, g_force_fallback = -1;
+static bool speculative_enabled()
 {
-    if (g_rank_mode < 0) {
-        const char *e = std::getenv("BCB_SORT_RANK");
-        g_rank_mode = (e && std::strcmp(e, "ordered") == 0) ? kRankOrderedAtoms : kRankAtomicOr;
+    if (g_speculative < 0) {
+        const char *e = std::getenv("BCB_SORT_SPECULATIVE");
+        g_speculative = (e && e[0] == '0') ? 0 : 1;
+        const char *f = std::getenv("BCB_SORT_FORCE_FALLBACK");
+        g_force_fallback = (f && f[0] == '1') ? 1 : 0;
     }
-    return g_rank_mode;
+    return g_speculative == 1;
+}
+
+// sortedness by the transformed key (the order the sort is defined by), 128-bit loads
+template <typename K>
+__global__ void __launch_bounds__(256) verify_sorted_kernel(const K *__restrict__ keys, size_t n, Transform tf, int *flag)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    int bad = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i + 1 < n; i += stride)
+        bad |= transformed_key<K>(__ldg(keys + i), tf) > transformed_key<K>(__ldg(keys + i + 1), tf);
+    if (bad) *flag = 1;
 }
 
 template <typename K, int VB, int THREADS, int ITEMS, int LBATCH = kLookbackBatch, int MINB = default_min_blocks(THREADS)>
 static int launch_pass(StreamState *st, const void *kin, void *kout, const void *vin, void *vout, const unsigned *base,
-                       unsigned long long *lookback, size_t n, int shift, const Transform &tf)
+                       unsigned long long *lookback, size_t n, int shift, const Transform &tf, int rank)
 {
     const bool ident = (tf.nm | tf.xc | tf.fa) == 0;  // unsigned ascending keys: the digit is a plain bit field
-    if constexpr (sizeof(K) == 4 && VB == 0) {
-        if (rank_mode() == kRankOrderedAtoms) {
+    if constexpr ((sizeof(K) == 4 || sizeof(K) == 8) && VB == 0) {
+        if (rank == kRankOrderedAtoms) {
             return ident ? launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankOrderedAtoms, kDigitIdent, MINB>(st, kin, kout, vin, vout, base, lookback, n, shift, tf)
                          : launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankOrderedAtoms, kDigitTransform, MINB>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
         }
@@ -493,7 +517,7 @@ static bool want_ns_kernel()
         const char *e = std::getenv("BCB_SORT_KERNEL");
         g_sort_kernel = (e && std::strcmp(e, "ns") == 0) ? 1 : 0;
     }
-    return g_sort_kernel == 1 && rank_mode() == kRankAtomicOr && sort_variant_is_default();
+    return g_sort_kernel == 1 && sort_variant_is_default();
 }
 
 static int g_sort_variant = -1;  // BCB_SORT_VARIANT: tuning variants of the u32 keys-only pass
@@ -528,24 +552,24 @@ static int tile_size_for()
 
 template <typename K, int VB>
 static int run_pass(StreamState *st, const void *kin, void *kout, const void *vin, void *vout, const unsigned *base,
-                    unsigned long long *lookback, size_t n, int shift, const Transform &tf)
+                    unsigned long long *lookback, size_t n, int shift, const Transform &tf, int rank)
 {
     if constexpr (VB == 0 && (sizeof(K) == 4 || sizeof(K) == 8)) {
-        if (want_ns_kernel()) {
+        if (want_ns_kernel() && rank == kRankAtomicOr) {
             const bool ident = (tf.nm | tf.xc | tf.fa) == 0;
             return ns_launch_pass(st, (int)sizeof(K), kin, kout, base, lookback, n, shift, tf, ident ? kDigitIdent : kDigitTransform);
         }
     }
     if constexpr (sizeof(K) == 4 && VB == 0) {
         switch (sort_variant()) {
-#define X(ID, T, I, LBV, MB) case ID: return launch_pass<K, VB, T, I, LBV, MB>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
+#define X(ID, T, I, LBV, MB) case ID: return launch_pass<K, VB, T, I, LBV, MB>(st, kin, kout, vin, vout, base, lookback, n, shift, tf, rank);
             BCB_U32_VARIANTS(X)
 #undef X
         default: break;
         }
     }
     return launch_pass<K, VB, PassConfig<K, VB>::THREADS, PassConfig<K, VB>::ITEMS>(st, kin, kout, vin, vout, base, lookback, n,
-                                                                                     shift, tf);
+                                                                                     shift, tf, rank);
 }
 
 // ---- multi-GPU partition pass: bucket histogram by splitters ---------------------------------------------
@@ -617,9 +641,17 @@ static int partition_by_value_size(StreamState *st, const void *kin, void *kout,
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 template <typename K, int VB>
-static int sort_typed(StreamState *st, void *keys, void *values, size_t n, const Transform &tf)
+static int sort_typed(StreamState *st, void *keys, void *values, size_t n, const Transform &tf, int rank = -1)
 {
     constexpr int NPASS = sizeof(K);
+    if (rank < 0) {
+        rank = kRankAtomicOr;
+        if constexpr (VB == 0 && (sizeof(K) == 4 || sizeof(K) == 8)) {
+            if (speculative_enabled() && n >= kSpeculativeMinKeys && !want_ns_kernel() && sort_variant_is_default()) rank = kRankOrderedAtoms;
+            const char *e = std::getenv("BCB_SORT_RANK");  // explicit override for experiments
+            if (e && std::strcmp(e, "ordered") == 0) rank = kRankOrderedAtoms;
+        }
+    }
     const size_t kbytes = align_up(n * sizeof(K), 256);
     const size_t vbytes = align_up(n * (size_t)VB, 256);
     void *scratch;
@@ -653,13 +685,34 @@ static int sort_typed(StreamState *st, void *keys, void *values, size_t n, const
     }
     void *kin = keys, *kout = tmp_keys, *vin = values, *vout = tmp_vals;
     for (int p = 0; p < NPASS; p++) {
-        BCB_TRY((run_pass<K, VB>(st, kin, kout, vin, vout, base + p * kRadixSize, (unsigned long long *)lb, n, p * kRadixBits, tf)));
+        BCB_TRY((run_pass<K, VB>(st, kin, kout, vin, vout, base + p * kRadixSize, (unsigned long long *)lb, n, p * kRadixBits, tf, rank)));
         void *t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;
     }
     if (kin != keys) {  // odd pass count (8-bit keys): result is in the temporary
         BCB_CUDA_TRY(cudaMemcpyAsync(keys, kin, n * sizeof(K), cudaMemcpyDeviceToDevice, st->stream));
         if (VB) BCB_CUDA_TRY(cudaMemcpyAsync(values, vin, n * (size_t)VB, cudaMemcpyDeviceToDevice, st->stream));
+    }
+    if constexpr (VB == 0 && (sizeof(K) == 4 || sizeof(K) == 8)) {
+        if (rank == kRankOrderedAtoms) {
+            // verify the speculation (see above); on failure sort again with the deterministic kernel
+            int *flag = (int *)st->pinned_slot_dev;
+            *(volatile int *)st->pinned_slot = 0;
+            size_t blocks = (n + 256 * 8 - 1) / (256 * 8);
+            const size_t cap = (size_t)st->sm_count * 8;
+            if (blocks > cap) blocks = cap;
+            {
+                LaunchTimer timer(st, BCB_K_OTHER);
+                verify_sorted_kernel<K><<<(unsigned)blocks, 256, 0, st->stream>>>((const K *)keys, n, tf, flag);
+            }
+            BCB_CUDA_TRY(cudaGetLastError());
+            BCB_CUDA_TRY(cudaStreamSynchronize(st->stream));
+            st->spec_runs++;
+            if (*(volatile int *)st->pinned_slot != 0 || g_force_fallback == 1) {
+                st->spec_fallbacks++;
+                return sort_typed<K, VB>(st, keys, values, n, tf, kRankAtomicOr);
+            }
+        }
     }
     return BCB_SUCCESS;
 }
@@ -786,6 +839,15 @@ int bcb_partition_points(bcb_stream stream, int key_dtype, int ascending, const 
     if (rc == BCB_SUCCESS && e != cudaSuccess) rc = (int)e;
     if (rc != BCB_SUCCESS) (void)cudaGetLastError();
     return rc;
+}
+
+int bcb_sort_speculation_stats(bcb_stream stream, unsigned long long *runs, unsigned long long *fallbacks)
+{
+    StreamState *st;
+    BCB_TRY(stream_state((cudaStream_t)stream, &st));
+    if (runs) *runs = st->spec_runs;
+    if (fallbacks) *fallbacks = st->spec_fallbacks;
+    return BCB_SUCCESS;
 }
 
 int bcb_partition_by_splitters(bcb_stream stream, int key_dtype, int ascending, const void *keys_in, void *keys_out,

@@ -106,6 +106,11 @@ BCB_API int bcb_workspace_release(bcb_stream stream);
  * value_bytes is sizeof(T2), any size >= 1.  ascending != 0 sorts by less<T>, 0 by greater<T>. */
 BCB_API int bcb_radix_sort(bcb_stream stream, int key_dtype, int ascending, void *keys, size_t n,
                    void *values, size_t value_bytes);
+/* Large keys-only sorts of 32/64-bit keys run a faster, speculatively stable pass kernel, verify the result (sorted by
+ * the transformed key <=> correct, because every pass is a permutation) and fall back to the deterministic kernel if the
+ * check fails; such calls block until the verification is done.  These counters report how often that happened on the
+ * stream.  BCB_SORT_SPECULATIVE=0 in the environment disables speculation. */
+BCB_API int bcb_sort_speculation_stats(bcb_stream stream, unsigned long long *verified_runs, unsigned long long *fallbacks);
 /* detail::serial_insertion_sort / _by_key (algorithm/detail/insertion_sort.hpp:25-159): one thread, native compare.
  * greater != 0 uses ">" (descending).  n <= 4096. */
 BCB_API int bcb_insertion_sort(bcb_stream stream, int key_dtype, int greater, void *keys, size_t n,

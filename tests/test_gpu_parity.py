@@ -278,3 +278,40 @@ def test_accumulate_paths(gpu):
     assert gpu.accumulate(f, np.int32(0), "plus", op_dtype=np.float32, acc_dtype=np.int32) == \
         oracle.accumulate(f, np.int32(0), "plus", op_dtype=np.float32, acc_dtype=np.int32)
     assert gpu.accumulate(np.empty(0, np.int32), np.int32(9), "plus") == 9
+
+
+# ------------------------------------------------------------------------------------------ speculative keys-only sorts
+@pytest.mark.parametrize("dtype", ["uint", "int", "float", "ulong", "double"])
+def test_large_keys_only_sort_speculative_path_bit_exact(dtype, gpu):
+    """n >= 2^22 keys-only sorts take the speculative (verified) pass kernel; results must stay byte-exact."""
+    n = (1 << 22) + 12345
+    for desc, mode in ((False, "bits"), (True, "few")):
+        k = random_keys(dtype, n, seed=17, mode=mode)
+        assert gpu.radix_sort(k, desc).tobytes() == oracle.radix_sort(k, desc).tobytes(), (dtype, desc, mode)
+    import ctypes
+    import compute_b200 as cb
+    runs, falls = ctypes.c_ulonglong(), ctypes.c_ulonglong()
+    cb.lib().bcb_sort_speculation_stats(cb.command_queue().handle, ctypes.byref(runs), ctypes.byref(falls))
+    assert runs.value >= 1 and falls.value == 0, (runs.value, falls.value)
+
+
+def test_speculation_fallback_path_in_subprocess():
+    """BCB_SORT_FORCE_FALLBACK=1 makes every verification 'fail': the deterministic re-sort must give the same bytes."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, ctypes, numpy as np\n"
+        f"sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r})\n"
+        "import gpu_api, oracle, compute_b200 as cb\n"
+        "rng = np.random.default_rng(3)\n"
+        "k = rng.integers(0, 2**32, size=(1 << 22) + 777, dtype=np.uint32)\n"
+        "k[::3] = k[0]\n"
+        "assert gpu_api.radix_sort(k).tobytes() == oracle.radix_sort(k).tobytes()\n"
+        "r, f = ctypes.c_ulonglong(), ctypes.c_ulonglong()\n"
+        "cb.lib().bcb_sort_speculation_stats(cb.command_queue().handle, ctypes.byref(r), ctypes.byref(f))\n"
+        "assert r.value == 1 and f.value == 1, (r.value, f.value)\n"
+        "print('FALLBACK_OK')\n"
+    )
+    env = dict(os.environ, BCB_SORT_FORCE_FALLBACK="1")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0 and "FALLBACK_OK" in out.stdout, out.stdout + out.stderr
