@@ -366,12 +366,21 @@ def ours(args):
     else:
         kname, per_elem = "reduce", bpe
     k_ms, k_cnt = kt[kname]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch of the dominant kernel, from ncu
+    if os.path.exists(tpath):
+        try:
+            t = json.load(open(tpath)).get(args.workload)
+            if t and int(t.get("n_per_gpu", -1)) == int(n_local):
+                traffic = t["dram_bytes_per_launch"]
+        except Exception:
+            traffic = None
     roofline = None
     if k_cnt:
         avg_ms = k_ms / k_cnt
         achieved = (n_local * per_elem / 1e9) / (avg_ms / 1e3)
         roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "avg_launch_ms": avg_ms, "launches": int(k_cnt),
+                    "traffic": traffic, "peak_source": peak_src, "avg_launch_ms": avg_ms, "launches": int(k_cnt),
                     "algorithmic_bytes_per_launch": int(n_local * per_elem),
                     "whole_step": {"algorithmic_bytes": int(n_local * bpe), "achieved": (n_local * bpe / 1e9) / (ms_per_step / 1e3),
                                    "frac": (n_local * bpe / 1e9) / (ms_per_step / 1e3) / peak},
@@ -382,6 +391,11 @@ def ours(args):
     if world == 1 and not args.no_e2e:
         e2e = e2e_run(args, cb, L, stream, kind, dt, vb, n_local, pristine, unit, bpe)
 
+    spec = None
+    if kind == "sort":
+        r_, f_ = ctypes.c_ulonglong(), ctypes.c_ulonglong()
+        check(L.bcb_sort_speculation_stats(stream, ctypes.byref(r_), ctypes.byref(f_)))
+        spec = {"verified_runs": int(r_.value), "fallbacks": int(f_.value)}
     if rank == 0:
         line = {
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -391,7 +405,7 @@ def ours(args):
                        "distribution": "uniform random, seed 12345+rank", "l2": "inputs >> L2 (no flush needed)",
                        "timing": "CUDA events per step on the launching stream, input reset outside the timed region",
                        "parallelism": f"{world} process(es), one per GPU"},
-            "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches), "verified": verified,
+            "roofline": roofline, "sort_speculation": spec, "clocks": clocks, "gpu_launches": int(launches), "verified": verified,
             "step_ms": step_ms, "e2e": e2e,
         }
         if world == 1 and not args.no_cpu:

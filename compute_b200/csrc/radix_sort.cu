@@ -119,7 +119,10 @@ template <> struct value_type<16> { typedef uint4 type; };
 template <typename K, int VB, int THREADS, int ITEMS, int RANK>
 struct PassSmem {
     static constexpr int WARPS = THREADS / 32;
-    static constexpr int VWARPS = THREADS / 16;  // 16-lane "virtual warps": one digit table and one key segment each
+    // lanes per "virtual warp" (one digit table and one contiguous key segment each): 16 for the atomic-OR ranking,
+    // whose {count:16 | mask:16} entries need a 16-bit peer mask; a full warp for the ordered-atomics ranking
+    static constexpr int VWL = (RANK == kRankAtomicOr) ? 16 : 32;
+    static constexpr int VWARPS = THREADS / VWL;
     static constexpr int TILE = THREADS * ITEMS;
     static constexpr size_t kElem = (sizeof(K) > (size_t)VB) ? sizeof(K) : (size_t)VB;
     static constexpr size_t kWarpTab = (size_t)VWARPS * kRadixSize * sizeof(unsigned);
@@ -129,26 +132,26 @@ struct PassSmem {
 
 // Tile layout: 16-lane virtual warp v = tid/16 owns the contiguous segment [v*ITEMS*16, (v+1)*ITEMS*16) of the tile;
 // its lane h holds items i*16 + h.  One warp instruction therefore reads two 64-byte pieces (full 32-byte sectors).
-template <int ITEMS>
+template <int ITEMS, int VWL>
 __device__ __forceinline__ unsigned tile_offset_of_item0()
 {
-    return (threadIdx.x >> 4) * (ITEMS * 16) + (threadIdx.x & 15u);
+    return (threadIdx.x / VWL) * (ITEMS * VWL) + (threadIdx.x % VWL);
 }
 
-template <typename K, int THREADS, int ITEMS>
+template <typename K, int THREADS, int ITEMS, int VWL>
 __device__ __forceinline__ void load_tile_keys(const K *__restrict__ keys_in, size_t n, size_t tile, K (&key)[ITEMS])
 {
     constexpr int TILE = THREADS * ITEMS;
     const size_t tile_base = tile * (size_t)TILE;
-    const unsigned off0 = tile_offset_of_item0<ITEMS>();
+    const unsigned off0 = tile_offset_of_item0<ITEMS, VWL>();
     if (tile_base + TILE <= n) {
 #pragma unroll
-        for (int i = 0; i < ITEMS; i++) key[i] = __ldg(keys_in + tile_base + off0 + i * 16);
+        for (int i = 0; i < ITEMS; i++) key[i] = __ldg(keys_in + tile_base + off0 + i * VWL);
     } else {
         const unsigned valid = (unsigned)(n - tile_base);
 #pragma unroll
         for (int i = 0; i < ITEMS; i++) {
-            const unsigned t = off0 + i * 16;
+            const unsigned t = off0 + i * VWL;
             key[i] = t < valid ? __ldg(keys_in + tile_base + t) : (K)0;
         }
     }
@@ -173,11 +176,11 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
     // (a 32-bit entry keeps every access a single-wavefront-per-bank operation); kRankOrderedAtoms stores the count.
     unsigned *tab = reinterpret_cast<unsigned *>(smem_raw);  // [VWARPS][256]
     constexpr int CSHIFT = (RANK == kRankAtomicOr) ? 16 : 0;
-    constexpr int VWARPS = L::VWARPS;
-    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, vwarp = tid >> 4;
+    constexpr int VWARPS = L::VWARPS, VWL = L::VWL;
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, vwarp = tid / VWL;
     const size_t tile_base = tile * (size_t)TILE;
     const unsigned valid = FULL ? (unsigned)TILE : (unsigned)(n - tile_base);
-    const unsigned off0 = tile_offset_of_item0<ITEMS>();  // in-tile index of this thread's item 0; item i is off0 + 16*i
+    const unsigned off0 = tile_offset_of_item0<ITEMS, VWL>();  // in-tile index of this thread's item 0; item i is off0 + VWL*i
     unsigned *wt = tab + vwarp * kRadixSize;
 
     // key[] already holds this tile's keys (loaded by the caller / prefetched during the previous tile).
@@ -191,7 +194,7 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
 #pragma unroll
         for (int i = 0; i < ITEMS; i++) {
             unsigned d = pass_digit<K, IDENT>(key[i], shift, tf);
-            if (!FULL && off0 + i * 16 >= valid) d = kRadixSize - 1;  // padding sorts last within the tile
+            if (!FULL && off0 + i * VWL >= valid) d = kRadixSize - 1;  // padding sorts last within the tile
             atomicOr(&wt[d], hbit);
             __syncwarp();
             const unsigned e = wt[d];  // {keys of digit d in earlier rounds : 16 | peers in this round : 16}
@@ -205,7 +208,7 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
 #pragma unroll
         for (int i = 0; i < ITEMS; i++) {
             unsigned d = pass_digit<K, IDENT>(key[i], shift, tf);
-            if (!FULL && off0 + i * 16 >= valid) d = kRadixSize - 1;
+            if (!FULL && off0 + i * VWL >= valid) d = kRadixSize - 1;
             rank[i] = (unsigned short)atomicAdd(&wt[d], 1u);
         }
     }
@@ -249,7 +252,7 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
         unsigned d = pass_digit<K, IDENT>(key[i], shift, tf);
-        if (!FULL && off0 + i * 16 >= valid) d = kRadixSize - 1;
+        if (!FULL && off0 + i * VWL >= valid) d = kRadixSize - 1;
         const unsigned pos = (wt[d] >> CSHIFT) + rank[i];
         rank[i] = (unsigned short)pos;
         keys_sorted[pos] = key[i];
@@ -259,7 +262,7 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
     // the store phase of this tile, so a tile never waits for its own input ----
     {
         const size_t next = tile + gridDim.x;  // round-robin tile assignment (see onesweep_pass)
-        if (next < num_tiles) load_tile_keys<K, THREADS, ITEMS>(keys_in, n, next, key);
+        if (next < num_tiles) load_tile_keys<K, THREADS, ITEMS, PassSmem<K, VB, THREADS, ITEMS, RANK>::VWL>(keys_in, n, next, key);
     }
 
     // ---- decoupled look-back (threads 0..255, one digit each).  The keys already sit in shared memory, so
@@ -320,13 +323,13 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
         V val[ITEMS];
 #pragma unroll
         for (int i = 0; i < ITEMS; i++) {
-            const unsigned t = off0 + i * 16;
+            const unsigned t = off0 + i * VWL;
             if (FULL || t < valid) val[i] = vals_in[tile_base + t];
         }
         __syncthreads();  // everyone is done reading keys_sorted
 #pragma unroll
         for (int i = 0; i < ITEMS; i++) {
-            const unsigned t = off0 + i * 16;
+            const unsigned t = off0 + i * VWL;
             if (FULL || t < valid) vals_sorted[rank[i]] = val[i];
         }
         __syncthreads();
@@ -355,7 +358,7 @@ onesweep_pass(const K *__restrict__ keys_in, K *__restrict__ keys_out, const voi
 
     size_t tile = blockIdx.x;
     K key[ITEMS];
-    if (tile < num_tiles) load_tile_keys<K, THREADS, ITEMS>(keys_in, n, tile, key);
+    if (tile < num_tiles) load_tile_keys<K, THREADS, ITEMS, L::VWL>(keys_in, n, tile, key);
     for (; tile < num_tiles; tile += gridDim.x) {
         // zero the digit tables (the previous tile left offsets in them)
         {
@@ -473,10 +476,30 @@ static bool speculative_enabled()
 template <typename K>
 __global__ void __launch_bounds__(256) verify_sorted_kernel(const K *__restrict__ keys, size_t n, Transform tf, int *flag)
 {
+    constexpr int VEC = 16 / sizeof(K);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     int bad = 0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i + 1 < n; i += stride)
-        bad |= transformed_key<K>(__ldg(keys + i), tf) > transformed_key<K>(__ldg(keys + i + 1), tf);
+    if ((((uintptr_t)keys) & 15) == 0) {
+        const size_t nvec = n / VEC;
+        for (size_t v = gid; v < nvec; v += stride) {
+            const uint4 x = ld_stream_v4(keys + v * VEC);
+            const K *e = reinterpret_cast<const K *>(&x);
+            unsigned long long prev = transformed_key<K>(e[0], tf);
+#pragma unroll
+            for (int k = 1; k < VEC; k++) {
+                const unsigned long long cur = transformed_key<K>(e[k], tf);
+                bad |= prev > cur;
+                prev = cur;
+            }
+            if ((v + 1) * VEC < n) bad |= prev > transformed_key<K>(__ldg(keys + (v + 1) * VEC), tf);  // seam to the next vector
+        }
+        for (size_t i = nvec * VEC + gid; i + 1 < n; i += stride)
+            bad |= transformed_key<K>(__ldg(keys + i), tf) > transformed_key<K>(__ldg(keys + i + 1), tf);
+    } else {
+        for (size_t i = gid; i + 1 < n; i += stride)
+            bad |= transformed_key<K>(__ldg(keys + i), tf) > transformed_key<K>(__ldg(keys + i + 1), tf);
+    }
     if (bad) *flag = 1;
 }
 
@@ -698,7 +721,7 @@ static int sort_typed(StreamState *st, void *keys, void *values, size_t n, const
             // verify the speculation (see above); on failure sort again with the deterministic kernel
             int *flag = (int *)st->pinned_slot_dev;
             *(volatile int *)st->pinned_slot = 0;
-            size_t blocks = (n + 256 * 8 - 1) / (256 * 8);
+            size_t blocks = (n + 256 * 16 - 1) / (256 * 16);
             const size_t cap = (size_t)st->sm_count * 8;
             if (blocks > cap) blocks = cap;
             {

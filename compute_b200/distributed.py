@@ -241,13 +241,11 @@ class Context:
             send = exchange_plan(points, n_local)
             src_keys, src_vals = keys, values
             plan = "sort-and-cut"
-        plans = self._all_gather_np(np.array([1 if plan == "partition" else 0], dtype=np.int32)).reshape(-1)
         counts = self._all_gather_np(np.asarray(send, dtype=np.int64))          # counts[src][dst]
         recv = counts[:, self.rank].copy()
         # exchange: contiguous slices, received in source-rank order
         out_keys = self._all_to_all(src_keys, send, recv)
         out_vals = self._all_to_all(src_vals, send, recv) if values is not None else None
-        _ = plans
         # 5. final local stable sort of the P received runs
         self.ops.sort(out_keys, out_vals, descending)
         self.last_stats = {"plan": plan, "sent": int(send.sum() - send[self.rank]), "received": int(recv.sum()),
