@@ -473,33 +473,52 @@ static bool speculative_enabled()
 }
 
 // sortedness by the transformed key (the order the sort is defined by), 128-bit loads
-template <typename K>
+template <typename K, bool IDENT>
+__device__ __forceinline__ typename key_traits<K>::U verify_key(K raw, const Transform &tf)
+{
+    typedef typename key_traits<K>::U U;
+    if constexpr (IDENT) return (U)raw;
+    else return (U)transformed_key<K>(raw, tf);
+}
+
+// coalesced 128-bit loads (lane l of a warp reads vector base + l); the seam to the next vector comes from the
+// neighbouring lane by shuffle, only lane 31 touches memory for it
+template <typename K, bool IDENT>
 __global__ void __launch_bounds__(256) verify_sorted_kernel(const K *__restrict__ keys, size_t n, Transform tf, int *flag)
 {
+    typedef typename key_traits<K>::U U;
     constexpr int VEC = 16 / sizeof(K);
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const size_t warp_id = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int bad = 0;
+    size_t done = 0;
     if ((((uintptr_t)keys) & 15) == 0) {
         const size_t nvec = n / VEC;
-        for (size_t v = gid; v < nvec; v += stride) {
-            const uint4 x = ld_stream_v4(keys + v * VEC);
+        for (size_t base = warp_id * 32; base < nvec; base += warps * 32) {  // warp-uniform trip count
+            const size_t v = base + lane;
+            const bool in = v < nvec;
+            uint4 x = make_uint4(0, 0, 0, 0);
+            if (in) x = ld_stream_v4(keys + v * VEC);
             const K *e = reinterpret_cast<const K *>(&x);
-            unsigned long long prev = transformed_key<K>(e[0], tf);
+            U k[VEC];
 #pragma unroll
-            for (int k = 1; k < VEC; k++) {
-                const unsigned long long cur = transformed_key<K>(e[k], tf);
-                bad |= prev > cur;
-                prev = cur;
+            for (int j = 0; j < VEC; j++) k[j] = verify_key<K, IDENT>(e[j], tf);
+#pragma unroll
+            for (int j = 1; j < VEC; j++) bad |= in && (k[j - 1] > k[j]);
+            U next = __shfl_down_sync(0xffffffffu, k[0], 1);
+            bool has_next = (v + 1) < nvec;
+            if (lane == 31 && in && (v + 1) * VEC < n) {  // seam across the warp's 32 vectors (and into the scalar tail)
+                next = verify_key<K, IDENT>(__ldg(keys + (v + 1) * VEC), tf);
+                has_next = true;
             }
-            if ((v + 1) * VEC < n) bad |= prev > transformed_key<K>(__ldg(keys + (v + 1) * VEC), tf);  // seam to the next vector
+            bad |= in && has_next && (k[VEC - 1] > next);
         }
-        for (size_t i = nvec * VEC + gid; i + 1 < n; i += stride)
-            bad |= transformed_key<K>(__ldg(keys + i), tf) > transformed_key<K>(__ldg(keys + i + 1), tf);
-    } else {
-        for (size_t i = gid; i + 1 < n; i += stride)
-            bad |= transformed_key<K>(__ldg(keys + i), tf) > transformed_key<K>(__ldg(keys + i + 1), tf);
+        done = nvec * VEC;
     }
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (done ? done - 1 : 0) + gid; i + 1 < n; i += stride)  // tail, including the seam into it
+        bad |= verify_key<K, IDENT>(__ldg(keys + i), tf) > verify_key<K, IDENT>(__ldg(keys + i + 1), tf);
     if (bad) *flag = 1;
 }
 
@@ -724,9 +743,13 @@ static int sort_typed(StreamState *st, void *keys, void *values, size_t n, const
             size_t blocks = (n + 256 * 16 - 1) / (256 * 16);
             const size_t cap = (size_t)st->sm_count * 8;
             if (blocks > cap) blocks = cap;
+            if (blocks < 1) blocks = 1;
             {
                 LaunchTimer timer(st, BCB_K_OTHER);
-                verify_sorted_kernel<K><<<(unsigned)blocks, 256, 0, st->stream>>>((const K *)keys, n, tf, flag);
+                if ((tf.nm | tf.xc | tf.fa) == 0)
+                    verify_sorted_kernel<K, true><<<(unsigned)blocks, 256, 0, st->stream>>>((const K *)keys, n, tf, flag);
+                else
+                    verify_sorted_kernel<K, false><<<(unsigned)blocks, 256, 0, st->stream>>>((const K *)keys, n, tf, flag);
             }
             BCB_CUDA_TRY(cudaGetLastError());
             BCB_CUDA_TRY(cudaStreamSynchronize(st->stream));

@@ -6,7 +6,8 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 echo "== dram traffic per launch"
 for w in sort_u32 scan_i32 reduce_i32; do
   case $w in sort_u32) k=onesweep_pass;; scan_i32) k=scan_tma;; reduce_i32) k=reduce_kernel;; esac
-  timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:$k -s 4 -c 1 --csv --log-file gpurun_out/traffic_$w.csv python bench.py --workload $w --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/traffic_$w.log 2>&1
+  if [ $w = sort_u32 ]; then skip=4; else skip=1; fi
+  timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:$k -s $skip -c 1 --csv --log-file gpurun_out/traffic_$w.csv python bench.py --workload $w --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/traffic_$w.log 2>&1
   tail -4 gpurun_out/traffic_$w.csv | cut -c1-300
 done
 echo "== full ncu of final kernels"

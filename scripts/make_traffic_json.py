@@ -10,6 +10,8 @@ for w, n in sizes.items():
     if not os.path.exists(p):
         continue
     rows = [r for r in csv.reader(open(p)) if len(r) > 5]
+    if len(rows) < 2:
+        continue
     hdr = rows[0]
     mi, vi, ui, ki = hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit"), hdr.index("Kernel Name")
     scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
