@@ -228,8 +228,8 @@ def ours(args):
     gen = torch.Generator(device="cuda")
     gen.manual_seed(12345 + rank)
     if kind == "sort":
-        scaling = "strong"  # the 2^30 keys of the named config are sharded over the ranks
-        n_local = n_total // world
+        scaling = "weak"  # every rank holds one block of 2^log2n keys of the global range (N x 2^30 keys in total)
+        n_local = n_total
         if dt == "ulong":
             pristine = torch.randint(-2**63, 2**63 - 1, (n_local,), dtype=torch.int64, device="cuda", generator=gen).view(tdt)
         elif dt == "float":
@@ -345,6 +345,26 @@ def ours(args):
             verified = bool(ok_sorted and s0 == s1 and x0 == x1)
         else:
             verified = bool(ok_sorted)
+    elif kind == "sort":
+        # global check: every shard sorted, shard boundaries in order, multiset checksums (sum, xor) preserved
+        out = result_holder["out"][0] if vb else result_holder["out"]
+        ok_local = bool(cb.is_sorted(out)) if out.numel() else True
+        bits = out.view(torch.int32 if out.element_size() == 4 else torch.int64)
+        ends = torch.zeros(3, dtype=torch.int64, device="cuda")
+        if out.numel():
+            tk = cbd.transformed_keys(bits[[0, -1]].cpu().numpy().view(np.uint32 if out.element_size() == 4 else np.uint64),
+                                      cb.dtype_code(out.dtype), True)
+            ends = torch.tensor([1, int(tk[0]) - 2**63, int(tk[1]) - 2**63], dtype=torch.int64, device="cuda")
+        all_ends = [torch.zeros_like(ends) for _ in range(world)]
+        dist.all_gather(all_ends, ends)
+        seq = [(int(e[1]), int(e[2])) for e in all_ends if int(e[0])]
+        ok_edges = all(seq[i][1] <= seq[i + 1][0] for i in range(len(seq) - 1))
+        pb = pristine.view(bits.dtype)
+        chk = torch.stack([pb.sum(dtype=torch.int64) - bits.sum(dtype=torch.int64),
+                           torch.tensor(int(pb.numel() - bits.numel()), device="cuda"),
+                           torch.tensor(0 if ok_local else 1, device="cuda")])
+        dist.all_reduce(chk)
+        verified = bool(ok_edges and int(chk[0]) == 0 and int(chk[1]) == 0 and int(chk[2]) == 0)
     elif kind == "scan" and world == 1:
         m = 1 << 20
         import oracle
@@ -354,7 +374,7 @@ def ours(args):
 
     peak, peak_src = measured_peaks()
     if unit == "Gkeys/s":
-        value = (n_total / 1e9) / (ms_per_step / 1e3)
+        value = (n_local * world / 1e9) / (ms_per_step / 1e3)
     else:
         value = (n_local * world * bpe / 1e9) / (ms_per_step / 1e3)
 
@@ -401,13 +421,15 @@ def ours(args):
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": {"uint": "u32", "float": "f32", "ulong": "u64", "int": "i32"}[dt], "data": "synthetic",
-            "config": {"workload": args.workload, "n": n_total, "n_per_gpu": n_local, "value_bytes": vb,
+            "config": {"workload": args.workload, "n": n_local * world, "n_per_gpu": n_local, "value_bytes": vb,
                        "distribution": "uniform random, seed 12345+rank", "l2": "inputs >> L2 (no flush needed)",
                        "timing": "CUDA events per step on the launching stream, input reset outside the timed region",
                        "parallelism": f"{world} process(es), one per GPU"},
             "roofline": roofline, "sort_speculation": spec, "clocks": clocks, "gpu_launches": int(launches), "verified": verified,
             "step_ms": step_ms, "e2e": e2e,
         }
+        if world > 1 and kind == "sort":
+            line["distributed"] = ctx.last_stats
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args.workload)
         print(json.dumps(line), flush=True)

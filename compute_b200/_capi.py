@@ -36,11 +36,18 @@ SIGNATURES = {
     "bcb_workspace_bytes": ([_vp, ctypes.POINTER(_sz)], _i),
     "bcb_workspace_release": ([_vp], _i),
     "bcb_radix_sort": ([_vp, _i, _i, _vp, _sz, _vp, _sz], _i),
+    "bcb_radix_sort_copy": ([_vp, _i, _i, _vp, _vp, _sz, _vp, _vp, _sz], _i),
     "bcb_sort_speculation_stats": ([_vp, ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong)], _i),
+    "bcb_is_sorted_by_radix_key": ([_vp, _i, _i, _vp, _sz, _pi], _i),
     "bcb_insertion_sort": ([_vp, _i, _i, _vp, _sz, _vp, _sz], _i),
     "bcb_sort_host": ([_vp, _i, _i, _vp, _sz], _i),
     "bcb_partition_points": ([_vp, _i, _i, _vp, _sz, _vp, _sz, _vp], _i),
     "bcb_partition_by_splitters": ([_vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _sz, _vp, _sz, _vp], _i),
+    "bcb_partition_counts": ([_vp, _i, _i, _vp, _sz, _vp, _sz, _vp], _i),
+    "bcb_partition_scatter": ([_vp, _i, _i, _vp, _vp, _sz, _sz, _vp, _sz, _vp, _vp], _i),
+    "bcb_ipc_export": ([_vp, _vp], _i),
+    "bcb_ipc_open": ([_vp, ctypes.POINTER(_vp)], _i),
+    "bcb_ipc_close": ([_vp], _i),
     "bcb_scan": ([_vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp], _i),
     "bcb_reduce": ([_vp, _i, _i, _i, _vp, _sz, _vp, _i], _i),
     "bcb_accumulate": ([_vp, _i, _i, _i, _i, _vp, _sz, _vp, _vp], _i),

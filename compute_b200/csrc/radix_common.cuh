@@ -21,6 +21,10 @@ struct Transform {
     // splitter mode (digit = number of splitters <= transformed key): used by the multi-GPU partition pass
     unsigned long long split[kMaxSplitters];
     int nsplit;
+    // splitter mode only: where bucket b goes (device addresses; other GPUs' memory when the multi-GPU sort scatters
+    // straight into its peers' receive buffers over NVLink)
+    unsigned long long dst_keys[kMaxSplitters + 1];
+    unsigned long long dst_vals[kMaxSplitters + 1];
 };
 
 inline Transform make_transform(int dtype, bool ascending)

@@ -299,7 +299,18 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
             st_relaxed_u64(lookback + tile * kRadixSize + tid,
                            ((unsigned long long)((epoch << 2) | kLbInclusive) << 32) | (unsigned)(excl + count));
         }
-        out_base[tid] = __ldg(digit_base + tid) + excl - my_start;  // global index = out_base[d] + position in the sorted tile
+        if constexpr (IDENT != kDigitSplit) {
+            out_base[tid] = __ldg(digit_base + tid) + excl - my_start;  // global index = out_base[d] + position in the sorted tile
+        } else {
+            // splitter mode: every bucket has its own destination (possibly another GPU's memory).  out_base is not
+            // needed as an index table, so it holds the byte address of "position 0 of the sorted tile" per bucket.
+            if (tid <= kMaxSplitters) {
+                const long long rel = (long long)((unsigned long long)__ldg(digit_base + tid) + excl) - (long long)my_start;
+                unsigned long long *addr = reinterpret_cast<unsigned long long *>(out_base);
+                addr[tid] = tf.dst_keys[tid] + (unsigned long long)(rel * (long long)sizeof(K));
+                if constexpr (VB > 0) addr[kMaxSplitters + 1 + tid] = tf.dst_vals[tid] + (unsigned long long)(rel * (long long)VB);
+            }
+        }
     }
     __syncthreads();
 
@@ -312,7 +323,12 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
             const K k = keys_sorted[p];
             const unsigned d = pass_digit<K, IDENT>(k, shift, tf);
             if constexpr (VB > 0) dig[i] = (unsigned char)d;
-            keys_out[(size_t)(out_base[d] + p)] = k;
+            if constexpr (IDENT == kDigitSplit) {
+                const unsigned long long *addr = reinterpret_cast<const unsigned long long *>(out_base);
+                *reinterpret_cast<K *>(addr[d] + (unsigned long long)p * sizeof(K)) = k;
+            } else {
+                keys_out[(size_t)(out_base[d] + p)] = k;
+            }
         }
     }
 
@@ -336,7 +352,14 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
 #pragma unroll
         for (int i = 0; i < ITEMS; i++) {
             const unsigned p = i * THREADS + tid;
-            if (FULL || p < valid) vals_out[(size_t)(out_base[dig[i]] + p)] = vals_sorted[p];
+            if (FULL || p < valid) {
+                if constexpr (IDENT == kDigitSplit) {
+                    const unsigned long long *addr = reinterpret_cast<const unsigned long long *>(out_base);
+                    *reinterpret_cast<V *>(addr[kMaxSplitters + 1 + dig[i]] + (unsigned long long)p * VB) = vals_sorted[p];
+                } else {
+                    vals_out[(size_t)(out_base[dig[i]] + p)] = vals_sorted[p];
+                }
+            }
         }
     }
 }
@@ -346,7 +369,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
 onesweep_pass(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *__restrict__ vals_in_v,
               void *__restrict__ vals_out_v, const unsigned *__restrict__ digit_base, unsigned long long *lookback,
               unsigned epoch, unsigned long long *ticket, unsigned long long ticket_base, size_t n, size_t num_tiles, int shift,
-              Transform tf)
+              const __grid_constant__ Transform tf)
 {
     // Persistent CTAs: the grid is sized to the number of resident CTAs and tiles are dealt round-robin (CTA b takes
     // tiles b, b + G, b + 2G ...).  All CTAs are co-resident, so every tile a look-back can wait for is being worked
@@ -481,13 +504,16 @@ __device__ __forceinline__ typename key_traits<K>::U verify_key(K raw, const Tra
     else return (U)transformed_key<K>(raw, tf);
 }
 
-// coalesced 128-bit loads (lane l of a warp reads vector base + l); the seam to the next vector comes from the
-// neighbouring lane by shuffle, only lane 31 touches memory for it
+// coalesced 128-bit loads: a warp takes kVerifyUnroll x 32 consecutive vectors per iteration (lane l reads vectors
+// base + j*32 + l, all loads issued before the first compare); the seam to the next vector comes from the neighbouring
+// lane by shuffle (lane 31: from lane 0 of the next group), only the seam after the warp's last vector touches memory again
+constexpr int kVerifyUnroll = 4;
 template <typename K, bool IDENT>
 __global__ void __launch_bounds__(256) verify_sorted_kernel(const K *__restrict__ keys, size_t n, Transform tf, int *flag)
 {
     typedef typename key_traits<K>::U U;
     constexpr int VEC = 16 / sizeof(K);
+    constexpr int UNR = kVerifyUnroll;
     const unsigned lane = threadIdx.x & 31u;
     const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
     const size_t warp_id = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -495,29 +521,44 @@ __global__ void __launch_bounds__(256) verify_sorted_kernel(const K *__restrict_
     size_t done = 0;
     if ((((uintptr_t)keys) & 15) == 0) {
         const size_t nvec = n / VEC;
-        for (size_t base = warp_id * 32; base < nvec; base += warps * 32) {  // warp-uniform trip count
-            const size_t v = base + lane;
-            const bool in = v < nvec;
-            uint4 x = make_uint4(0, 0, 0, 0);
-            if (in) x = ld_stream_v4(keys + v * VEC);
-            const K *e = reinterpret_cast<const K *>(&x);
-            U k[VEC];
+        for (size_t base = warp_id * (32 * UNR); base < nvec; base += warps * (32 * UNR)) {  // warp-uniform trip count
+            uint4 x[UNR];
 #pragma unroll
-            for (int j = 0; j < VEC; j++) k[j] = verify_key<K, IDENT>(e[j], tf);
-#pragma unroll
-            for (int j = 1; j < VEC; j++) bad |= in && (k[j - 1] > k[j]);
-            U next = __shfl_down_sync(0xffffffffu, k[0], 1);
-            bool has_next = (v + 1) < nvec;
-            if (lane == 31 && in && (v + 1) * VEC < n) {  // seam across the warp's 32 vectors (and into the scalar tail)
-                next = verify_key<K, IDENT>(__ldg(keys + (v + 1) * VEC), tf);
-                has_next = true;
+            for (int j = 0; j < UNR; j++) {
+                const size_t v = base + j * 32 + lane;
+                x[j] = make_uint4(0, 0, 0, 0);
+                if (v < nvec) x[j] = ld_stream_v4(keys + v * VEC);
             }
-            bad |= in && has_next && (k[VEC - 1] > next);
+            // first key after the warp's chunk (the next chunk's first vector); lane 31 only
+            const size_t after = (base + (size_t)UNR * 32) * VEC;
+            U after_key = 0;
+            if (lane == 31 && after < nvec * VEC) after_key = verify_key<K, IDENT>(__ldg(keys + after), tf);
+            U first[UNR], last[UNR];
+#pragma unroll
+            for (int j = 0; j < UNR; j++) {
+                const K *e = reinterpret_cast<const K *>(&x[j]);
+                U k[VEC];
+#pragma unroll
+                for (int i = 0; i < VEC; i++) k[i] = verify_key<K, IDENT>(e[i], tf);
+                const bool in = base + j * 32 + lane < nvec;
+#pragma unroll
+                for (int i = 1; i < VEC; i++) bad |= in && (k[i - 1] > k[i]);
+                first[j] = k[0];
+                last[j] = k[VEC - 1];
+            }
+#pragma unroll
+            for (int j = 0; j < UNR; j++) {
+                const size_t v = base + j * 32 + lane;
+                U next = __shfl_down_sync(0xffffffffu, first[j], 1);
+                const U wrap = __shfl_sync(0xffffffffu, j + 1 < UNR ? first[(j + 1) % UNR] : after_key, j + 1 < UNR ? 0 : 31);
+                if (lane == 31) next = wrap;
+                bad |= (v + 1 < nvec) && (last[j] > next);  // the seam into the scalar tail is checked below
+            }
         }
         done = nvec * VEC;
     }
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (done ? done - 1 : 0) + gid; i + 1 < n; i += stride)  // tail, including the seam into it
+    for (size_t i = (done ? done - 1 : 0) + gid; i + 1 < n; i += stride)  // scalar tail, including the seam into it
         bad |= verify_key<K, IDENT>(__ldg(keys + i), tf) > verify_key<K, IDENT>(__ldg(keys + i + 1), tf);
     if (bad) *flag = 1;
 }
@@ -636,17 +677,11 @@ __global__ void __launch_bounds__(256) split_histogram(const K *__restrict__ key
     }
 }
 
-template <typename K, int VB>
-static int partition_typed(StreamState *st, const void *kin, void *kout, const void *vin, void *vout, size_t n, const Transform &tf,
-                           unsigned long long *counts_host)
+// bucket sizes of the splitter partition: hist[0..nsplit] on the device, copied to counts_host (blocks)
+template <typename K>
+static int partition_counts_typed(StreamState *st, const void *kin, size_t n, const Transform &tf, unsigned long long *counts_host)
 {
-    constexpr int THREADS = PassConfig<K, VB>::THREADS, ITEMS = PassConfig<K, VB>::ITEMS;
-    const size_t tile = (size_t)THREADS * ITEMS;
-    const size_t tiles = (n + tile - 1) / tile;
-    void *lb;
-    BCB_TRY(lookback_reserve(st, tiles * kRadixSize * sizeof(unsigned long long), &lb));
     unsigned *hist = st->hist;
-    unsigned *base = st->hist + 8 * kRadixSize;
     BCB_CUDA_TRY(cudaMemsetAsync(hist, 0, kRadixSize * sizeof(unsigned), st->stream));
     size_t blocks = (n + 256 * 16 - 1) / (256 * 16);
     const size_t cap = (size_t)st->sm_count * 8;
@@ -657,34 +692,62 @@ static int partition_typed(StreamState *st, const void *kin, void *kout, const v
         split_histogram<K><<<(unsigned)blocks, 256, 0, st->stream>>>((const K *)kin, n, hist, tf);
     }
     BCB_CUDA_TRY(cudaGetLastError());
-    digit_scan<<<1, kRadixSize, 0, st->stream>>>(hist, base);
-    BCB_CUDA_TRY(cudaGetLastError());
     unsigned host_counts[kMaxSplitters + 1];
     BCB_CUDA_TRY(cudaMemcpyAsync(host_counts, hist, sizeof(host_counts), cudaMemcpyDeviceToHost, st->stream));
-    BCB_TRY((launch_pass_impl<K, VB, THREADS, ITEMS, kLookbackBatch, kRankAtomicOr, kDigitSplit>(st, kin, kout, vin, vout, base,
-                                                                                                (unsigned long long *)lb, n, 0, tf)));
     BCB_CUDA_TRY(cudaStreamSynchronize(st->stream));
     for (int j = 0; j <= tf.nsplit; j++) counts_host[j] = host_counts[j];
     return BCB_SUCCESS;
 }
 
-template <typename K>
-static int partition_by_value_size(StreamState *st, const void *kin, void *kout, const void *vin, void *vout, size_t vb, size_t n,
-                                   const Transform &tf, unsigned long long *counts_host)
+// one stable onesweep pass whose "digit" is the splitter bucket; bucket b is written contiguously from tf.dst_keys[b]
+// (+ base[b] elements).  Asynchronous.
+template <typename K, int VB>
+static int partition_scatter_typed(StreamState *st, const void *kin, const void *vin, size_t n, const Transform &tf, const unsigned *base)
 {
-    if (!vin || vb == 0) return partition_typed<K, 0>(st, kin, kout, nullptr, nullptr, n, tf, counts_host);
+    constexpr int THREADS = PassConfig<K, VB>::THREADS, ITEMS = PassConfig<K, VB>::ITEMS;
+    const size_t tile = (size_t)THREADS * ITEMS;
+    const size_t tiles = (n + tile - 1) / tile;
+    void *lb;
+    BCB_TRY(lookback_reserve(st, tiles * kRadixSize * sizeof(unsigned long long), &lb));
+    return launch_pass_impl<K, VB, THREADS, ITEMS, kLookbackBatch, kRankAtomicOr, kDigitSplit>(st, kin, nullptr, vin, nullptr, base,
+                                                                                              (unsigned long long *)lb, n, 0, tf);
+}
+
+template <typename K>
+static int partition_scatter_by_value_size(StreamState *st, const void *kin, const void *vin, size_t vb, size_t n, const Transform &tf,
+                                           const unsigned *base)
+{
+    if (!vin || vb == 0) return partition_scatter_typed<K, 0>(st, kin, nullptr, n, tf, base);
     switch (vb) {
-    case 4: return partition_typed<K, 4>(st, kin, kout, vin, vout, n, tf, counts_host);
-    case 8: return partition_typed<K, 8>(st, kin, kout, vin, vout, n, tf, counts_host);
+    case 4: return partition_scatter_typed<K, 4>(st, kin, vin, n, tf, base);
+    case 8: return partition_scatter_typed<K, 8>(st, kin, vin, n, tf, base);
     default: return BCB_EUNSUPPORTED;  // callers fall back to sort-then-cut (bcb_partition_points)
     }
 }
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-template <typename K, int VB>
-static int sort_typed(StreamState *st, void *keys, void *values, size_t n, const Transform &tf, int rank = -1)
+template <typename K>
+static int run_verify(StreamState *st, const void *keys, size_t n, const Transform &tf, int *flag)
 {
+    size_t blocks = (n + 256 * 16 - 1) / (256 * 16);
+    const size_t cap = (size_t)st->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    if ((tf.nm | tf.xc | tf.fa) == 0)
+        verify_sorted_kernel<K, true><<<(unsigned)blocks, 256, 0, st->stream>>>((const K *)keys, n, tf, flag);
+    else
+        verify_sorted_kernel<K, false><<<(unsigned)blocks, 256, 0, st->stream>>>((const K *)keys, n, tf, flag);
+    BCB_CUDA_TRY(cudaGetLastError());
+    return BCB_SUCCESS;
+}
+
+template <typename K, int VB>
+static int sort_typed(StreamState *st, void *keys, void *values, size_t n, const Transform &tf, const void *src_keys = nullptr,
+                      const void *src_vals = nullptr, int rank = -1)
+{
+    // src_keys / src_vals: read the input from there instead (sorted copy; the source is left untouched)
+    if (!src_keys) { src_keys = keys; src_vals = values; }
     constexpr int NPASS = sizeof(K);
     if (rank < 0) {
         rank = kRankAtomicOr;
@@ -716,7 +779,7 @@ static int sort_typed(StreamState *st, void *keys, void *values, size_t n, const
         if (blocks < 1) blocks = 1;
         {
             LaunchTimer timer(st, BCB_K_RADIX_HISTOGRAM);
-            radix_histogram<K><<<(unsigned)blocks, kHistThreads, 0, st->stream>>>((const K *)keys, n, hist, tf);
+            radix_histogram<K><<<(unsigned)blocks, kHistThreads, 0, st->stream>>>((const K *)src_keys, n, hist, tf);
         }
         BCB_CUDA_TRY(cudaGetLastError());
         {
@@ -727,7 +790,8 @@ static int sort_typed(StreamState *st, void *keys, void *values, size_t n, const
     }
     void *kin = keys, *kout = tmp_keys, *vin = values, *vout = tmp_vals;
     for (int p = 0; p < NPASS; p++) {
-        BCB_TRY((run_pass<K, VB>(st, kin, kout, vin, vout, base + p * kRadixSize, (unsigned long long *)lb, n, p * kRadixBits, tf, rank)));
+        BCB_TRY((run_pass<K, VB>(st, p == 0 ? src_keys : kin, kout, p == 0 ? src_vals : vin, vout, base + p * kRadixSize,
+                                 (unsigned long long *)lb, n, p * kRadixBits, tf, rank)));
         void *t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;
     }
@@ -740,23 +804,16 @@ static int sort_typed(StreamState *st, void *keys, void *values, size_t n, const
             // verify the speculation (see above); on failure sort again with the deterministic kernel
             int *flag = (int *)st->pinned_slot_dev;
             *(volatile int *)st->pinned_slot = 0;
-            size_t blocks = (n + 256 * 16 - 1) / (256 * 16);
-            const size_t cap = (size_t)st->sm_count * 8;
-            if (blocks > cap) blocks = cap;
-            if (blocks < 1) blocks = 1;
             {
                 LaunchTimer timer(st, BCB_K_OTHER);
-                if ((tf.nm | tf.xc | tf.fa) == 0)
-                    verify_sorted_kernel<K, true><<<(unsigned)blocks, 256, 0, st->stream>>>((const K *)keys, n, tf, flag);
-                else
-                    verify_sorted_kernel<K, false><<<(unsigned)blocks, 256, 0, st->stream>>>((const K *)keys, n, tf, flag);
+                BCB_TRY(run_verify<K>(st, keys, n, tf, flag));
             }
             BCB_CUDA_TRY(cudaGetLastError());
             BCB_CUDA_TRY(cudaStreamSynchronize(st->stream));
             st->spec_runs++;
             if (*(volatile int *)st->pinned_slot != 0 || g_force_fallback == 1) {
                 st->spec_fallbacks++;
-                return sort_typed<K, VB>(st, keys, values, n, tf, kRankAtomicOr);
+                return sort_typed<K, VB>(st, keys, values, n, tf, src_keys, src_vals, kRankAtomicOr);
             }
         }
     }
@@ -764,19 +821,24 @@ static int sort_typed(StreamState *st, void *keys, void *values, size_t n, const
 }
 
 template <typename K>
-static int sort_by_value_size(StreamState *st, void *keys, void *values, size_t vb, size_t n, const Transform &tf)
+static int sort_by_value_size(StreamState *st, void *keys, void *values, size_t vb, size_t n, const Transform &tf,
+                              const void *src_keys = nullptr, const void *src_vals = nullptr)
 {
-    if (!values || vb == 0) return sort_typed<K, 0>(st, keys, nullptr, n, tf);
-    const bool aligned = ((uintptr_t)values % (vb <= 16 ? vb : 1)) == 0;
+    if (!values || vb == 0) return sort_typed<K, 0>(st, keys, nullptr, n, tf, src_keys, nullptr);
+    const bool aligned = ((uintptr_t)values % (vb <= 16 ? vb : 1)) == 0 && (!src_vals || ((uintptr_t)src_vals % (vb <= 16 ? vb : 1)) == 0);
     if (aligned) {
         switch (vb) {
-        case 1: return sort_typed<K, 1>(st, keys, values, n, tf);
-        case 2: return sort_typed<K, 2>(st, keys, values, n, tf);
-        case 4: return sort_typed<K, 4>(st, keys, values, n, tf);
-        case 8: return sort_typed<K, 8>(st, keys, values, n, tf);
-        case 16: return sort_typed<K, 16>(st, keys, values, n, tf);
+        case 1: return sort_typed<K, 1>(st, keys, values, n, tf, src_keys, src_vals);
+        case 2: return sort_typed<K, 2>(st, keys, values, n, tf, src_keys, src_vals);
+        case 4: return sort_typed<K, 4>(st, keys, values, n, tf, src_keys, src_vals);
+        case 8: return sort_typed<K, 8>(st, keys, values, n, tf, src_keys, src_vals);
+        case 16: return sort_typed<K, 16>(st, keys, values, n, tf, src_keys, src_vals);
         default: break;
         }
+    }
+    if (src_keys) {  // generic payload: copy first, then sort in place
+        BCB_CUDA_TRY(cudaMemcpyAsync(keys, src_keys, n * sizeof(K), cudaMemcpyDeviceToDevice, st->stream));
+        BCB_CUDA_TRY(cudaMemcpyAsync(values, src_vals, n * vb, cudaMemcpyDeviceToDevice, st->stream));
     }
     // generic payload: stable-sort (key, original index) pairs, then gather the payload bytes
     unsigned *idx;
@@ -802,14 +864,15 @@ static int sort_by_value_size(StreamState *st, void *keys, void *values, size_t 
     return rc;
 }
 
-static int radix_sort_impl(StreamState *st, int key_dtype, int ascending, void *keys, size_t n, void *values, size_t vb)
+static int radix_sort_impl(StreamState *st, int key_dtype, int ascending, void *keys, size_t n, void *values, size_t vb,
+                           const void *src_keys = nullptr, const void *src_vals = nullptr)
 {
     const Transform tf = make_transform(key_dtype, ascending != 0);
     switch (dtype_size(key_dtype)) {
-    case 1: return sort_by_value_size<unsigned char>(st, keys, values, vb, n, tf);
-    case 2: return sort_by_value_size<unsigned short>(st, keys, values, vb, n, tf);
-    case 4: return sort_by_value_size<unsigned>(st, keys, values, vb, n, tf);
-    case 8: return sort_by_value_size<unsigned long long>(st, keys, values, vb, n, tf);
+    case 1: return sort_by_value_size<unsigned char>(st, keys, values, vb, n, tf, src_keys, src_vals);
+    case 2: return sort_by_value_size<unsigned short>(st, keys, values, vb, n, tf, src_keys, src_vals);
+    case 4: return sort_by_value_size<unsigned>(st, keys, values, vb, n, tf, src_keys, src_vals);
+    case 8: return sort_by_value_size<unsigned long long>(st, keys, values, vb, n, tf, src_keys, src_vals);
     default: return BCB_EINVAL;
     }
 }
@@ -842,6 +905,29 @@ int bcb_radix_sort(bcb_stream stream, int key_dtype, int ascending, void *keys, 
     StreamState *st;
     BCB_TRY(stream_state((cudaStream_t)stream, &st));
     return radix_sort_impl(st, key_dtype, ascending, keys, n, values, values ? value_bytes : 0);
+}
+
+int bcb_radix_sort_copy(bcb_stream stream, int key_dtype, int ascending, const void *keys_in, void *keys_out, size_t n,
+                        const void *values_in, void *values_out, size_t value_bytes)
+{
+    const size_t w = dtype_size(key_dtype);
+    if (!w) return BCB_EINVAL;
+    if (n == 0) return BCB_SUCCESS;
+    if (!keys_in || !keys_out || ((values_in != nullptr) != (values_out != nullptr))) return BCB_EINVAL;
+    if ((keys_in == keys_out) != (values_in == values_out) && values_in) return BCB_EINVAL;  // in place means both
+    if (n >= 0xffff0000ull) return BCB_ETOOLARGE;
+    StreamState *st;
+    BCB_TRY(stream_state((cudaStream_t)stream, &st));
+    const size_t vb = values_in ? value_bytes : 0;
+    if (n < 2 || keys_in == keys_out) {
+        if (keys_in != keys_out) {
+            BCB_CUDA_TRY(cudaMemcpyAsync(keys_out, keys_in, n * w, cudaMemcpyDeviceToDevice, st->stream));
+            if (vb) BCB_CUDA_TRY(cudaMemcpyAsync(values_out, values_in, n * vb, cudaMemcpyDeviceToDevice, st->stream));
+        }
+        if (n < 2) return BCB_SUCCESS;
+        return radix_sort_impl(st, key_dtype, ascending, keys_out, n, values_out, vb);
+    }
+    return radix_sort_impl(st, key_dtype, ascending, keys_out, n, values_out, vb, keys_in, values_in);
 }
 
 int bcb_insertion_sort(bcb_stream stream, int key_dtype, int greater, void *keys, size_t n, void *values, size_t value_bytes)
@@ -887,6 +973,28 @@ int bcb_partition_points(bcb_stream stream, int key_dtype, int ascending, const 
     return rc;
 }
 
+int bcb_is_sorted_by_radix_key(bcb_stream stream, int key_dtype, int ascending, const void *keys, size_t n, int *result_host)
+{
+    if (!result_host || !dtype_size(key_dtype)) return BCB_EINVAL;
+    *result_host = 1;
+    if (n < 2) return BCB_SUCCESS;
+    if (!keys) return BCB_EINVAL;
+    StreamState *st;
+    BCB_TRY(stream_state((cudaStream_t)stream, &st));
+    const Transform tf = make_transform(key_dtype, ascending != 0);
+    int *flag = (int *)st->pinned_slot_dev;
+    *(volatile int *)st->pinned_slot = 0;
+    switch (dtype_size(key_dtype)) {
+    case 1: BCB_TRY(run_verify<unsigned char>(st, keys, n, tf, flag)); break;
+    case 2: BCB_TRY(run_verify<unsigned short>(st, keys, n, tf, flag)); break;
+    case 4: BCB_TRY(run_verify<unsigned>(st, keys, n, tf, flag)); break;
+    default: BCB_TRY(run_verify<unsigned long long>(st, keys, n, tf, flag)); break;
+    }
+    BCB_CUDA_TRY(cudaStreamSynchronize(st->stream));
+    *result_host = (*(volatile int *)st->pinned_slot) ? 0 : 1;
+    return BCB_SUCCESS;
+}
+
 int bcb_sort_speculation_stats(bcb_stream stream, unsigned long long *runs, unsigned long long *fallbacks)
 {
     StreamState *st;
@@ -896,28 +1004,97 @@ int bcb_sort_speculation_stats(bcb_stream stream, unsigned long long *runs, unsi
     return BCB_SUCCESS;
 }
 
+static int split_transform(int key_dtype, int ascending, const unsigned long long *splitters_host, size_t num_splitters, Transform *tf)
+{
+    if (!dtype_size(key_dtype)) return BCB_EINVAL;
+    if (num_splitters > (size_t)kMaxSplitters) return BCB_EUNSUPPORTED;
+    if (num_splitters && !splitters_host) return BCB_EINVAL;
+    *tf = make_transform(key_dtype, ascending != 0);
+    tf->nsplit = (int)num_splitters;
+    for (size_t j = 0; j < num_splitters; j++) tf->split[j] = splitters_host[j];
+    return BCB_SUCCESS;
+}
+
+int bcb_partition_counts(bcb_stream stream, int key_dtype, int ascending, const void *keys, size_t n,
+                         const unsigned long long *splitters_host, size_t num_splitters, unsigned long long *counts_host)
+{
+    if (!counts_host) return BCB_EINVAL;
+    Transform tf;
+    BCB_TRY(split_transform(key_dtype, ascending, splitters_host, num_splitters, &tf));
+    for (size_t j = 0; j <= num_splitters; j++) counts_host[j] = 0;
+    if (n == 0) return BCB_SUCCESS;
+    if (!keys) return BCB_EINVAL;
+    if (n >= 0xffff0000ull) return BCB_ETOOLARGE;
+    StreamState *st;
+    BCB_TRY(stream_state((cudaStream_t)stream, &st));
+    switch (dtype_size(key_dtype)) {
+    case 1: return partition_counts_typed<unsigned char>(st, keys, n, tf, counts_host);
+    case 2: return partition_counts_typed<unsigned short>(st, keys, n, tf, counts_host);
+    case 4: return partition_counts_typed<unsigned>(st, keys, n, tf, counts_host);
+    default: return partition_counts_typed<unsigned long long>(st, keys, n, tf, counts_host);
+    }
+}
+
+static int partition_scatter_dispatch(StreamState *st, int key_dtype, const void *keys_in, const void *values_in, size_t vb, size_t n,
+                                      const Transform &tf, const unsigned *base)
+{
+    switch (dtype_size(key_dtype)) {
+    case 1: return partition_scatter_by_value_size<unsigned char>(st, keys_in, values_in, vb, n, tf, base);
+    case 2: return partition_scatter_by_value_size<unsigned short>(st, keys_in, values_in, vb, n, tf, base);
+    case 4: return partition_scatter_by_value_size<unsigned>(st, keys_in, values_in, vb, n, tf, base);
+    default: return partition_scatter_by_value_size<unsigned long long>(st, keys_in, values_in, vb, n, tf, base);
+    }
+}
+
+int bcb_partition_scatter(bcb_stream stream, int key_dtype, int ascending, const void *keys_in, const void *values_in,
+                          size_t value_bytes, size_t n, const unsigned long long *splitters_host, size_t num_splitters,
+                          void *const *dst_keys, void *const *dst_values)
+{
+    Transform tf;
+    BCB_TRY(split_transform(key_dtype, ascending, splitters_host, num_splitters, &tf));
+    if (n == 0) return BCB_SUCCESS;
+    if (!keys_in || !dst_keys) return BCB_EINVAL;
+    if (n >= 0xffff0000ull) return BCB_ETOOLARGE;
+    const size_t vb = values_in ? value_bytes : 0;
+    if (vb && !dst_values) return BCB_EINVAL;
+    for (size_t j = 0; j <= num_splitters; j++) {
+        tf.dst_keys[j] = (unsigned long long)(uintptr_t)dst_keys[j];
+        tf.dst_vals[j] = vb ? (unsigned long long)(uintptr_t)dst_values[j] : 0ull;
+    }
+    StreamState *st;
+    BCB_TRY(stream_state((cudaStream_t)stream, &st));
+    unsigned *base = st->hist + 8 * kRadixSize;  // every bucket starts at its own destination pointer
+    BCB_CUDA_TRY(cudaMemsetAsync(base, 0, kRadixSize * sizeof(unsigned), st->stream));
+    return partition_scatter_dispatch(st, key_dtype, keys_in, values_in, vb, n, tf, base);
+}
+
 int bcb_partition_by_splitters(bcb_stream stream, int key_dtype, int ascending, const void *keys_in, void *keys_out,
                                const void *values_in, void *values_out, size_t value_bytes, size_t n,
                                const unsigned long long *splitters_host, size_t num_splitters, unsigned long long *counts_host)
 {
-    if (!dtype_size(key_dtype) || !counts_host) return BCB_EINVAL;
-    if (num_splitters > (size_t)kMaxSplitters) return BCB_EUNSUPPORTED;
+    if (!counts_host) return BCB_EINVAL;
+    Transform tf;
+    BCB_TRY(split_transform(key_dtype, ascending, splitters_host, num_splitters, &tf));
     for (size_t j = 0; j <= num_splitters; j++) counts_host[j] = 0;
     if (n == 0) return BCB_SUCCESS;
-    if (!keys_in || !keys_out || (num_splitters && !splitters_host)) return BCB_EINVAL;
+    if (!keys_in || !keys_out) return BCB_EINVAL;
     if (n >= 0xffff0000ull) return BCB_ETOOLARGE;
+    const size_t vb = (values_in && values_out) ? value_bytes : 0;
+    if (vb != 0 && vb != 4 && vb != 8) return BCB_EUNSUPPORTED;
+    BCB_TRY(bcb_partition_counts(stream, key_dtype, ascending, keys_in, n, splitters_host, num_splitters, counts_host));
     StreamState *st;
     BCB_TRY(stream_state((cudaStream_t)stream, &st));
-    Transform tf = make_transform(key_dtype, ascending != 0);
-    tf.nsplit = (int)num_splitters;
-    for (size_t j = 0; j < num_splitters; j++) tf.split[j] = splitters_host[j];
-    const size_t vb = (values_in && values_out) ? value_bytes : 0;
-    switch (dtype_size(key_dtype)) {
-    case 1: return partition_by_value_size<unsigned char>(st, keys_in, keys_out, values_in, values_out, vb, n, tf, counts_host);
-    case 2: return partition_by_value_size<unsigned short>(st, keys_in, keys_out, values_in, values_out, vb, n, tf, counts_host);
-    case 4: return partition_by_value_size<unsigned>(st, keys_in, keys_out, values_in, values_out, vb, n, tf, counts_host);
-    default: return partition_by_value_size<unsigned long long>(st, keys_in, keys_out, values_in, values_out, vb, n, tf, counts_host);
+    // one output buffer: bucket b starts at the exclusive prefix of the counts (digit_scan of the histogram)
+    unsigned *base = st->hist + 8 * kRadixSize;
+    digit_scan<<<1, kRadixSize, 0, st->stream>>>(st->hist, base);
+    BCB_CUDA_TRY(cudaGetLastError());
+    for (size_t j = 0; j <= num_splitters; j++) {
+        tf.dst_keys[j] = (unsigned long long)(uintptr_t)keys_out;
+        tf.dst_vals[j] = (unsigned long long)(uintptr_t)values_out;
     }
+    BCB_TRY(partition_scatter_dispatch(st, key_dtype, keys_in, values_in, vb, n, tf, base));
+    BCB_CUDA_TRY(cudaStreamSynchronize(st->stream));
+    return BCB_SUCCESS;
 }
 
 int bcb_sort_host(bcb_stream stream, int key_dtype, int descending, void *host_keys, size_t n)

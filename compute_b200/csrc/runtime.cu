@@ -334,6 +334,33 @@ int bcb_free(void *device_ptr)
     return BCB_SUCCESS;
 }
 
+// ---- peer memory (multi-GPU): legacy CUDA IPC handles of bcb_malloc'ed buffers, exchanged by the host layer ----
+int bcb_ipc_export(void *device_ptr, unsigned char *handle64)
+{
+    if (!device_ptr || !handle64) return BCB_EINVAL;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
+    cudaIpcMemHandle_t h;
+    BCB_CUDA_TRY(cudaIpcGetMemHandle(&h, device_ptr));
+    std::memcpy(handle64, &h, sizeof(h));
+    return BCB_SUCCESS;
+}
+
+int bcb_ipc_open(const unsigned char *handle64, void **device_ptr)
+{
+    if (!handle64 || !device_ptr) return BCB_EINVAL;
+    *device_ptr = nullptr;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, sizeof(h));
+    BCB_CUDA_TRY(cudaIpcOpenMemHandle(device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return BCB_SUCCESS;
+}
+
+int bcb_ipc_close(void *device_ptr)
+{
+    if (device_ptr) BCB_CUDA_TRY(cudaIpcCloseMemHandle(device_ptr));
+    return BCB_SUCCESS;
+}
+
 int bcb_host_alloc(void **host_ptr, size_t bytes)
 {
     if (!host_ptr) return BCB_EINVAL;

@@ -21,6 +21,7 @@ CPU oracle there.  The product only ever uses ``CudaLocalOps`` (C ABI -> sm_100a
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -146,6 +147,54 @@ class CudaLocalOps:
         self._check(rc)
         return out_k, out_v, counts.astype(np.int64)
 
+    # ---- peer-memory exchange (NVLink stores from inside the partition pass) --------------------------------
+    @staticmethod
+    def _row_bytes(values) -> int:
+        return 0 if values is None else values.element_size() * (values.numel() // max(1, values.shape[0]))
+
+    def partition_counts(self, keys, splitters: np.ndarray, descending: bool) -> np.ndarray:
+        counts = np.zeros(splitters.size + 1, dtype=np.uint64)
+        sp = np.ascontiguousarray(splitters, dtype=np.uint64)
+        self._check(self._lib.bcb_partition_counts(self.queue.handle, dtype_code(keys.dtype), int(not descending), keys.data_ptr(),
+                                                   keys.shape[0], sp.ctypes.data, sp.size, counts.ctypes.data))
+        return counts.astype(np.int64)
+
+    def partition_scatter(self, keys, values, splitters: np.ndarray, descending: bool, dst_keys, dst_values) -> None:
+        """Bucket b of the stable partition goes to the device address dst_keys[b] (dst_values[b]); asynchronous."""
+        nb = splitters.size + 1
+        sp = np.ascontiguousarray(splitters, dtype=np.uint64)
+        dk = (ctypes.c_void_p * nb)(*[int(a) for a in dst_keys])
+        dv = (ctypes.c_void_p * nb)(*[int(a) for a in dst_values]) if values is not None else None
+        self._check(self._lib.bcb_partition_scatter(self.queue.handle, dtype_code(keys.dtype), int(not descending), keys.data_ptr(),
+                                                    None if values is None else values.data_ptr(), self._row_bytes(values),
+                                                    keys.shape[0], sp.ctypes.data, sp.size, dk, dv))
+
+    def sort_copy(self, src_keys_ptr: int, out_keys, src_values_ptr, out_values, descending: bool) -> None:
+        self._check(self._lib.bcb_radix_sort_copy(self.queue.handle, dtype_code(out_keys.dtype), int(not descending), src_keys_ptr,
+                                                  out_keys.data_ptr(), out_keys.shape[0],
+                                                  None if out_values is None else src_values_ptr,
+                                                  None if out_values is None else out_values.data_ptr(), self._row_bytes(out_values)))
+
+    def peer_alloc(self, nbytes: int):
+        """(local device pointer, 64-byte IPC handle) of a fresh buffer other ranks can map."""
+        ptr = ctypes.c_void_p()
+        self._check(self._lib.bcb_malloc(ctypes.byref(ptr), nbytes))
+        handle = np.zeros(64, dtype=np.uint8)
+        self._check(self._lib.bcb_ipc_export(ptr, handle.ctypes.data))
+        return int(ptr.value), handle
+
+    def peer_open(self, handle: np.ndarray) -> int:
+        ptr = ctypes.c_void_p()
+        h = np.ascontiguousarray(handle, dtype=np.uint8)
+        self._check(self._lib.bcb_ipc_open(h.ctypes.data, ctypes.byref(ptr)))
+        return int(ptr.value)
+
+    def peer_close(self, ptr: int) -> None:
+        self._check(self._lib.bcb_ipc_close(ctypes.c_void_p(ptr)))
+
+    def peer_free(self, ptr: int) -> None:
+        self._check(self._lib.bcb_free(ctypes.c_void_p(ptr)))
+
     def gather_bits(self, keys, positions: np.ndarray) -> np.ndarray:
         """Raw bit patterns of keys[positions] as unsigned ints on the host."""
         w = keys.element_size()
@@ -172,6 +221,70 @@ class CudaLocalOps:
 # ------------------------------------------------------------------------------------------------------------
 # the distributed algorithms
 # ------------------------------------------------------------------------------------------------------------
+class PeerExchange:
+    """One receive buffer per rank, mapped into every other rank's address space (CUDA IPC over NVLink / NVSwitch),
+    so that the partition pass of the multi-GPU sort can store each key directly where it belongs on its destination
+    GPU.  All methods are collective and take the same arguments on every rank."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.capacity = 0
+        self.local = 0          # this rank's buffer
+        self.peers = []         # device address of rank r's buffer in THIS process (peers[rank] == local)
+        self.failed = False     # peer mapping is not possible here: callers use the NCCL all-to-all plan
+        self._live = False      # an allocation round took place (same value on every rank)
+
+    def release(self):
+        ops, ctx = self.ctx.ops, self.ctx
+        if not self._live:
+            return
+        for r, p in enumerate(self.peers):
+            if r != ctx.rank and p:
+                ops.peer_close(p)
+        self.peers = []
+        ctx._all_gather_np(np.zeros(1, np.int32))  # every rank has unmapped the buffers before any is freed
+        if self.local:
+            ops.peer_free(self.local)
+        self.local, self.capacity, self._live = 0, 0, False
+
+    def ensure(self, nbytes: int) -> bool:
+        if self.failed:
+            return False
+        if nbytes <= self.capacity:
+            return True
+        ops, ctx = self.ctx.ops, self.ctx
+        self.release()
+        cap = (int(nbytes * 1.125) + (2 << 20)) & ~((2 << 20) - 1)
+        ok, handle = 1, np.zeros(64, dtype=np.uint8)
+        self._live = True
+        try:
+            self.local, handle = ops.peer_alloc(cap)
+        except Exception:  # noqa: BLE001 -- any failure here only selects the NCCL plan
+            ok = 0
+        handles = ctx._all_gather_np(handle)
+        oks = ctx._all_gather_np(np.array([ok], np.int32)).reshape(-1)
+        peers = [0] * ctx.world
+        if oks.all():
+            for r in range(ctx.world):
+                if r == ctx.rank:
+                    peers[r] = self.local
+                    continue
+                try:
+                    peers[r] = ops.peer_open(handles[r])
+                except Exception:  # noqa: BLE001
+                    ok = 0
+                    break
+        else:
+            ok = 0
+        self.peers = peers
+        if not ctx._all_gather_np(np.array([ok], np.int32)).all():
+            self.release()
+            self.failed = True
+            return False
+        self.capacity = cap
+        return True
+
+
 class Context:
     def __init__(self, group=None, local_ops=None, samples_per_rank: int = 1024):
         self.group = group
@@ -180,6 +293,32 @@ class Context:
         self.ops = local_ops if local_ops is not None else CudaLocalOps()
         self.samples_per_rank = samples_per_rank
         self.last_stats = {}
+        self.peer = PeerExchange(self)
+        # BCB_DIST_PEER=0: always exchange through NCCL all-to-all; BCB_DIST_PROFILE=1: synchronise after every phase
+        # and record last_stats["phases_ms"] (diagnostics only -- the synchronisation costs time)
+        self.use_peer_memory = os.environ.get("BCB_DIST_PEER", "1") != "0"
+        self.profile = os.environ.get("BCB_DIST_PROFILE", "0") == "1"
+        self._flag = None
+
+    def _phase(self, name):
+        if not self.profile:
+            return
+        import time
+        if self.ops.device_type == "cuda":
+            torch.cuda.synchronize()
+        now = time.perf_counter()
+        if name is None:
+            self._phases, self._t0 = {}, now
+            return
+        self._phases[name] = self._phases.get(name, 0.0) + (now - self._t0) * 1e3
+        self._t0 = now
+
+    def _stream_barrier(self):
+        """Stream-ordered barrier: everything enqueued before it on every rank has completed before anything after it
+        starts on any rank (a one-element all-reduce; no host synchronisation)."""
+        if self._flag is None:
+            self._flag = torch.zeros(1, dtype=torch.int32, device="cuda" if self.ops.device_type == "cuda" else "cpu")
+        dist.all_reduce(self._flag, group=self.group)
 
     # -- helpers ----------------------------------------------------------------------------------------
     def _all_gather_np(self, arr: np.ndarray) -> np.ndarray:
@@ -225,9 +364,18 @@ class Context:
                 tk = np.concatenate([tk, np.full(s - tk.size, np.iinfo(np.uint64).max, np.uint64)])
             return select_splitters(self._all_gather_np(tk), P)
 
+        self._phase(None)
         # Preferred plan: evenly spaced samples of the UNSORTED shard -> splitters -> ONE stable partition pass
-        # (bucket = number of splitters <= transformed key) -> all-to-all -> one local sort.
+        # (bucket = number of splitters <= transformed key) whose stores go straight into the destination ranks'
+        # receive buffers over NVLink -> one local sort out of the receive buffer.
         splitters = sample_splitters(keys)
+        self._phase("sample")
+        vb = 0 if values is None else values.element_size() * (values.numel() // max(1, values.shape[0]))
+        if (self.use_peer_memory and hasattr(self.ops, "partition_scatter") and not self.peer.failed and P - 1 <= 7
+                and vb in (0, 4, 8)):
+            done = self._sort_peer(keys, values, descending, splitters, vb)
+            if done is not None:
+                return done
         part = self.ops.partition(keys, values, splitters, descending) if hasattr(self.ops, "partition") else None
         if part is not None:
             src_keys, src_vals, send = part
@@ -241,15 +389,48 @@ class Context:
             send = exchange_plan(points, n_local)
             src_keys, src_vals = keys, values
             plan = "sort-and-cut"
+        self._phase("partition")
         counts = self._all_gather_np(np.asarray(send, dtype=np.int64))          # counts[src][dst]
         recv = counts[:, self.rank].copy()
         # exchange: contiguous slices, received in source-rank order
         out_keys = self._all_to_all(src_keys, send, recv)
         out_vals = self._all_to_all(src_vals, send, recv) if values is not None else None
+        self._phase("all_to_all")
         # 5. final local stable sort of the P received runs
         self.ops.sort(out_keys, out_vals, descending)
-        self.last_stats = {"plan": plan, "sent": int(send.sum() - send[self.rank]), "received": int(recv.sum()),
+        self._phase("sort")
+        self.last_stats = {"plan": plan, "phases_ms": dict(getattr(self, "_phases", {})) if self.profile else None, "sent": int(send.sum() - send[self.rank]), "received": int(recv.sum()),
                            "imbalance": float(counts.sum(axis=0).max() * P / max(1, counts.sum()))}
+        return out_keys if values is None else (out_keys, out_vals)
+
+    def _sort_peer(self, keys, values, descending, splitters, vb):
+        """The peer-memory plan (see sort).  Returns None -- collectively -- when the buffers cannot be mapped."""
+        P, me = self.world, self.rank
+        ksize = keys.element_size()
+        send = self.ops.partition_counts(keys, splitters, descending)
+        self._phase("counts")
+        counts = self._all_gather_np(send)                               # counts[src][dst]
+        recv_tot = counts.sum(axis=0)
+        max_recv = int(recv_tot.max())
+        val_off = (max_recv * ksize + 255) & ~255                        # values region of every receive buffer
+        # the all-gather above also orders this call after every rank's previous use of its receive buffer
+        if not self.peer.ensure(val_off + max_recv * vb):
+            return None
+        offs = np.cumsum(counts, axis=0) - counts                        # offs[src][dst]: where src's slice starts at dst
+        dst_k = [self.peer.peers[d] + int(offs[me][d]) * ksize for d in range(P)]
+        dst_v = [self.peer.peers[d] + val_off + int(offs[me][d]) * vb for d in range(P)]
+        self._phase("plan")
+        self.ops.partition_scatter(keys, values, splitters, descending, dst_k, dst_v)
+        self._stream_barrier()                                           # all incoming stores have landed
+        self._phase("scatter")
+        n_out = int(recv_tot[me])
+        out_keys = self.ops.empty(n_out, keys)
+        out_vals = self.ops.empty(n_out, values) if values is not None else None
+        self.ops.sort_copy(self.peer.local, out_keys, self.peer.local + val_off, out_vals, descending)
+        self._phase("sort")
+        self.last_stats = {"plan": "peer-scatter", "phases_ms": dict(self._phases) if self.profile else None,
+                           "sent": int(send.sum() - send[me]), "received": n_out,
+                           "imbalance": float(recv_tot.max() * P / max(1, counts.sum()))}
         return out_keys if values is None else (out_keys, out_vals)
 
     # -- scan -------------------------------------------------------------------------------------------

@@ -106,11 +106,21 @@ BCB_API int bcb_workspace_release(bcb_stream stream);
  * value_bytes is sizeof(T2), any size >= 1.  ascending != 0 sorts by less<T>, 0 by greater<T>. */
 BCB_API int bcb_radix_sort(bcb_stream stream, int key_dtype, int ascending, void *keys, size_t n,
                    void *values, size_t value_bytes);
+/* bcb_radix_sort as a sorted copy: reads keys_in (and values_in), leaves them untouched, writes the sorted range to
+ * keys_out (values_out).  Same kernels and pass count (the first pass reads the source).  In place when the pointers
+ * are equal. */
+BCB_API int bcb_radix_sort_copy(bcb_stream stream, int key_dtype, int ascending, const void *keys_in, void *keys_out,
+                                size_t n, const void *values_in, void *values_out, size_t value_bytes);
+
 /* Large keys-only sorts of 32/64-bit keys run a faster, speculatively stable pass kernel, verify the result (sorted by
  * the transformed key <=> correct, because every pass is a permutation) and fall back to the deterministic kernel if the
  * check fails; such calls block until the verification is done.  These counters report how often that happened on the
  * stream.  BCB_SORT_SPECULATIVE=0 in the environment disables speculation. */
 BCB_API int bcb_sort_speculation_stats(bcb_stream stream, unsigned long long *verified_runs, unsigned long long *fallbacks);
+/* is the range sorted by the transformed radix key of radix_sort.hpp:100-127 (the order radix_sort defines, which for
+ * floats differs from operator< on +-0 / NaN)?  This is the check the speculative sort runs on its own output. Blocks. */
+BCB_API int bcb_is_sorted_by_radix_key(bcb_stream stream, int key_dtype, int ascending, const void *keys, size_t n,
+                                       int *result_host);
 /* detail::serial_insertion_sort / _by_key (algorithm/detail/insertion_sort.hpp:25-159): one thread, native compare.
  * greater != 0 uses ">" (descending).  n <= 4096. */
 BCB_API int bcb_insertion_sort(bcb_stream stream, int key_dtype, int greater, void *keys, size_t n,
@@ -135,6 +145,26 @@ BCB_API int bcb_partition_by_splitters(bcb_stream stream, int key_dtype, int asc
                                        const void *values_in, void *values_out, size_t value_bytes, size_t n,
                                        const unsigned long long *splitters_host, size_t num_splitters,
                                        unsigned long long *counts_host);
+
+/* The two halves of the partition as separate calls, for the multi-GPU sort that scatters straight into its peers'
+ * receive buffers: bcb_partition_counts returns the bucket sizes (blocks); the host layer exchanges them, derives where
+ * this rank's slice of every bucket starts inside each destination rank's buffer, and bcb_partition_scatter then writes
+ * bucket b contiguously from dst_keys[b] (and dst_values[b]) -- plain device addresses, which may be another GPU's
+ * memory opened with bcb_ipc_open, so the exchange is fused into the pass (NVLink stores, no all-to-all).
+ * bcb_partition_scatter is asynchronous; value_bytes 0, 4 or 8 (else BCB_EUNSUPPORTED). */
+BCB_API int bcb_partition_counts(bcb_stream stream, int key_dtype, int ascending, const void *keys, size_t n,
+                                 const unsigned long long *splitters_host, size_t num_splitters,
+                                 unsigned long long *counts_host);
+BCB_API int bcb_partition_scatter(bcb_stream stream, int key_dtype, int ascending, const void *keys_in,
+                                  const void *values_in, size_t value_bytes, size_t n,
+                                  const unsigned long long *splitters_host, size_t num_splitters, void *const *dst_keys,
+                                  void *const *dst_values);
+
+/* Peer memory for the above: export a bcb_malloc'ed buffer as a 64-byte handle, open a peer's handle in this process
+ * (cudaIpcGetMemHandle / cudaIpcOpenMemHandle with lazy peer access), close it again. */
+BCB_API int bcb_ipc_export(void *device_ptr, unsigned char *handle64);
+BCB_API int bcb_ipc_open(const unsigned char *handle64, void **device_ptr);
+BCB_API int bcb_ipc_close(void *device_ptr);
 
 /* ---- scan ---- */
 /* detail::scan (algorithm/detail/scan.hpp:22-39) with the operator-generic semantics of serial_scan.hpp:26-97:

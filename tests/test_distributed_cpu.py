@@ -82,6 +82,71 @@ class OracleLocalOps:
         ov = torch.from_numpy(self._np(values)[order].copy()) if values is not None else None
         return ok, ov, counts
 
+    # ---- emulated peer memory: POSIX shared memory stands in for CUDA IPC, memmove for the NVLink stores ----
+    def _buckets(self, keys, splitters, descending):
+        k = self._np(keys)
+        bits = k.view({1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[k.dtype.itemsize])
+        tk = cbd.transformed_keys(bits, dtype_code(k.dtype), not descending)
+        return np.searchsorted(splitters, tk, side="right")
+
+    def partition_counts(self, keys, splitters, descending):
+        return np.bincount(self._buckets(keys, splitters, descending), minlength=splitters.size + 1).astype(np.int64)
+
+    def partition_scatter(self, keys, values, splitters, descending, dst_keys, dst_values):
+        import ctypes
+        bucket = self._buckets(keys, splitters, descending)
+        for b in range(splitters.size + 1):
+            sel = np.flatnonzero(bucket == b)  # ascending positions: stable
+            if sel.size == 0:
+                continue
+            kb = np.ascontiguousarray(self._np(keys)[sel])
+            ctypes.memmove(int(dst_keys[b]), kb.ctypes.data, kb.nbytes)
+            if values is not None:
+                vb = np.ascontiguousarray(self._np(values)[sel])
+                ctypes.memmove(int(dst_values[b]), vb.ctypes.data, vb.nbytes)
+
+    def sort_copy(self, src_keys_ptr, out_keys, src_values_ptr, out_values, descending):
+        import ctypes
+        k = self._np(out_keys)
+        ctypes.memmove(k.ctypes.data, int(src_keys_ptr), k.nbytes)
+        if out_values is not None:
+            v = self._np(out_values)
+            ctypes.memmove(v.ctypes.data, int(src_values_ptr), v.nbytes)
+        self.sort(out_keys, out_values, descending)
+
+    def peer_alloc(self, nbytes):
+        import ctypes
+        from multiprocessing import shared_memory
+        if getattr(self, "fail_peer_alloc", False):
+            raise RuntimeError("no peer memory here")
+        shm = shared_memory.SharedMemory(create=True, size=nbytes)
+        self._shm = getattr(self, "_shm", {})
+        addr = ctypes.addressof(ctypes.c_char.from_buffer(shm.buf))
+        self._shm[addr] = shm
+        handle = np.zeros(64, dtype=np.uint8)
+        name = shm.name.encode()
+        handle[: len(name)] = np.frombuffer(name, dtype=np.uint8)
+        return addr, handle
+
+    def peer_open(self, handle):
+        import ctypes
+        from multiprocessing import shared_memory
+        name = bytes(handle[handle != 0]).decode()
+        shm = shared_memory.SharedMemory(name=name)
+        addr = ctypes.addressof(ctypes.c_char.from_buffer(shm.buf))
+        self._shm[addr] = shm
+        return addr
+
+    def peer_close(self, ptr):
+        self._shm.pop(ptr)  # (the mapping stays until process exit: ctypes still holds an export of the buffer)
+
+    def peer_free(self, ptr):
+        shm = self._shm.pop(ptr)
+        try:
+            shm.unlink()
+        except FileNotFoundError:
+            pass
+
     def gather_bits(self, keys, positions):
         k = self._np(keys)
         return k.view({1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[k.dtype.itemsize])[positions]
@@ -135,6 +200,14 @@ def _worker(rank, world, port, results):
         k, v = ctx.sort(torch.from_numpy(keys[lo:hi].copy()), torch.from_numpy(vals[lo:hi].copy()))
         out["pairs_k"], out["pairs_v"] = k.numpy().copy(), v.numpy().copy()
         out["stats"] = dict(ctx.last_stats)
+        # a second, larger call on the same Context: the receive buffers grow (collective re-allocation)
+        big = rng.integers(0, 2**32, size=60_000, dtype=np.uint64).astype(np.uint32)
+        blo, bhi = rank * 60_000 // world, (rank + 1) * 60_000 // world
+        out["big"] = ctx.sort(torch.from_numpy(big[blo:bhi].copy())).numpy().copy()
+        ctx.use_peer_memory = False     # NCCL-style all-to-all plan: same bytes
+        k1, v1 = ctx.sort(torch.from_numpy(keys[lo:hi].copy()), torch.from_numpy(vals[lo:hi].copy()))
+        out["pairs_k1"], out["pairs_v1"] = k1.numpy().copy(), v1.numpy().copy()
+        out["stats1"] = dict(ctx.last_stats)
         ops.force_sort_and_cut = True   # the fallback plan must give the same bytes
         k2, v2 = ctx.sort(torch.from_numpy(keys[lo:hi].copy()), torch.from_numpy(vals[lo:hi].copy()))
         out["pairs_k2"], out["pairs_v2"] = k2.numpy().copy(), v2.numpy().copy()
@@ -154,6 +227,14 @@ def _worker(rank, world, port, results):
         out["sum"] = ctx.reduce(mine)
         out["min"] = ctx.reduce(mine, "min")
         out["acc"] = ctx.accumulate(mine, 5)
+        # peer mapping unavailable on one rank only: every rank must fall back together
+        ctx2 = cbd.Context(local_ops=ops, samples_per_rank=64)
+        ops.fail_peer_alloc = (rank == 1)
+        out["fb"] = ctx2.sort(torch.from_numpy(allk[lo:hi].copy()), None, descending=True).numpy().copy()
+        out["stats_fb"] = dict(ctx2.last_stats)
+        ops.fail_peer_alloc = False
+        ctx.peer.release()
+        ctx2.peer.release()
         results[rank] = out
     finally:
         dist.destroy_process_group()
@@ -180,7 +261,14 @@ def test_two_rank_gloo_matches_single_device_oracle():
     assert np.concatenate([r["pairs_v"] for r in res]).tobytes() == ev.tobytes()
     assert np.concatenate([r["pairs_k2"] for r in res]).tobytes() == ek.tobytes()
     assert np.concatenate([r["pairs_v2"] for r in res]).tobytes() == ev.tobytes()
-    assert res[0]["stats"]["plan"] == "partition" and res[0]["stats2"]["plan"] == "sort-and-cut"
+    assert np.concatenate([r["pairs_k1"] for r in res]).tobytes() == ek.tobytes()
+    assert np.concatenate([r["pairs_v1"] for r in res]).tobytes() == ev.tobytes()
+    big = rng.integers(0, 2**32, size=60_000, dtype=np.uint64).astype(np.uint32)
+    assert np.concatenate([r["big"] for r in res]).tobytes() == oracle.radix_sort(big, False).tobytes()
+    assert np.concatenate([r["fb"] for r in res]).tobytes() == oracle.radix_sort(allk, True).tobytes()
+    assert [r["stats_fb"]["plan"] for r in res] == ["partition", "partition"]
+    assert res[0]["stats"]["plan"] == "peer-scatter" and res[0]["stats1"]["plan"] == "partition"
+    assert res[0]["stats2"]["plan"] == "sort-and-cut"
     assert res[0]["stats"]["imbalance"] < 1.5
     x = rng.integers(-2**31, 2**31 - 1, size=9001).astype(np.int32)
     np.testing.assert_array_equal(np.concatenate([r["excl"] for r in res]), oracle.scan(x, "plus", True, 11))

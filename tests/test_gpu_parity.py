@@ -315,3 +315,36 @@ def test_speculation_fallback_path_in_subprocess():
     env = dict(os.environ, BCB_SORT_FORCE_FALLBACK="1")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0 and "FALLBACK_OK" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("dtype", ["uint", "float", "ulong", "short"])
+def test_radix_key_sortedness_check_detects_every_seam(dtype, gpu):
+    """The speculative sort trusts bcb_is_sorted_by_radix_key on its own output: one swapped pair anywhere -- inside a
+    128-bit vector, across vectors, across a warp's 32 vectors, into the scalar tail, at either end -- must be seen."""
+    import ctypes
+    import compute_b200 as cb
+    from compute_b200.core import dtype_code
+    n = 70_003
+    k = oracle.radix_sort(random_keys(dtype, n, seed=5, mode="bits"), False)
+    q = cb.command_queue()
+
+    def check(arr, asc=True):
+        d = gpu.to_dev(arr)
+        res = ctypes.c_int(-1)
+        cb._capi.check(cb.lib().bcb_is_sorted_by_radix_key(q.handle, dtype_code(arr.dtype), int(asc), d.data_ptr(), arr.size,
+                                                             ctypes.byref(res)))
+        return bool(res.value)
+
+    assert check(k)
+    assert check(oracle.radix_sort(k, True), asc=False)
+    vec = 16 // k.dtype.itemsize
+    positions = [0, 1, vec - 1, vec, 32 * vec - 1, 32 * vec, 64 * vec - 1, 128 * vec - 1, 128 * vec, 256 * vec - 1, 1000, n // 2, (n // vec) * vec - 1, (n // vec) * vec, n - 2]
+    bits = k.view({2: np.uint16, 4: np.uint32, 8: np.uint64}[k.dtype.itemsize])
+    for p in positions:
+        if p + 1 >= n:
+            continue
+        if oracle.radix_key(dtype, True, int(bits[p])) == oracle.radix_key(dtype, True, int(bits[p + 1])):
+            continue  # swapping equal keys keeps the range sorted
+        bad = k.copy()
+        bad[p], bad[p + 1] = k[p + 1], k[p]
+        assert not check(bad), (dtype, p)
