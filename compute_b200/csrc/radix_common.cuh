@@ -103,10 +103,12 @@ __device__ __forceinline__ unsigned pass_digit(K raw, int shift, const Transform
     if constexpr (IDENT == kDigitIdent) {
         return (unsigned)(raw >> shift) & (kRadixSize - 1);
     } else if constexpr (IDENT == kDigitSplit) {
-        const unsigned long long t = transformed_key<K>(raw, tf);
+        // compares in the key's own compute width (splitters of narrower keys fit it by construction)
+        typedef typename key_traits<K>::U U;
+        const U t = (U)transformed_key<K>(raw, tf);
         unsigned d = 0;
 #pragma unroll
-        for (int j = 0; j < kMaxSplitters; j++) d += (j < tf.nsplit && t >= tf.split[j]) ? 1u : 0u;
+        for (int j = 0; j < kMaxSplitters; j++) d += (j < tf.nsplit && t >= (U)tf.split[j]) ? 1u : 0u;
         return d;
     } else {
         return digit_of<K>(raw, shift, tf);

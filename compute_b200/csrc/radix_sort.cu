@@ -106,7 +106,10 @@ __global__ void __launch_bounds__(kRadixSize) digit_scan(const unsigned *__restr
 //   kRankOrderedAtoms (experimental, BCB_SORT_RANK=ordered): rank = atomicAdd(count, 1).  One instruction per key, but
 //                     stable only if same-address atomics of one warp instruction are applied in lane order, which
 //                     CUDA does not promise; never selected by default.
-enum { kRankAtomicOr = 0, kRankOrderedAtoms = 1 };
+//   kRankBallot       splitter mode only (at most 8 buckets + padding): the peer mask of a key comes from three
+//                     ballots over the bits of its bucket, the running count of bucket b lives in a register of lane
+//                     b.  No shared memory, no atomics (same-address atomics of 2..8 buckets would serialise).
+enum { kRankAtomicOr = 0, kRankOrderedAtoms = 1, kRankBallot = 2 };
 
 template <int VB> struct value_type;
 template <> struct value_type<0> { typedef unsigned char type; };
@@ -204,6 +207,28 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
             if (((e & 0xffffu) >> (lane & 15u)) == 1u) wt[d] = (e & 0xffff0000u) + ((below + 1u) << 16);  // highest peer
             __syncwarp();
         }
+    } else if constexpr (RANK == kRankBallot) {
+        static_assert(IDENT == kDigitSplit || RANK != kRankBallot, "ballot ranking covers the splitter buckets only");
+        const unsigned lt = (1u << lane) - 1u;
+        unsigned cnt = 0;  // lane b < 8: keys of bucket b seen so far by this warp; lane 8: padding
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            unsigned d = pass_digit<K, IDENT>(key[i], shift, tf);
+            const bool pad = !FULL && off0 + i * VWL >= valid;
+            if (pad) d = 8;
+            unsigned peers = 0xffffffffu, mine = 0xffffffffu;  // lanes with my key's bucket / with bucket == my lane id
+#pragma unroll
+            for (int b = 0; b < (FULL ? 3 : 4); b++) {
+                const unsigned bal = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+                peers &= ((d >> b) & 1u) ? bal : ~bal;
+                mine &= ((lane >> b) & 1u) ? bal : ~bal;
+            }
+            const unsigned before = __shfl_sync(0xffffffffu, cnt, d);
+            rank[i] = (unsigned short)(before + __popc(peers & lt));
+            cnt += __popc(mine);  // (lanes above 8 count buckets that do not exist: never read)
+        }
+        if (lane <= kMaxSplitters) wt[lane] = cnt;
+        if (!FULL && lane == 8) wt[kRadixSize - 1] = cnt;  // padding sorts last within the tile, as in the other modes
     } else {
 #pragma unroll
         for (int i = 0; i < ITEMS; i++) {
@@ -656,25 +681,69 @@ static int run_pass(StreamState *st, const void *kin, void *kout, const void *vi
 }
 
 // ---- multi-GPU partition pass: bucket histogram by splitters ---------------------------------------------
+// ge[j] = number of keys whose transformed key is >= splitter j (7 compare-and-add per key, 128-bit loads); the bucket
+// sizes are the differences: bucket b = ge[b-1] - ge[b] with ge[-1] = n, ge[nsplit] = 0
 template <typename K>
 __global__ void __launch_bounds__(256) split_histogram(const K *__restrict__ keys, size_t n, unsigned *__restrict__ hist, Transform tf)
 {
-    unsigned cnt[kMaxSplitters + 1];
+    typedef typename key_traits<K>::U U;
+    constexpr int VEC = 16 / sizeof(K);
+    unsigned ge[kMaxSplitters];
+    U sp[kMaxSplitters];
 #pragma unroll
-    for (int j = 0; j <= kMaxSplitters; j++) cnt[j] = 0;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const unsigned d = pass_digit<K, kDigitSplit>(__ldg(keys + i), 0, tf);
+    for (int j = 0; j < kMaxSplitters; j++) { ge[j] = 0; sp[j] = (U)tf.split[j]; }
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    size_t done = 0;
+    if ((((uintptr_t)keys) & 15) == 0) {
+        const size_t nvec = n / VEC;
+        size_t v = gid;
+        for (; v + stride < nvec; v += 2 * stride) {  // two independent 128-bit loads in flight
+            const uint4 x0 = ld_stream_v4(keys + v * VEC), x1 = ld_stream_v4(keys + (v + stride) * VEC);
+            const K *e0 = reinterpret_cast<const K *>(&x0), *e1 = reinterpret_cast<const K *>(&x1);
 #pragma unroll
-        for (int j = 0; j <= kMaxSplitters; j++) cnt[j] += (d == (unsigned)j);
+            for (int i = 0; i < VEC; i++) {
+                const U t0 = (U)transformed_key<K>(e0[i], tf), t1 = (U)transformed_key<K>(e1[i], tf);
+#pragma unroll
+                for (int j = 0; j < kMaxSplitters; j++) ge[j] += (unsigned)(t0 >= sp[j]) + (unsigned)(t1 >= sp[j]);
+            }
+        }
+        for (; v < nvec; v += stride) {
+            const uint4 x0 = ld_stream_v4(keys + v * VEC);
+            const K *e0 = reinterpret_cast<const K *>(&x0);
+#pragma unroll
+            for (int i = 0; i < VEC; i++) {
+                const U t0 = (U)transformed_key<K>(e0[i], tf);
+#pragma unroll
+                for (int j = 0; j < kMaxSplitters; j++) ge[j] += (unsigned)(t0 >= sp[j]);
+            }
+        }
+        done = nvec * VEC;
     }
+    for (size_t i = done + gid; i < n; i += stride) {
+        const U t = (U)transformed_key<K>(__ldg(keys + i), tf);
 #pragma unroll
-    for (int j = 0; j <= kMaxSplitters; j++) {
-        unsigned v = cnt[j];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-        if ((threadIdx.x & 31u) == 0 && v) atomicAdd(hist + j, v);
+        for (int j = 0; j < kMaxSplitters; j++) ge[j] += (unsigned)(t >= sp[j]);
     }
+    __shared__ unsigned block_ge[kMaxSplitters];
+    if (threadIdx.x < kMaxSplitters) block_ge[threadIdx.x] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kMaxSplitters; j++) {
+        const unsigned v = __reduce_add_sync(0xffffffffu, ge[j]);
+        if ((threadIdx.x & 31u) == 0 && v) atomicAdd(block_ge + j, v);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < tf.nsplit && block_ge[threadIdx.x]) atomicAdd(hist + kRadixSize + threadIdx.x, block_ge[threadIdx.x]);
+}
+
+// hist[256 + j] = ge[j]  ->  hist[b] = size of bucket b
+__global__ void split_counts_kernel(unsigned *hist, unsigned n, int nsplit)
+{
+    const int b = threadIdx.x;
+    if (b > nsplit) return;
+    const unsigned hi = b == 0 ? n : hist[kRadixSize + b - 1];
+    const unsigned lo = b == nsplit ? 0u : hist[kRadixSize + b];
+    hist[b] = hi - lo;
 }
 
 // bucket sizes of the splitter partition: hist[0..nsplit] on the device, copied to counts_host (blocks)
@@ -682,7 +751,7 @@ template <typename K>
 static int partition_counts_typed(StreamState *st, const void *kin, size_t n, const Transform &tf, unsigned long long *counts_host)
 {
     unsigned *hist = st->hist;
-    BCB_CUDA_TRY(cudaMemsetAsync(hist, 0, kRadixSize * sizeof(unsigned), st->stream));
+    BCB_CUDA_TRY(cudaMemsetAsync(hist, 0, 2 * kRadixSize * sizeof(unsigned), st->stream));
     size_t blocks = (n + 256 * 16 - 1) / (256 * 16);
     const size_t cap = (size_t)st->sm_count * 8;
     if (blocks > cap) blocks = cap;
@@ -691,6 +760,8 @@ static int partition_counts_typed(StreamState *st, const void *kin, size_t n, co
         LaunchTimer timer(st, BCB_K_RADIX_HISTOGRAM);
         split_histogram<K><<<(unsigned)blocks, 256, 0, st->stream>>>((const K *)kin, n, hist, tf);
     }
+    BCB_CUDA_TRY(cudaGetLastError());
+    split_counts_kernel<<<1, 32, 0, st->stream>>>(hist, (unsigned)n, tf.nsplit);
     BCB_CUDA_TRY(cudaGetLastError());
     unsigned host_counts[kMaxSplitters + 1];
     BCB_CUDA_TRY(cudaMemcpyAsync(host_counts, hist, sizeof(host_counts), cudaMemcpyDeviceToHost, st->stream));
@@ -709,7 +780,7 @@ static int partition_scatter_typed(StreamState *st, const void *kin, const void 
     const size_t tiles = (n + tile - 1) / tile;
     void *lb;
     BCB_TRY(lookback_reserve(st, tiles * kRadixSize * sizeof(unsigned long long), &lb));
-    return launch_pass_impl<K, VB, THREADS, ITEMS, kLookbackBatch, kRankAtomicOr, kDigitSplit>(st, kin, nullptr, vin, nullptr, base,
+    return launch_pass_impl<K, VB, THREADS, ITEMS, kLookbackBatch, kRankBallot, kDigitSplit>(st, kin, nullptr, vin, nullptr, base,
                                                                                               (unsigned long long *)lb, n, 0, tf);
 }
 

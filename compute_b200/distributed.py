@@ -326,10 +326,19 @@ class Context:
         if self.world == 1:
             return arr[None]
         dev = "cuda" if self.ops.device_type == "cuda" else "cpu"
-        t = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1).copy()).to(dev)
-        outs = [torch.empty_like(t) for _ in range(self.world)]
-        dist.all_gather(outs, t, group=self.group)
-        return np.stack([o.cpu().numpy().view(arr.dtype).reshape(arr.shape) for o in outs])
+        t = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1).copy()).to(dev, non_blocking=True)
+        out = torch.empty(self.world * t.numel(), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(out, t, group=self.group)
+        return out.cpu().numpy().view(arr.dtype).reshape((self.world,) + arr.shape)  # one device->host copy
+
+    def _gather_partials(self, local: np.ndarray, has: bool):
+        """One all-gather of (partial value, "shard not empty") -> (partials[world], present[world])."""
+        w = local.dtype.itemsize
+        packed = np.zeros(16, dtype=np.uint8)
+        packed[:w] = local.reshape(-1)[:1].view(np.uint8)
+        packed[8] = 1 if has else 0
+        allp = self._all_gather_np(packed)
+        return allp[:, :w].copy().view(local.dtype).reshape(-1), allp[:, 8].astype(np.int32)
 
     def _all_to_all(self, src: torch.Tensor, send_counts: np.ndarray, recv_counts: np.ndarray) -> torch.Tensor:
         """variable-size all-to-all of contiguous row slices (bitwise; rows may be wider than one element)."""
@@ -442,9 +451,7 @@ class Context:
         np_dt = NP_OF_CODE[dtype_code(out.dtype)].type
         w = np.dtype(np_dt).itemsize
         local = (part.view(_BITS_VIEW[w]).cpu().numpy().view(np_dt) if part is not None else np.zeros(1, np_dt))
-        has = np.array([1 if x.numel() else 0], dtype=np.int32)
-        partials = self._all_gather_np(local).reshape(-1)
-        present = self._all_gather_np(has).reshape(-1)
+        partials, present = self._gather_partials(local, bool(x.numel()))
         carry = None if not exclusive else np_dt(0 if init is None else init)
         fn = _NP_OPS[op]
         with np.errstate(over="ignore"):
@@ -477,8 +484,7 @@ class Context:
             local = np.zeros(1, np_dt)
         if self.world == 1:
             return local[0] if x.numel() else None
-        partials = self._all_gather_np(local).reshape(-1)
-        present = self._all_gather_np(np.array([1 if x.numel() else 0], dtype=np.int32)).reshape(-1)
+        partials, present = self._gather_partials(local, bool(x.numel()))
         acc = None
         fn = _NP_OPS[op]
         with np.errstate(over="ignore"):

@@ -348,3 +348,75 @@ def test_radix_key_sortedness_check_detects_every_seam(dtype, gpu):
         bad = k.copy()
         bad[p], bad[p + 1] = k[p + 1], k[p]
         assert not check(bad), (dtype, p)
+
+
+# ------------------------------------------------------------------------------ multi-GPU building blocks, on one GPU
+@pytest.mark.parametrize("dtype,value_bytes,n", [("uint", 0, 1 << 22), ("uint", 0, 100_001), ("float", 0, 7681), ("int", 8, 300_001),
+                                                  ("ulong", 4, 50_000), ("short", 0, 9999), ("uchar", 0, 70_000), ("double", 12, 5000)])
+def test_radix_sort_copy_leaves_source_untouched(dtype, value_bytes, n, gpu):
+    import compute_b200 as cb
+    from compute_b200.core import dtype_code
+    k = random_keys(dtype, n, seed=21, mode="bits")
+    v = np.arange(n * max(1, value_bytes), dtype=np.uint8).reshape(n, max(1, value_bytes)) if value_bytes else None
+    for desc in (False, True):
+        dk, dv = gpu.to_dev(k), (gpu.to_dev(v) if v is not None else None)
+        ok = gpu.to_dev(np.zeros_like(k))
+        ov = gpu.to_dev(np.zeros_like(v)) if v is not None else None
+        q = cb.command_queue()
+        cb._capi.check(cb.lib().bcb_radix_sort_copy(q.handle, dtype_code(k.dtype), int(not desc), dk.data_ptr(), ok.data_ptr(), n,
+                                                    None if v is None else dv.data_ptr(), None if v is None else ov.data_ptr(),
+                                                    value_bytes))
+        q.finish()
+        assert gpu.to_host(dk, k.dtype).tobytes() == k.tobytes()
+        if v is None:
+            assert gpu.to_host(ok, k.dtype).tobytes() == oracle.radix_sort(k, desc).tobytes()
+        else:
+            ek, ev = oracle.radix_sort(k, desc, v)
+            assert gpu.to_host(ok, k.dtype).tobytes() == ek.tobytes()
+            assert gpu.to_host(ov, v.dtype).reshape(v.shape).tobytes() == ev.tobytes()
+            assert gpu.to_host(dv, v.dtype).reshape(v.shape).tobytes() == v.tobytes()
+
+
+@pytest.mark.parametrize("dtype,value_bytes,nsplit,n", [("uint", 0, 1, 1 << 21), ("uint", 0, 7, 1_000_003), ("float", 4, 3, 200_000),
+                                                         ("long", 8, 7, 77_777), ("short", 0, 2, 50_001), ("int", 0, 5, 100)])
+def test_partition_counts_and_scatter_to_separate_buffers(dtype, value_bytes, nsplit, n, gpu):
+    """The multi-GPU exchange on one GPU: every bucket goes to its own destination buffer, stable, with exact counts."""
+    import ctypes
+    import torch
+    import compute_b200 as cb
+    from compute_b200 import distributed as cbd
+    from compute_b200.core import dtype_code
+    k = random_keys(dtype, n, seed=33, mode="bits" if dtype != "short" else "few")
+    w = k.dtype.itemsize
+    bits = k.view({1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[w])
+    for desc in (False, True):
+        tk = cbd.transformed_keys(bits, dtype_code(k.dtype), not desc)
+        sp = np.sort(tk[np.random.default_rng(3).integers(0, n, size=nsplit)]).astype(np.uint64)
+        if nsplit >= 3:
+            sp[1] = sp[0]  # an empty bucket
+        bucket = np.searchsorted(sp, tk, side="right")
+        exp_counts = np.bincount(bucket, minlength=nsplit + 1)
+        q = cb.command_queue()
+        dk = gpu.to_dev(k)
+        v = (np.arange(n * value_bytes, dtype=np.uint8).reshape(n, value_bytes)) if value_bytes else None
+        dv = gpu.to_dev(v) if v is not None else None
+        counts = np.zeros(nsplit + 1, dtype=np.uint64)
+        cb._capi.check(cb.lib().bcb_partition_counts(q.handle, dtype_code(k.dtype), int(not desc), dk.data_ptr(), n, sp.ctypes.data, nsplit,
+                                                     counts.ctypes.data))
+        np.testing.assert_array_equal(counts.astype(np.int64), exp_counts)
+        outs_k = [torch.zeros(int(c) * w + 16, dtype=torch.uint8, device="cuda") for c in exp_counts]
+        outs_v = [torch.zeros(int(c) * value_bytes + 16, dtype=torch.uint8, device="cuda") for c in exp_counts]
+        pk = (ctypes.c_void_p * (nsplit + 1))(*[t.data_ptr() for t in outs_k])
+        pv = (ctypes.c_void_p * (nsplit + 1))(*[t.data_ptr() for t in outs_v])
+        cb._capi.check(cb.lib().bcb_partition_scatter(q.handle, dtype_code(k.dtype), int(not desc), dk.data_ptr(),
+                                                      None if v is None else dv.data_ptr(), value_bytes, n, sp.ctypes.data, nsplit, pk,
+                                                      pv if v is not None else None))
+        q.finish()
+        for b in range(nsplit + 1):
+            sel = np.flatnonzero(bucket == b)
+            got = outs_k[b].cpu().numpy()
+            assert got[: sel.size * w].tobytes() == k[sel].tobytes(), (dtype, desc, b)
+            assert not got[sel.size * w:].any()  # nothing written past the bucket
+            if v is not None:
+                gv = outs_v[b].cpu().numpy()
+                assert gv[: sel.size * value_bytes].tobytes() == v[sel].tobytes(), (dtype, desc, b)
