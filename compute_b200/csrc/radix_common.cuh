@@ -106,10 +106,18 @@ __device__ __forceinline__ unsigned pass_digit(K raw, int shift, const Transform
         // compares in the key's own compute width (splitters of narrower keys fit it by construction)
         typedef typename key_traits<K>::U U;
         const U t = (U)transformed_key<K>(raw, tf);
-        unsigned d = 0;
+        // unused splitters are all-ones (split_transform): they can only count for t == all-ones, whose bucket is the
+        // last one anyway, hence the clamp instead of a "j < nsplit" test per compare
+        // (nsplit is uniform: 2 ranks pay for one compare, 4 ranks for three, 8 ranks for seven)
+        unsigned d = (t >= (U)tf.split[0]) ? 1u : 0u;
+        if (tf.nsplit > 1) {
+            d += ((t >= (U)tf.split[1]) ? 1u : 0u) + ((t >= (U)tf.split[2]) ? 1u : 0u);
+            if (tf.nsplit > 3) {
 #pragma unroll
-        for (int j = 0; j < kMaxSplitters; j++) d += (j < tf.nsplit && t >= (U)tf.split[j]) ? 1u : 0u;
-        return d;
+                for (int j = 3; j < kMaxSplitters; j++) d += (t >= (U)tf.split[j]) ? 1u : 0u;
+            }
+        }
+        return min(d, (unsigned)tf.nsplit);
     } else {
         return digit_of<K>(raw, shift, tf);
     }

@@ -191,6 +191,8 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
 
     // ---- rank inside the warp (stable: item-major, lane-minor == memory order) ----
     unsigned short rank[ITEMS];
+    unsigned dpk[IDENT == kDigitSplit ? (ITEMS + 7) / 8 : 1] = {};  // splitter mode: packed buckets of this thread's keys
+    unsigned char *dig_sorted = elem_buf + (size_t)TILE * L::kElem;  // splitter mode: bucket of every sorted-tile position
     if constexpr (RANK == kRankAtomicOr) {
         const unsigned hbit = 1u << (lane & 15u);
         const unsigned hlt = hbit - 1u;
@@ -211,23 +213,39 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
         static_assert(IDENT == kDigitSplit || RANK != kRankBallot, "ballot ranking covers the splitter buckets only");
         const unsigned lt = (1u << lane) - 1u;
         unsigned cnt = 0;  // lane b < 8: keys of bucket b seen so far by this warp; lane 8: padding
+        // lane_inv[b] = 0 if bit b of my lane id is set, else all-ones: (ballot ^ lane_inv[b]) = lanes agreeing with it
+        const unsigned lane_inv0 = (lane & 1u) ? 0u : ~0u, lane_inv1 = (lane & 2u) ? 0u : ~0u, lane_inv2 = (lane & 4u) ? 0u : ~0u,
+                       lane_inv3 = (lane & 8u) ? 0u : ~0u;
+        const int nbits = tf.nsplit > 3 ? 3 : (tf.nsplit > 1 ? 2 : 1);  // uniform: bits that tell the buckets apart
 #pragma unroll
         for (int i = 0; i < ITEMS; i++) {
             unsigned d = pass_digit<K, IDENT>(key[i], shift, tf);
             const bool pad = !FULL && off0 + i * VWL >= valid;
             if (pad) d = 8;
-            unsigned peers = 0xffffffffu, mine = 0xffffffffu;  // lanes with my key's bucket / with bucket == my lane id
-#pragma unroll
-            for (int b = 0; b < (FULL ? 3 : 4); b++) {
-                const unsigned bal = __ballot_sync(0xffffffffu, (d >> b) & 1u);
-                peers &= ((d >> b) & 1u) ? bal : ~bal;
-                mine &= ((lane >> b) & 1u) ? bal : ~bal;
+            dpk[i / 8] |= d << (4 * (i % 8));  // the bucket costs up to 7 compares: evaluate it once, keep 4 bits per key
+            // peers = lanes whose key has my key's bucket; mine = lanes whose key's bucket is my lane id
+            unsigned bal = __ballot_sync(0xffffffffu, d & 1u);
+            unsigned peers = bal ^ ((d & 1u) - 1u), mine = bal ^ lane_inv0;
+            if (nbits > 1) {
+                bal = __ballot_sync(0xffffffffu, d & 2u);
+                peers &= bal ^ (((d >> 1) & 1u) - 1u);
+                mine &= bal ^ lane_inv1;
+                if (nbits > 2) {
+                    bal = __ballot_sync(0xffffffffu, d & 4u);
+                    peers &= bal ^ (((d >> 2) & 1u) - 1u);
+                    mine &= bal ^ lane_inv2;
+                }
+            }
+            if (!FULL) {
+                bal = __ballot_sync(0xffffffffu, d & 8u);
+                peers &= bal ^ (((d >> 3) & 1u) - 1u);
+                mine &= bal ^ lane_inv3;
             }
             const unsigned before = __shfl_sync(0xffffffffu, cnt, d);
             rank[i] = (unsigned short)(before + __popc(peers & lt));
-            cnt += __popc(mine);  // (lanes above 8 count buckets that do not exist: never read)
+            cnt += __popc(mine);  // (lanes that stand for no bucket count garbage that is never read)
         }
-        if (lane <= kMaxSplitters) wt[lane] = cnt;
+        if ((int)lane <= tf.nsplit) wt[lane] = cnt;  // (higher lanes stand for no bucket: with fewer ballot bits they hold aliases)
         if (!FULL && lane == 8) wt[kRadixSize - 1] = cnt;  // padding sorts last within the tile, as in the other modes
     } else {
 #pragma unroll
@@ -276,11 +294,14 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
     // ---- reorder the tile through shared memory ----
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
-        unsigned d = pass_digit<K, IDENT>(key[i], shift, tf);
+        unsigned d;
+        if constexpr (IDENT == kDigitSplit) d = (dpk[i / 8] >> (4 * (i % 8))) & 15u;
+        else d = pass_digit<K, IDENT>(key[i], shift, tf);
         if (!FULL && off0 + i * VWL >= valid) d = kRadixSize - 1;
         const unsigned pos = (wt[d] >> CSHIFT) + rank[i];
         rank[i] = (unsigned short)pos;
         keys_sorted[pos] = key[i];
+        if constexpr (IDENT == kDigitSplit) dig_sorted[pos] = (unsigned char)d;
     }
 
     // ---- prefetch the next tile's keys into the (now dead) key registers: the loads fly during the look-back and
@@ -346,7 +367,9 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
         const unsigned p = i * THREADS + tid;
         if (FULL || p < valid) {
             const K k = keys_sorted[p];
-            const unsigned d = pass_digit<K, IDENT>(k, shift, tf);
+            unsigned d;
+            if constexpr (IDENT == kDigitSplit) d = dig_sorted[p];
+            else d = pass_digit<K, IDENT>(k, shift, tf);
             if constexpr (VB > 0) dig[i] = (unsigned char)d;
             if constexpr (IDENT == kDigitSplit) {
                 const unsigned long long *addr = reinterpret_cast<const unsigned long long *>(out_base);
@@ -471,17 +494,19 @@ static int launch_pass_impl(StreamState *st, const void *kin, void *kout, const 
                        unsigned long long *lookback, size_t n, int shift, const Transform &tf)
 {
     typedef PassSmem<K, VB, THREADS, ITEMS, RANK> L;
+    static_assert((IDENT == kDigitSplit) == (RANK == kRankBallot), "the splitter pass and the ballot ranking go together");
+    constexpr size_t kSmemBytes = L::kBytes + (IDENT == kDigitSplit ? (size_t)L::TILE : 0);  // + bucket byte per position
     static bool configured[64] = {};  // per instantiation and device: opt in to > 48 KB dynamic shared memory once
     auto kernel = onesweep_pass<K, VB, THREADS, ITEMS, LBATCH, RANK, IDENT, MINB>;
     if (st->device >= 64 || !configured[st->device]) {
-        BCB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kBytes));
+        BCB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
         if (st->device < 64) configured[st->device] = true;
     }
     const size_t tiles = (n + L::TILE - 1) / L::TILE;
     static int resident[64] = {};  // CTAs of this kernel that fit one SM
     int per_sm = (st->device < 64) ? resident[st->device] : 0;
     if (per_sm == 0) {
-        BCB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, L::kBytes));
+        BCB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, kSmemBytes));
         if (per_sm < 1) per_sm = 1;
         if (st->device < 64) resident[st->device] = per_sm;
     }
@@ -491,7 +516,7 @@ static int launch_pass_impl(StreamState *st, const void *kin, void *kout, const 
     BCB_TRY(next_epoch(st, &epoch));
     const unsigned long long tbase = st->ticket_base;  // (tickets are no longer drawn by this kernel)
     LaunchTimer timer(st, BCB_K_ONESWEEP_PASS);
-    kernel<<<(unsigned)grid, THREADS, L::kBytes, st->stream>>>((const K *)kin, (K *)kout, vin, vout, base, lookback, epoch,
+    kernel<<<(unsigned)grid, THREADS, kSmemBytes, st->stream>>>((const K *)kin, (K *)kout, vin, vout, base, lookback, epoch,
                                                                st->control + kControlTicket, tbase, n, tiles, shift, tf);
     BCB_CUDA_TRY(cudaGetLastError());
     return BCB_SUCCESS;
@@ -1082,7 +1107,7 @@ static int split_transform(int key_dtype, int ascending, const unsigned long lon
     if (num_splitters && !splitters_host) return BCB_EINVAL;
     *tf = make_transform(key_dtype, ascending != 0);
     tf->nsplit = (int)num_splitters;
-    for (size_t j = 0; j < num_splitters; j++) tf->split[j] = splitters_host[j];
+    for (size_t j = 0; j < (size_t)kMaxSplitters; j++) tf->split[j] = j < num_splitters ? splitters_host[j] : ~0ull;
     return BCB_SUCCESS;
 }
 
