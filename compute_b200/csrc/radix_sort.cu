@@ -75,6 +75,63 @@ radix_histogram(const K *__restrict__ keys, size_t n, unsigned *__restrict__ his
     }
 }
 
+// Variant with one counter COLUMN per lane: bin (p, d) of lane l lives at word (p*256 + d)*COLS + (l % COLS), i.e. in
+// bank l -- the 32 atomics of a warp instruction never share a bank, whatever the digits are (the plain layout above
+// pays ~3 wavefronts per instruction for random digits).  One 1024-thread CTA per SM owns NPASS x 256 x COLS counters
+// (128 KB for 32- and 64-bit keys); the columns are summed when the CTA flushes.
+template <typename K, int COLS>
+__global__ void __launch_bounds__(1024, 1)
+radix_histogram_columns(const K *__restrict__ keys, size_t n, unsigned *__restrict__ hist, Transform tf)
+{
+    constexpr int NPASS = sizeof(K);
+    constexpr int VEC = 16 / sizeof(K);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned *sh = reinterpret_cast<unsigned *>(smem_raw);
+    for (int i = threadIdx.x; i < NPASS * kRadixSize * COLS / 4; i += blockDim.x) reinterpret_cast<uint4 *>(sh)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    unsigned *mine = sh + (threadIdx.x & (COLS - 1));
+
+    const size_t gthreads = (size_t)gridDim.x * blockDim.x;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t head = ((16 - ((uintptr_t)keys & 15)) & 15) / sizeof(K);
+    if (head > n) head = n;
+    const size_t nvec = (n - head) / VEC;
+    const size_t tail_start = head + nvec * VEC;
+    const uint4 *vin = reinterpret_cast<const uint4 *>(keys + head);
+
+    auto count_key = [&](K k) {
+#pragma unroll
+        for (int p = 0; p < NPASS; p++) atomicAdd(mine + (p * kRadixSize + digit_of<K>(k, p * kRadixBits, tf)) * COLS, 1u);
+    };
+    size_t v = gid;
+    for (; v + gthreads < nvec; v += 2 * gthreads) {  // two independent 128-bit loads in flight
+        const uint4 a = ld_stream_v4(vin + v);
+        const uint4 b = ld_stream_v4(vin + v + gthreads);
+        const K *ea = reinterpret_cast<const K *>(&a);
+        const K *eb = reinterpret_cast<const K *>(&b);
+#pragma unroll
+        for (int k = 0; k < VEC; k++) count_key(ea[k]);
+#pragma unroll
+        for (int k = 0; k < VEC; k++) count_key(eb[k]);
+    }
+    for (; v < nvec; v += gthreads) {
+        const uint4 a = ld_stream_v4(vin + v);
+        const K *ea = reinterpret_cast<const K *>(&a);
+#pragma unroll
+        for (int k = 0; k < VEC; k++) count_key(ea[k]);
+    }
+    if (gid < head) count_key(keys[gid]);
+    if (tail_start + gid < n) count_key(keys[tail_start + gid]);
+
+    __syncthreads();
+    for (int bin = threadIdx.x; bin < NPASS * kRadixSize; bin += blockDim.x) {
+        unsigned c = 0;
+#pragma unroll
+        for (int j = 0; j < COLS; j++) c += sh[bin * COLS + ((j + threadIdx.x) & (COLS - 1))];  // rotated: conflict-free
+        if (c) atomicAdd(hist + bin, c);
+    }
+}
+
 // ---- 2. exclusive scan of each digit histogram: hist[p][d] -> base[p][d] -------------------------
 __global__ void __launch_bounds__(kRadixSize) digit_scan(const unsigned *__restrict__ hist, unsigned *__restrict__ base)
 {
@@ -109,7 +166,12 @@ __global__ void __launch_bounds__(kRadixSize) digit_scan(const unsigned *__restr
 //   kRankBallot       splitter mode only (at most 8 buckets + padding): the peer mask of a key comes from three
 //                     ballots over the bits of its bucket, the running count of bucket b lives in a register of lane
 //                     b.  No shared memory, no atomics (same-address atomics of 2..8 buckets would serialise).
-enum { kRankAtomicOr = 0, kRankOrderedAtoms = 1, kRankBallot = 2 };
+//   kRankTwoSweep     the ordered-atomics idea without the rank registers: sweep 1 only counts (atomicAdd, result
+//                     unused), the tables turn into offsets, sweep 2 repeats the same atomicAdds in the same order
+//                     and takes the returned value as the key's position.  Same assumption, same verification;
+//                     the freed registers allow larger tiles.  Keys only.
+enum { kRankAtomicOr = 0, kRankOrderedAtoms = 1, kRankBallot = 2, kRankTwoSweep = 3 };
+static inline bool rank_is_speculative(int rank) { return rank == kRankOrderedAtoms || rank == kRankTwoSweep; }
 
 template <int VB> struct value_type;
 template <> struct value_type<0> { typedef unsigned char type; };
@@ -190,7 +252,8 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
     (void)ticket; (void)ticket_base;
 
     // ---- rank inside the warp (stable: item-major, lane-minor == memory order) ----
-    unsigned short rank[ITEMS];
+    static_assert(VB == 0 || RANK != kRankTwoSweep, "the two-sweep ranking keeps no ranks for a payload");
+    unsigned short rank[RANK == kRankTwoSweep ? 1 : ITEMS];
     unsigned dpk[IDENT == kDigitSplit ? (ITEMS + 7) / 8 : 1] = {};  // splitter mode: packed buckets of this thread's keys
     unsigned char *dig_sorted = elem_buf + (size_t)TILE * L::kElem;  // splitter mode: bucket of every sorted-tile position
     if constexpr (RANK == kRankAtomicOr) {
@@ -247,6 +310,13 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
         }
         if ((int)lane <= tf.nsplit) wt[lane] = cnt;  // (higher lanes stand for no bucket: with fewer ballot bits they hold aliases)
         if (!FULL && lane == 8) wt[kRadixSize - 1] = cnt;  // padding sorts last within the tile, as in the other modes
+    } else if constexpr (RANK == kRankTwoSweep) {
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            unsigned d = pass_digit<K, IDENT>(key[i], shift, tf);
+            if (!FULL && off0 + i * VWL >= valid) d = kRadixSize - 1;
+            atomicAdd(&wt[d], 1u);  // count only; the position comes from the second sweep
+        }
     } else {
 #pragma unroll
         for (int i = 0; i < ITEMS; i++) {
@@ -298,8 +368,13 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
         if constexpr (IDENT == kDigitSplit) d = (dpk[i / 8] >> (4 * (i % 8))) & 15u;
         else d = pass_digit<K, IDENT>(key[i], shift, tf);
         if (!FULL && off0 + i * VWL >= valid) d = kRadixSize - 1;
-        const unsigned pos = (wt[d] >> CSHIFT) + rank[i];
-        rank[i] = (unsigned short)pos;
+        unsigned pos;
+        if constexpr (RANK == kRankTwoSweep) {
+            pos = atomicAdd(&wt[d], 1u);  // same atomics, same order as the counting sweep: offset + rank
+        } else {
+            pos = (wt[d] >> CSHIFT) + rank[i];
+            rank[i] = (unsigned short)pos;
+        }
         keys_sorted[pos] = key[i];
         if constexpr (IDENT == kDigitSplit) dig_sorted[pos] = (unsigned char)d;
     }
@@ -628,7 +703,17 @@ static int launch_pass(StreamState *st, const void *kin, void *kout, const void 
                  : launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankAtomicOr, kDigitTransform, MINB>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
 }
 
-// tile shapes: (key bytes, value bytes) -> THREADS x ITEMS
+// the speculative two-sweep pass (keys only, 32- and 64-bit keys)
+template <typename K, int THREADS, int ITEMS, int LBATCH, int MINB>
+static int launch_two_sweep(StreamState *st, const void *kin, void *kout, const unsigned *base, unsigned long long *lookback, size_t n,
+                            int shift, const Transform &tf)
+{
+    const bool ident = (tf.nm | tf.xc | tf.fa) == 0;
+    return ident ? launch_pass_impl<K, 0, THREADS, ITEMS, LBATCH, kRankTwoSweep, kDigitIdent, MINB>(st, kin, kout, nullptr, nullptr, base, lookback, n, shift, tf)
+                 : launch_pass_impl<K, 0, THREADS, ITEMS, LBATCH, kRankTwoSweep, kDigitTransform, MINB>(st, kin, kout, nullptr, nullptr, base, lookback, n, shift, tf);
+}
+
+// tile shapes of the deterministic pass: (key bytes, value bytes) -> THREADS x ITEMS
 template <typename K, int VB> struct PassConfig { static constexpr int THREADS = 384, ITEMS = 16; };
 template <> struct PassConfig<unsigned, 0> { static constexpr int THREADS = 384, ITEMS = 20; };
 template <> struct PassConfig<unsigned short, 0> { static constexpr int THREADS = 384, ITEMS = 20; };
@@ -638,7 +723,12 @@ template <typename K> struct PassConfig<K, 8> { static constexpr int THREADS = 3
 template <typename K> struct PassConfig<K, 16> { static constexpr int THREADS = 384, ITEMS = 8; };
 template <> struct PassConfig<unsigned long long, 4> { static constexpr int THREADS = 384, ITEMS = 12; };
 
-static bool sort_variant_is_default() { const char *e = std::getenv("BCB_SORT_VARIANT"); return !e || std::atoi(e) == 0; }
+// tile shapes of the two-sweep pass: without rank registers 32 keys per thread fit 80 registers (2 CTAs of 384 threads
+// per SM); the per-tile costs (digit scan, look-back, barriers) are spread over 12288 keys.  Measured on B200,
+// 2^30 u32 keys, 4 passes: 384x20 14.0 ms, 384x24 12.5 ms, 384x32 11.0 ms, 384x40 11.5 ms, 512x24 11.6 ms.
+template <typename K> struct SpecConfig { static constexpr int THREADS = 384, ITEMS = 32, LB = 4, MINB = 2; };
+// (2^28 u64 keys, 8 passes: 384x12 10.9 ms, 384x16 9.2 ms, 384x20 8.7 ms, 384x24 8.7 ms)
+template <> struct SpecConfig<unsigned long long> { static constexpr int THREADS = 384, ITEMS = 20, LB = 4, MINB = 2; };
 
 // BCB_SORT_KERNEL=ns selects the experimental nibble-split pass kernel (radix_sort_ns.cu) for 32/64-bit keys-only
 // sorts.  It is bit-exact but measured SLOWER on B200 (34 vs 53 Gkeys/s: 147 instructions per key make it ALU bound,
@@ -650,10 +740,10 @@ static bool want_ns_kernel()
         const char *e = std::getenv("BCB_SORT_KERNEL");
         g_sort_kernel = (e && std::strcmp(e, "ns") == 0) ? 1 : 0;
     }
-    return g_sort_kernel == 1 && sort_variant_is_default();
+    return g_sort_kernel == 1;
 }
 
-static int g_sort_variant = -1;  // BCB_SORT_VARIANT: tuning variants of the u32 keys-only pass
+static int g_sort_variant = -1;  // BCB_SORT_VARIANT: tuning variants of the two-sweep pass (experiments)
 static int sort_variant()
 {
     if (g_sort_variant < 0) {
@@ -663,21 +753,24 @@ static int sort_variant()
     return g_sort_variant;
 }
 
-// BCB_SORT_VARIANT selects tuning variants of the u32 keys-only pass: {threads, items, look-back batch}
-#define BCB_U32_VARIANTS(X) X(1, 512, 16, 8, 2) X(2, 384, 16, 8, 3) X(3, 256, 24, 8, 3) X(4, 384, 16, 8, 2) X(5, 256, 16, 8, 4) X(6, 256, 16, 8, 3) X(7, 512, 12, 8, 2) X(8, 256, 20, 8, 3)
+// {id, threads, items, look-back batch, min CTAs per SM}
+#define BCB_SPEC_VARIANTS_32(X) X(1, 384, 24, 4, 2) X(3, 512, 24, 4, 2) X(5, 384, 32, 2, 2)
+#define BCB_SPEC_VARIANTS_64(X) X(1, 384, 16, 4, 2) X(3, 384, 24, 4, 2) X(5, 256, 24, 4, 3)
 
 template <typename K, int VB>
-static int tile_size_for()
+static int tile_size_for(int rank)
 {
     if constexpr (VB == 0 && (sizeof(K) == 4 || sizeof(K) == 8)) {
-        if (want_ns_kernel()) return (int)ns_tile_size();
-    }
-    if constexpr (sizeof(K) == 4 && VB == 0) {
-        switch (sort_variant()) {
+        if (want_ns_kernel() && rank == kRankAtomicOr) return (int)ns_tile_size();
+        if (rank == kRankTwoSweep) {
 #define X(ID, T, I, LBV, MB) case ID: return T * I;
-            BCB_U32_VARIANTS(X)
+            if constexpr (sizeof(K) == 4) {
+                switch (sort_variant()) { BCB_SPEC_VARIANTS_32(X) default: break; }
+            } else {
+                switch (sort_variant()) { BCB_SPEC_VARIANTS_64(X) default: break; }
+            }
 #undef X
-        default: break;
+            return SpecConfig<K>::THREADS * SpecConfig<K>::ITEMS;
         }
     }
     return PassConfig<K, VB>::THREADS * PassConfig<K, VB>::ITEMS;
@@ -692,13 +785,16 @@ static int run_pass(StreamState *st, const void *kin, void *kout, const void *vi
             const bool ident = (tf.nm | tf.xc | tf.fa) == 0;
             return ns_launch_pass(st, (int)sizeof(K), kin, kout, base, lookback, n, shift, tf, ident ? kDigitIdent : kDigitTransform);
         }
-    }
-    if constexpr (sizeof(K) == 4 && VB == 0) {
-        switch (sort_variant()) {
-#define X(ID, T, I, LBV, MB) case ID: return launch_pass<K, VB, T, I, LBV, MB>(st, kin, kout, vin, vout, base, lookback, n, shift, tf, rank);
-            BCB_U32_VARIANTS(X)
+        if (rank == kRankTwoSweep) {
+#define X(ID, T, I, LBV, MB) case ID: return launch_two_sweep<K, T, I, LBV, MB>(st, kin, kout, base, lookback, n, shift, tf);
+            if constexpr (sizeof(K) == 4) {
+                switch (sort_variant()) { BCB_SPEC_VARIANTS_32(X) default: break; }
+            } else {
+                switch (sort_variant()) { BCB_SPEC_VARIANTS_64(X) default: break; }
+            }
 #undef X
-        default: break;
+            return launch_two_sweep<K, SpecConfig<K>::THREADS, SpecConfig<K>::ITEMS, SpecConfig<K>::LB, SpecConfig<K>::MINB>(
+                st, kin, kout, base, lookback, n, shift, tf);
         }
     }
     return launch_pass<K, VB, PassConfig<K, VB>::THREADS, PassConfig<K, VB>::ITEMS>(st, kin, kout, vin, vout, base, lookback, n,
@@ -848,9 +944,10 @@ static int sort_typed(StreamState *st, void *keys, void *values, size_t n, const
     if (rank < 0) {
         rank = kRankAtomicOr;
         if constexpr (VB == 0 && (sizeof(K) == 4 || sizeof(K) == 8)) {
-            if (speculative_enabled() && n >= kSpeculativeMinKeys && !want_ns_kernel() && sort_variant_is_default()) rank = kRankOrderedAtoms;
+            if (speculative_enabled() && n >= kSpeculativeMinKeys && !want_ns_kernel()) rank = kRankTwoSweep;
             const char *e = std::getenv("BCB_SORT_RANK");  // explicit override for experiments
             if (e && std::strcmp(e, "ordered") == 0) rank = kRankOrderedAtoms;
+            if (e && std::strcmp(e, "twosweep") == 0) rank = kRankTwoSweep;
         }
     }
     const size_t kbytes = align_up(n * sizeof(K), 256);
@@ -860,7 +957,7 @@ static int sort_typed(StreamState *st, void *keys, void *values, size_t n, const
     void *tmp_keys = scratch;
     void *tmp_vals = VB ? (void *)((char *)scratch + kbytes) : nullptr;
 
-    const size_t tile = (size_t)tile_size_for<K, VB>();
+    const size_t tile = (size_t)tile_size_for<K, VB>(rank);
     const size_t tiles = (n + tile - 1) / tile;
     void *lb;
     BCB_TRY(lookback_reserve(st, tiles * kRadixSize * sizeof(unsigned long long), &lb));
@@ -873,7 +970,20 @@ static int sort_typed(StreamState *st, void *keys, void *values, size_t n, const
         const size_t cap = (size_t)st->sm_count * (2048 / kHistThreads);
         if (blocks > cap) blocks = cap;
         if (blocks < 1) blocks = 1;
-        {
+        static int hist_variant = -1;  // BCB_HIST_VARIANT=0: plain layout; 1 (default for large inputs): one column per lane
+        if (hist_variant < 0) { const char *e = std::getenv("BCB_HIST_VARIANT"); hist_variant = e ? std::atoi(e) : 1; }
+        if (hist_variant == 1 && n >= ((size_t)1 << 22)) {
+            constexpr int COLS = sizeof(K) == 8 ? 16 : 32;
+            constexpr size_t kSmem = sizeof(K) * kRadixSize * COLS * sizeof(unsigned);
+            auto kernel = radix_histogram_columns<K, COLS>;
+            static bool configured[64] = {};
+            if (st->device >= 64 || !configured[st->device]) {
+                BCB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+                if (st->device < 64) configured[st->device] = true;
+            }
+            LaunchTimer timer(st, BCB_K_RADIX_HISTOGRAM);
+            kernel<<<(unsigned)st->sm_count, 1024, kSmem, st->stream>>>((const K *)src_keys, n, hist, tf);
+        } else {
             LaunchTimer timer(st, BCB_K_RADIX_HISTOGRAM);
             radix_histogram<K><<<(unsigned)blocks, kHistThreads, 0, st->stream>>>((const K *)src_keys, n, hist, tf);
         }
@@ -896,7 +1006,7 @@ static int sort_typed(StreamState *st, void *keys, void *values, size_t n, const
         if (VB) BCB_CUDA_TRY(cudaMemcpyAsync(values, vin, n * (size_t)VB, cudaMemcpyDeviceToDevice, st->stream));
     }
     if constexpr (VB == 0 && (sizeof(K) == 4 || sizeof(K) == 8)) {
-        if (rank == kRankOrderedAtoms) {
+        if (rank_is_speculative(rank)) {
             // verify the speculation (see above); on failure sort again with the deterministic kernel
             int *flag = (int *)st->pinned_slot_dev;
             *(volatile int *)st->pinned_slot = 0;

@@ -185,6 +185,14 @@ static int grid_for(size_t n, int sm_count)
 
 using namespace bcb;
 
+// SM-issued copy: what a kernel's own stores to (peer) memory can sustain, next to the copy engines of bcb_memcpy_d2d
+template <typename V>
+__global__ void __launch_bounds__(256) sm_copy_kernel(V *__restrict__ dst, const V *__restrict__ src, size_t n)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
+}
+
 extern "C" {
 
 const char *bcb_error_string(int status)
@@ -397,6 +405,24 @@ int bcb_memcpy_d2d(bcb_stream stream, void *dst, const void *src, size_t bytes)
     if (bytes == 0) return BCB_SUCCESS;
     if (!dst || !src) return BCB_EINVAL;
     BCB_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return BCB_SUCCESS;
+}
+
+int bcb_copy_kernel(bcb_stream stream, void *dst, const void *src, size_t bytes, int vector_bytes)
+{
+    if (bytes == 0) return BCB_SUCCESS;
+    if (!dst || !src) return BCB_EINVAL;
+    if ((vector_bytes != 4 && vector_bytes != 8 && vector_bytes != 16) || bytes % vector_bytes || ((uintptr_t)dst | (uintptr_t)src) % vector_bytes)
+        return BCB_EINVAL;
+    StreamState *st;
+    BCB_TRY(stream_state((cudaStream_t)stream, &st));
+    const size_t n = bytes / vector_bytes;
+    size_t blocks = (n + 255) / 256;
+    if (blocks > (size_t)st->sm_count * 8) blocks = (size_t)st->sm_count * 8;
+    if (vector_bytes == 4) sm_copy_kernel<unsigned><<<(unsigned)blocks, 256, 0, st->stream>>>((unsigned *)dst, (const unsigned *)src, n);
+    else if (vector_bytes == 8) sm_copy_kernel<uint2><<<(unsigned)blocks, 256, 0, st->stream>>>((uint2 *)dst, (const uint2 *)src, n);
+    else sm_copy_kernel<uint4><<<(unsigned)blocks, 256, 0, st->stream>>>((uint4 *)dst, (const uint4 *)src, n);
+    BCB_CUDA_TRY(cudaGetLastError());
     return BCB_SUCCESS;
 }
 

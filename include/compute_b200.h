@@ -84,6 +84,9 @@ BCB_API int bcb_memcpy_h2d(bcb_stream stream, void *device_dst, const void *host
 BCB_API int bcb_memcpy_d2h(bcb_stream stream, void *host_dst, const void *device_src, size_t bytes);
 BCB_API int bcb_memcpy_d2d(bcb_stream stream, void *device_dst, const void *device_src, size_t bytes);
 /* fill / iota / is_sorted (algorithm/fill.hpp, iota.hpp, is_sorted.hpp:39-68) -- the helpers either side of the path */
+/* copy by a kernel's own loads and stores (vector_bytes 4, 8 or 16 per thread) instead of the copy engines: the
+ * diagnostic for what SM-issued stores into peer memory sustain over NVLink (scripts/peer_bandwidth.py) */
+BCB_API int bcb_copy_kernel(bcb_stream stream, void *dst, const void *src, size_t bytes, int vector_bytes);
 BCB_API int bcb_fill(bcb_stream stream, void *device_ptr, size_t n, const void *value_host, size_t value_bytes);
 BCB_API int bcb_iota(bcb_stream stream, int dtype, void *device_ptr, size_t n, const void *start_host);
 BCB_API int bcb_is_sorted(bcb_stream stream, int dtype, int descending, const void *keys, size_t n, int *result_host);
