@@ -7,12 +7,15 @@
 //   1. radix_histogram: ONE read of the keys builds the 256-bin histogram of every digit position
 //      (128-bit loads, shared-memory atomics, one flush per CTA);
 //   2. digit_scan: exclusive scan of each 256-bin histogram -> global base of every digit value;
-//   3. onesweep_pass, once per digit: each CTA takes a tile id from an atomic ticket, loads its keys
-//      warp-striped, ranks them with warp-level multi-split (__match_any_sync) against per-warp shared-memory
-//      histograms, publishes the tile's 256 digit counts, obtains the counts of all earlier tiles by decoupled
-//      look-back (one thread per digit value), reorders the tile through shared memory and writes each digit's
-//      run to its final position.  The scatter is stable (ranks follow the original order), so the result is
-//      identical to the reference's stable 4-bit LSD sort by the same transformed key.
+//   3. onesweep_pass, once per digit: persistent CTAs take tiles round-robin (the next tile's keys are prefetched
+//      into the dead key registers), rank the keys of each warp's contiguous segment against per-warp
+//      shared-memory digit tables (shared-memory atomics, see "Ranking modes" below -- hardware match.any is far too
+//      slow on this part), publish the tile's 256 digit counts, obtain the counts of all earlier tiles by batched
+//      decoupled look-back (one thread per digit value), reorder the tile through shared memory and write each
+//      digit's run to its final position.  The scatter is stable (ranks follow the original order), so the result
+//      is identical to the reference's stable 4-bit LSD sort by the same transformed key.
+//   4. large keys-only sorts use the faster "two-sweep" ranking speculatively and verify the result
+//      (verify_sorted_kernel, one more read); see "Speculative ranking" below.
 // Keys stay in their original bit pattern in memory; the reference's order-preserving transform
 // (radix_sort.hpp:100-127, asc and desc, incl. its descending quirks) is applied in registers when a digit is
 // extracted, because the descending float transform is not invertible (-0.0 and +denorm_min collide).
@@ -21,6 +24,7 @@
 #include "radix_common.cuh"
 
 #include <cstdlib>
+#include <type_traits>
 #include <cstring>
 
 namespace bcb {
@@ -156,13 +160,14 @@ __global__ void __launch_bounds__(kRadixSize) digit_scan(const unsigned *__restr
 // with ~30 distinct values costs 62, an 8-ballot software match 27, shared-memory atomics / loads about 1.5-1.8.
 // At HBM speed an SM must retire 32 keys every ~11 cycles, so both match flavours are out; ranking is built from
 // shared-memory atomics instead:
-//   kRankAtomicOr     (default): every lane ORs its lane bit into a per-warp {mask, count} entry of its digit;
+//   kRankAtomicOr     (default for pairs and small inputs): every lane ORs its lane bit into a per-warp {mask, count} entry of its digit;
 //                     after a warp barrier the entry holds the full peer mask (order independent), the rank inside
 //                     the round is popc(mask & lanes below), the highest peer clears the mask and bumps the count.
 //                     Deterministic by construction: 3 shared-memory instructions per key.
-//   kRankOrderedAtoms (experimental, BCB_SORT_RANK=ordered): rank = atomicAdd(count, 1).  One instruction per key, but
-//                     stable only if same-address atomics of one warp instruction are applied in lane order, which
-//                     CUDA does not promise; never selected by default.
+//   kRankOrderedAtoms (BCB_SORT_RANK=ordered): rank = atomicAdd(count, 1).  One instruction per key, but stable only
+//                     if same-address atomics of one warp instruction are applied in lane order, which CUDA does
+//                     not promise -- usable only where the result is verified (keys-only sorts, below).
+//                     Superseded by kRankTwoSweep.
 //   kRankBallot       splitter mode only (at most 8 buckets + padding): the peer mask of a key comes from three
 //                     ballots over the bits of its bucket, the running count of bucket b lives in a register of lane
 //                     b.  No shared memory, no atomics (same-address atomics of 2..8 buckets would serialise).
@@ -253,7 +258,10 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
 
     // ---- rank inside the warp (stable: item-major, lane-minor == memory order) ----
     static_assert(VB == 0 || RANK != kRankTwoSweep, "the two-sweep ranking keeps no ranks for a payload");
-    unsigned short rank[RANK == kRankTwoSweep ? 1 : ITEMS];
+    // with a payload, rank[i] later also carries (in its upper half) the digit of the sorted-tile position this thread
+    // writes in round i: one register per item instead of two
+    static_assert(TILE <= 65536, "in-tile positions are 16-bit");
+    typename std::conditional<(VB > 0), unsigned, unsigned short>::type rank[RANK == kRankTwoSweep ? 1 : ITEMS];
     unsigned dpk[IDENT == kDigitSplit ? (ITEMS + 7) / 8 : 1] = {};  // splitter mode: packed buckets of this thread's keys
     unsigned char *dig_sorted = elem_buf + (size_t)TILE * L::kElem;  // splitter mode: bucket of every sorted-tile position
     if constexpr (RANK == kRankAtomicOr) {
@@ -373,7 +381,7 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
             pos = atomicAdd(&wt[d], 1u);  // same atomics, same order as the counting sweep: offset + rank
         } else {
             pos = (wt[d] >> CSHIFT) + rank[i];
-            rank[i] = (unsigned short)pos;
+            rank[i] = (unsigned short)pos;  // (zero-extends when the element type is 32-bit)
         }
         keys_sorted[pos] = key[i];
         if constexpr (IDENT == kDigitSplit) dig_sorted[pos] = (unsigned char)d;
@@ -436,7 +444,6 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
     __syncthreads();
 
     // ---- write keys: consecutive threads -> consecutive addresses inside each digit run ----
-    unsigned char dig[VB > 0 ? ITEMS : 1];
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
         const unsigned p = i * THREADS + tid;
@@ -445,7 +452,7 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
             unsigned d;
             if constexpr (IDENT == kDigitSplit) d = dig_sorted[p];
             else d = pass_digit<K, IDENT>(k, shift, tf);
-            if constexpr (VB > 0) dig[i] = (unsigned char)d;
+            if constexpr (VB > 0) rank[i] |= d << 16;
             if constexpr (IDENT == kDigitSplit) {
                 const unsigned long long *addr = reinterpret_cast<const unsigned long long *>(out_base);
                 *reinterpret_cast<K *>(addr[d] + (unsigned long long)p * sizeof(K)) = k;
@@ -469,7 +476,7 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
 #pragma unroll
         for (int i = 0; i < ITEMS; i++) {
             const unsigned t = off0 + i * VWL;
-            if (FULL || t < valid) vals_sorted[rank[i]] = val[i];
+            if (FULL || t < valid) vals_sorted[rank[i] & 0xffffu] = val[i];
         }
         __syncthreads();
 #pragma unroll
@@ -478,9 +485,9 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
             if (FULL || p < valid) {
                 if constexpr (IDENT == kDigitSplit) {
                     const unsigned long long *addr = reinterpret_cast<const unsigned long long *>(out_base);
-                    *reinterpret_cast<V *>(addr[kMaxSplitters + 1 + dig[i]] + (unsigned long long)p * VB) = vals_sorted[p];
+                    *reinterpret_cast<V *>(addr[kMaxSplitters + 1 + (rank[i] >> 16)] + (unsigned long long)p * VB) = vals_sorted[p];
                 } else {
-                    vals_out[(size_t)(out_base[dig[i]] + p)] = vals_sorted[p];
+                    vals_out[(size_t)(out_base[rank[i] >> 16] + p)] = vals_sorted[p];
                 }
             }
         }
@@ -604,7 +611,10 @@ static int launch_pass_impl(StreamState *st, const void *kin, void *kout, const 
 // took, so the output is the correct result if and only if it is sorted by the transformed key.  sort_typed therefore
 // runs the fast passes, verifies sortedness in one extra read (4 B/key), and in the (never observed) failure case
 // simply sorts the buffer again with the deterministic kernel -- re-sorting a permutation of the input gives the same
-// bytes.  Key-value sorts never speculate (stability of the payload cannot be verified from the keys).
+// bytes.  Key-value sorts never speculate (stability of the payload cannot be verified from the keys), and neither do
+// descending float sorts (their key transform is not injective, see sort_typed).  The shipped speculative kernel is
+// kRankTwoSweep (same assumption, no rank registers, 12288-key tiles): 2^30 u32 keys in 11.0 ms of passes against
+// 14.1 ms (ordered atomics, 7680-key tiles) and 18.6 ms (deterministic atomic-OR).
 //   BCB_SORT_SPECULATIVE=0       always use the deterministic atomic-OR kernel
 //   BCB_SORT_FORCE_FALLBACK=1    test hook: treat every verification as failed
 constexpr size_t kSpeculativeMinKeys = (size_t)1 << 22;  // below this the sort stays fully asynchronous
@@ -944,10 +954,18 @@ static int sort_typed(StreamState *st, void *keys, void *values, size_t n, const
     if (rank < 0) {
         rank = kRankAtomicOr;
         if constexpr (VB == 0 && (sizeof(K) == 4 || sizeof(K) == 8)) {
-            if (speculative_enabled() && n >= kSpeculativeMinKeys && !want_ns_kernel()) rank = kRankTwoSweep;
-            const char *e = std::getenv("BCB_SORT_RANK");  // explicit override for experiments
-            if (e && std::strcmp(e, "ordered") == 0) rank = kRankOrderedAtoms;
-            if (e && std::strcmp(e, "twosweep") == 0) rank = kRankTwoSweep;
+            // The verification argument needs an INJECTIVE key transform (sorted permutation => unique bytes).  The
+            // reference's descending float transform is not (radix_sort.hpp:100-127: -0.0 / +denorm_min and
+            // +0.0 / -denorm_min collide, and their relative order is then decided by stability alone), so
+            // descending float / double sorts always take the deterministic kernel.
+            const bool injective = !(tf.fa != 0 && tf.nm != 0);
+            if (injective) {
+                if (speculative_enabled() && n >= kSpeculativeMinKeys && !want_ns_kernel()) rank = kRankTwoSweep;
+                const char *e = std::getenv("BCB_SORT_RANK");  // explicit override for experiments
+                if (e && std::strcmp(e, "ordered") == 0) rank = kRankOrderedAtoms;
+                if (e && std::strcmp(e, "twosweep") == 0) rank = kRankTwoSweep;
+                if (e && std::strcmp(e, "atomic_or") == 0) rank = kRankAtomicOr;
+            }
         }
     }
     const size_t kbytes = align_up(n * sizeof(K), 256);

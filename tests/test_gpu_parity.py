@@ -420,3 +420,27 @@ def test_partition_counts_and_scatter_to_separate_buffers(dtype, value_bytes, ns
             if v is not None:
                 gv = outs_v[b].cpu().numpy()
                 assert gv[: sel.size * value_bytes].tobytes() == v[sel].tobytes(), (dtype, desc, b)
+
+
+@pytest.mark.parametrize("dtype", ["float", "double"])
+def test_large_descending_float_sort_with_colliding_keys_stays_deterministic(dtype, gpu):
+    """Descending float keys: -0.0 / +denorm_min (and +0.0 / -denorm_min) share a transformed key in the reference
+    (radix_sort.hpp:100-127), so their output order is decided by stability alone and a sortedness check could not
+    see a swap.  Such sorts must not take the speculative path, and must still match the oracle byte for byte."""
+    import ctypes
+    import compute_b200 as cb
+    npdt = np.dtype(NPD[dtype])
+    tiny = np.finfo(npdt).smallest_subnormal
+    pool = np.array([-0.0, tiny, 0.0, -tiny, 1.0, -1.0], dtype=npdt)
+    n = (1 << 22) + 77
+    k = pool[np.random.default_rng(9).integers(0, pool.size, size=n)]
+    runs0, falls = ctypes.c_ulonglong(), ctypes.c_ulonglong()
+    q = cb.command_queue()
+    cb.lib().bcb_sort_speculation_stats(q.handle, ctypes.byref(runs0), ctypes.byref(falls))
+    assert gpu.radix_sort(k, True).tobytes() == oracle.radix_sort(k, True).tobytes()
+    runs1 = ctypes.c_ulonglong()
+    cb.lib().bcb_sort_speculation_stats(q.handle, ctypes.byref(runs1), ctypes.byref(falls))
+    assert runs1.value == runs0.value  # no speculative run for the descending order
+    assert gpu.radix_sort(k, False).tobytes() == oracle.radix_sort(k, False).tobytes()
+    cb.lib().bcb_sort_speculation_stats(q.handle, ctypes.byref(runs1), ctypes.byref(falls))
+    assert runs1.value == runs0.value + 1 and falls.value == 0  # ascending: injective transform, speculative + verified
