@@ -263,7 +263,6 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
     static_assert(TILE <= 65536, "in-tile positions are 16-bit");
     typename std::conditional<(VB > 0), unsigned, unsigned short>::type rank[RANK == kRankTwoSweep ? 1 : ITEMS];
     unsigned dpk[IDENT == kDigitSplit ? (ITEMS + 7) / 8 : 1] = {};  // splitter mode: packed buckets of this thread's keys
-    unsigned char *dig_sorted = elem_buf + (size_t)TILE * L::kElem;  // splitter mode: bucket of every sorted-tile position
     if constexpr (RANK == kRankAtomicOr) {
         const unsigned hbit = 1u << (lane & 15u);
         const unsigned hlt = hbit - 1u;
@@ -384,7 +383,6 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
             rank[i] = (unsigned short)pos;  // (zero-extends when the element type is 32-bit)
         }
         keys_sorted[pos] = key[i];
-        if constexpr (IDENT == kDigitSplit) dig_sorted[pos] = (unsigned char)d;
     }
 
     // ---- prefetch the next tile's keys into the (now dead) key registers: the loads fly during the look-back and
@@ -432,31 +430,47 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
             out_base[tid] = __ldg(digit_base + tid) + excl - my_start;  // global index = out_base[d] + position in the sorted tile
         } else {
             // splitter mode: every bucket has its own destination (possibly another GPU's memory).  out_base is not
-            // needed as an index table, so it holds the byte address of "position 0 of the sorted tile" per bucket.
+            // needed as an index table, so it holds, per bucket: the byte address of the first element of this tile's
+            // run (keys, values), the run's start inside the sorted tile and its length.
             if (tid <= kMaxSplitters) {
-                const long long rel = (long long)((unsigned long long)__ldg(digit_base + tid) + excl) - (long long)my_start;
+                const unsigned long long first = (unsigned long long)__ldg(digit_base + tid) + excl;  // elements before the run
                 unsigned long long *addr = reinterpret_cast<unsigned long long *>(out_base);
-                addr[tid] = tf.dst_keys[tid] + (unsigned long long)(rel * (long long)sizeof(K));
-                if constexpr (VB > 0) addr[kMaxSplitters + 1 + tid] = tf.dst_vals[tid] + (unsigned long long)(rel * (long long)VB);
+                addr[tid] = tf.dst_keys[tid] + first * sizeof(K);
+                if constexpr (VB > 0) addr[kMaxSplitters + 1 + tid] = tf.dst_vals[tid] + first * (unsigned long long)VB;
+                out_base[32 + tid] = my_start;
+                out_base[40 + tid] = count;
             }
         }
     }
     __syncthreads();
 
     // ---- write keys: consecutive threads -> consecutive addresses inside each digit run ----
+    if constexpr (IDENT == kDigitSplit) {
+        // Few, long runs (<= 8 buckets).  Walk them one by one with the lanes aligned to the DESTINATION: lane l of a
+        // warp always writes an address whose element index is l mod 32, so every warp store is one aligned line
+        // instead of straddling two -- over NVLink a straddling store is two packets (measured: 7.2-8.0 ms -> see
+        // DESIGN.md for the 8-rank exchange pass).
+        const unsigned long long *addr = reinterpret_cast<const unsigned long long *>(out_base);
+        for (int b = 0; b <= tf.nsplit; b++) {
+            const unsigned s = out_base[32 + b], c = out_base[40 + b];
+            if (c == 0) continue;
+            const unsigned long long a0 = addr[b];
+            const unsigned mis = (unsigned)(a0 / sizeof(K)) & 31u;  // element index of the run start inside its line
+            for (unsigned v = tid; v < c + mis; v += THREADS) {
+                if (v >= mis) {
+                    const unsigned j = v - mis;
+                    *reinterpret_cast<K *>(a0 + (unsigned long long)j * sizeof(K)) = keys_sorted[s + j];
+                }
+            }
+        }
+    } else {
 #pragma unroll
-    for (int i = 0; i < ITEMS; i++) {
-        const unsigned p = i * THREADS + tid;
-        if (FULL || p < valid) {
-            const K k = keys_sorted[p];
-            unsigned d;
-            if constexpr (IDENT == kDigitSplit) d = dig_sorted[p];
-            else d = pass_digit<K, IDENT>(k, shift, tf);
-            if constexpr (VB > 0) rank[i] |= d << 16;
-            if constexpr (IDENT == kDigitSplit) {
-                const unsigned long long *addr = reinterpret_cast<const unsigned long long *>(out_base);
-                *reinterpret_cast<K *>(addr[d] + (unsigned long long)p * sizeof(K)) = k;
-            } else {
+        for (int i = 0; i < ITEMS; i++) {
+            const unsigned p = i * THREADS + tid;
+            if (FULL || p < valid) {
+                const K k = keys_sorted[p];
+                const unsigned d = pass_digit<K, IDENT>(k, shift, tf);
+                if constexpr (VB > 0) rank[i] |= d << 16;
                 keys_out[(size_t)(out_base[d] + p)] = k;
             }
         }
@@ -479,16 +493,25 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
             if (FULL || t < valid) vals_sorted[rank[i] & 0xffffu] = val[i];
         }
         __syncthreads();
-#pragma unroll
-        for (int i = 0; i < ITEMS; i++) {
-            const unsigned p = i * THREADS + tid;
-            if (FULL || p < valid) {
-                if constexpr (IDENT == kDigitSplit) {
-                    const unsigned long long *addr = reinterpret_cast<const unsigned long long *>(out_base);
-                    *reinterpret_cast<V *>(addr[kMaxSplitters + 1 + (rank[i] >> 16)] + (unsigned long long)p * VB) = vals_sorted[p];
-                } else {
-                    vals_out[(size_t)(out_base[rank[i] >> 16] + p)] = vals_sorted[p];
+        if constexpr (IDENT == kDigitSplit) {
+            const unsigned long long *addr = reinterpret_cast<const unsigned long long *>(out_base);
+            for (int b = 0; b <= tf.nsplit; b++) {
+                const unsigned s = out_base[32 + b], c = out_base[40 + b];
+                if (c == 0) continue;
+                const unsigned long long a0 = addr[kMaxSplitters + 1 + b];
+                const unsigned mis = (unsigned)(a0 / VB) & 31u;
+                for (unsigned v = tid; v < c + mis; v += THREADS) {
+                    if (v >= mis) {
+                        const unsigned j = v - mis;
+                        *reinterpret_cast<V *>(a0 + (unsigned long long)j * VB) = vals_sorted[s + j];
+                    }
                 }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < ITEMS; i++) {
+                const unsigned p = i * THREADS + tid;
+                if (FULL || p < valid) vals_out[(size_t)(out_base[rank[i] >> 16] + p)] = vals_sorted[p];
             }
         }
     }
@@ -577,7 +600,7 @@ static int launch_pass_impl(StreamState *st, const void *kin, void *kout, const 
 {
     typedef PassSmem<K, VB, THREADS, ITEMS, RANK> L;
     static_assert((IDENT == kDigitSplit) == (RANK == kRankBallot), "the splitter pass and the ballot ranking go together");
-    constexpr size_t kSmemBytes = L::kBytes + (IDENT == kDigitSplit ? (size_t)L::TILE : 0);  // + bucket byte per position
+    constexpr size_t kSmemBytes = L::kBytes;
     static bool configured[64] = {};  // per instantiation and device: opt in to > 48 KB dynamic shared memory once
     auto kernel = onesweep_pass<K, VB, THREADS, ITEMS, LBATCH, RANK, IDENT, MINB>;
     if (st->device >= 64 || !configured[st->device]) {
@@ -903,16 +926,33 @@ static int partition_counts_typed(StreamState *st, const void *kin, size_t n, co
 
 // one stable onesweep pass whose "digit" is the splitter bucket; bucket b is written contiguously from tf.dst_keys[b]
 // (+ base[b] elements).  Asynchronous.
-template <typename K, int VB>
-static int partition_scatter_typed(StreamState *st, const void *kin, const void *vin, size_t n, const Transform &tf, const unsigned *base)
+template <typename K, int VB, int THREADS, int ITEMS, int MINB>
+static int partition_scatter_shape(StreamState *st, const void *kin, const void *vin, size_t n, const Transform &tf, const unsigned *base)
 {
-    constexpr int THREADS = PassConfig<K, VB>::THREADS, ITEMS = PassConfig<K, VB>::ITEMS;
     const size_t tile = (size_t)THREADS * ITEMS;
     const size_t tiles = (n + tile - 1) / tile;
     void *lb;
     BCB_TRY(lookback_reserve(st, tiles * kRadixSize * sizeof(unsigned long long), &lb));
-    return launch_pass_impl<K, VB, THREADS, ITEMS, kLookbackBatch, kRankBallot, kDigitSplit>(st, kin, nullptr, vin, nullptr, base,
-                                                                                              (unsigned long long *)lb, n, 0, tf);
+    return launch_pass_impl<K, VB, THREADS, ITEMS, kLookbackBatch, kRankBallot, kDigitSplit, MINB>(st, kin, nullptr, vin, nullptr, base,
+                                                                                                  (unsigned long long *)lb, n, 0, tf);
+}
+
+template <typename K, int VB>
+static int partition_scatter_typed(StreamState *st, const void *kin, const void *vin, size_t n, const Transform &tf, const unsigned *base)
+{
+    if constexpr (sizeof(K) == 4 && VB == 0) {  // BCB_SPLIT_VARIANT: tile shapes of the exchange pass (experiments)
+        static int variant = -1;
+        if (variant < 0) { const char *e = std::getenv("BCB_SPLIT_VARIANT"); variant = e ? std::atoi(e) : 0; }
+        switch (variant) {
+        case 1: return partition_scatter_shape<K, VB, 256, 20, 3>(st, kin, vin, n, tf, base);
+        case 2: return partition_scatter_shape<K, VB, 256, 16, 4>(st, kin, vin, n, tf, base);
+        case 3: return partition_scatter_shape<K, VB, 384, 28, 2>(st, kin, vin, n, tf, base);
+        case 4: return partition_scatter_shape<K, VB, 512, 16, 2>(st, kin, vin, n, tf, base);
+        default: break;
+        }
+    }
+    return partition_scatter_shape<K, VB, PassConfig<K, VB>::THREADS, PassConfig<K, VB>::ITEMS, default_min_blocks(PassConfig<K, VB>::THREADS)>(
+        st, kin, vin, n, tf, base);
 }
 
 template <typename K>
