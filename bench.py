@@ -155,9 +155,13 @@ def reference_arm(args):
     value = (n / 1e9) / (ms / 1e3) if unit == "Gkeys/s" else (n * bpe / 1e9) / (ms / 1e3)
     line = {
         "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if kind == "sort" else "weak",
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32" if kind == "sort" else "i32", "data": "synthetic",
-        "config": {"workload": args.workload, "note": "reference CPU-device algorithm on host cores, bounded sample"},
+        "config": {"workload": args.workload, "n": (1 << (args.log2n if args.log2n else log2n)) * max(1, args.gpus),
+                   "n_per_gpu": 1 << (args.log2n if args.log2n else log2n), "value_bytes": vb,
+                   "distribution": "uniform random, seed 12345", "sample_n": n,
+                   "note": "reference CPU-device algorithm (oracle port) on the host cores of rank 0, bounded sample per step",
+                   "parallelism": f"{cores} host threads"},
         "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

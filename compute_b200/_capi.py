@@ -25,6 +25,8 @@ SIGNATURES = {
     "bcb_free": ([_vp], _i),
     "bcb_host_alloc": ([ctypes.POINTER(_vp), _sz], _i),
     "bcb_host_free": ([_vp], _i),
+    "bcb_host_register": ([_vp, _sz, ctypes.POINTER(_vp)], _i),
+    "bcb_host_unregister": ([_vp], _i),
     "bcb_memcpy_h2d": ([_vp, _vp, _vp, _sz], _i),
     "bcb_memcpy_d2h": ([_vp, _vp, _vp, _sz], _i),
     "bcb_memcpy_d2d": ([_vp, _vp, _vp, _sz], _i),

@@ -384,6 +384,31 @@ int bcb_host_free(void *host_ptr)
     return BCB_SUCCESS;
 }
 
+// mapped_view (container/mapped_view.hpp:217-240, CL_MEM_USE_HOST_PTR): make an existing host range addressable by the
+// device (zero copy over PCIe).  Returns the device alias of host_ptr.
+int bcb_host_register(void *host_ptr, size_t bytes, void **device_ptr)
+{
+    if (!host_ptr || !device_ptr || bytes == 0) return BCB_EINVAL;
+    *device_ptr = nullptr;
+    BCB_CUDA_TRY(cudaHostRegister(host_ptr, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
+    cudaError_t e = cudaHostGetDevicePointer(device_ptr, host_ptr, 0);
+    if (e != cudaSuccess) {
+        (void)cudaHostUnregister(host_ptr);
+        (void)cudaGetLastError();
+        return (int)e;
+    }
+    return BCB_SUCCESS;
+}
+
+int bcb_host_unregister(void *host_ptr)
+{
+    if (!host_ptr) return BCB_SUCCESS;
+    // like cudaFree for device buffers: work that still addresses the range finishes first
+    BCB_CUDA_TRY(cudaDeviceSynchronize());
+    BCB_CUDA_TRY(cudaHostUnregister(host_ptr));
+    return BCB_SUCCESS;
+}
+
 int bcb_memcpy_h2d(bcb_stream stream, void *dst, const void *src, size_t bytes)
 {
     if (bytes == 0) return BCB_SUCCESS;

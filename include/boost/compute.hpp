@@ -2,7 +2,7 @@
 #ifndef BOOST_COMPUTE_HPP
 #define BOOST_COMPUTE_HPP
 #include <boost/compute/algorithm.hpp>
-#include <boost/compute/container/vector.hpp>
+#include <boost/compute/container.hpp>
 #include <boost/compute/core.hpp>
 #include <boost/compute/functional.hpp>
 #include <boost/compute/iterator/buffer_iterator.hpp>

@@ -79,6 +79,12 @@ BCB_API int bcb_malloc(void **device_ptr, size_t bytes);
 BCB_API int bcb_free(void *device_ptr);
 BCB_API int bcb_host_alloc(void **host_ptr, size_t bytes);
 BCB_API int bcb_host_free(void *host_ptr);
+/* mapped_view (container/mapped_view.hpp:217-240, CL_MEM_USE_HOST_PTR): register an existing host range so kernels
+ * can address it in place (zero copy over PCIe); *device_ptr receives the device alias.  Unregister (which first waits
+ * for the device, like bcb_free) before freeing the host memory. */
+BCB_API int bcb_host_register(void *host_ptr, size_t bytes, void **device_ptr);
+BCB_API int bcb_host_unregister(void *host_ptr);
+
 /* enqueue_write_buffer / enqueue_read_buffer / enqueue_copy_buffer (command_queue.hpp:297-675); async on stream */
 BCB_API int bcb_memcpy_h2d(bcb_stream stream, void *device_dst, const void *host_src, size_t bytes);
 BCB_API int bcb_memcpy_d2h(bcb_stream stream, void *host_dst, const void *device_src, size_t bytes);

@@ -2,6 +2,8 @@
 // reference's Boost.Test files use it: vectors from host ranges, algorithms on begin()/end() with a queue, results
 // checked against the reference's golden vectors (file:line cited per case) and against std:: algorithms.
 #include <algorithm>
+#include <array>
+#include <stdexcept>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -359,6 +361,56 @@ static void test_reduce_accumulate(compute::command_queue &queue)
     }
 }
 
+// container/array.hpp and container/mapped_view.hpp (the containers either side of the path)
+static void test_array_and_mapped_view(compute::command_queue &queue)
+{
+    // test_array.cpp:33-52 -- construct from a host array, read back, fill, element access
+    std::array<int, 6> host = {{5, -1, 9, 0, 7, 2}};
+    compute::array<int, 6> a(host, queue);
+    CHECK(a.size() == 6 && !a.empty());
+    CHECK(int(a[2]) == 9 && int(a.front()) == 5 && int(a.back()) == 2);
+    compute::sort(a.begin(), a.end(), queue);
+    std::vector<int> got(6);
+    compute::copy(a.begin(), a.end(), got.begin(), queue);
+    const int sorted[] = {-1, 0, 2, 5, 7, 9};
+    CHECK(equals(got, sorted));
+    CHECK(compute::accumulate(a.begin(), a.end(), 0, queue) == 22);
+    compute::array<int, 6> b(a);
+    CHECK(int(b[5]) == 9);
+    a.fill(3, queue);
+    CHECK(compute::accumulate(a.begin(), a.end(), 0, queue) == 18);
+    bool threw = false;
+    try { a.at(6); } catch(std::out_of_range &) { threw = true; }
+    CHECK(threw);
+
+    // test_mapped_view.cpp:29-75 -- algorithms run on host memory in place
+    std::vector<unsigned> keys(100000);
+    std::mt19937 rng(7);
+    for(size_t i = 0; i < keys.size(); i++) keys[i] = rng();
+    std::vector<unsigned> expected(keys);
+    std::sort(expected.begin(), expected.end());
+    {
+        compute::mapped_view<unsigned> view(&keys[0], keys.size(), queue.get_context());
+        CHECK(view.size() == keys.size());
+        compute::sort(view.begin(), view.end(), queue);
+        view.map(queue);
+        CHECK(keys == expected);
+        unsigned long long total = 0;
+        for(size_t i = 0; i < keys.size(); i++) total += keys[i];
+        unsigned device_total = 0;
+        compute::reduce(view.begin(), view.end(), &device_total, queue);
+        CHECK(device_total == static_cast<unsigned>(total));
+        view.unmap(queue);
+    }
+    std::vector<int> ones(1000, 1), sums(1000);
+    {
+        compute::mapped_view<int> in(&ones[0], ones.size()), out(&sums[0], sums.size());
+        compute::inclusive_scan(in.begin(), in.end(), out.begin(), queue);
+        out.map(queue);
+    }
+    CHECK(sums[0] == 1 && sums[999] == 1000);
+}
+
 int main()
 {
     try {
@@ -370,6 +422,7 @@ int main()
         test_sort_by_key(queue);
         test_scan(queue);
         test_reduce_accumulate(queue);
+        test_array_and_mapped_view(queue);
         queue.finish();
     } catch(std::exception &e) {
         std::printf("EXCEPTION: %s\n", e.what());
