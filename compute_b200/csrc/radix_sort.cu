@@ -232,7 +232,7 @@ __device__ __forceinline__ void
 pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *__restrict__ vals_in_v,
           void *__restrict__ vals_out_v, const unsigned *__restrict__ digit_base, unsigned long long *lookback,
           unsigned epoch, size_t n, int shift, const Transform &tf, size_t tile, unsigned char *smem_raw,
-          K (&key)[ITEMS], unsigned long long *ticket, unsigned long long ticket_base, size_t num_tiles)
+          K (&key)[ITEMS], size_t num_tiles)
 {
     typedef PassSmem<K, VB, THREADS, ITEMS, RANK> L;
     typedef typename value_type<VB>::type V;
@@ -254,7 +254,6 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
     unsigned *wt = tab + vwarp * kRadixSize;
 
     // key[] already holds this tile's keys (loaded by the caller / prefetched during the previous tile).
-    (void)ticket; (void)ticket_base;
 
     // ---- rank inside the warp (stable: item-major, lane-minor == memory order) ----
     static_assert(VB == 0 || RANK != kRankTwoSweep, "the two-sweep ranking keeps no ranks for a payload");
@@ -521,7 +520,7 @@ template <typename K, int VB, int THREADS, int ITEMS, int LBATCH, int RANK, int 
 __global__ void __launch_bounds__(THREADS, MINB)
 onesweep_pass(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *__restrict__ vals_in_v,
               void *__restrict__ vals_out_v, const unsigned *__restrict__ digit_base, unsigned long long *lookback,
-              unsigned epoch, unsigned long long *ticket, unsigned long long ticket_base, size_t n, size_t num_tiles, int shift,
+              unsigned epoch, size_t n, size_t num_tiles, int shift,
               const __grid_constant__ Transform tf)
 {
     // Persistent CTAs: the grid is sized to the number of resident CTAs and tiles are dealt round-robin (CTA b takes
@@ -544,11 +543,11 @@ onesweep_pass(const K *__restrict__ keys_in, K *__restrict__ keys_out, const voi
         __syncthreads();
         if ((tile + 1) * (size_t)L::TILE <= n)
             pass_tile<K, VB, THREADS, ITEMS, LBATCH, RANK, IDENT, true>(keys_in, keys_out, vals_in_v, vals_out_v, digit_base, lookback,
-                                                                         epoch, n, shift, tf, tile, smem_raw, key, ticket, ticket_base,
+                                                                         epoch, n, shift, tf, tile, smem_raw, key,
                                                                          num_tiles);
         else
             pass_tile<K, VB, THREADS, ITEMS, LBATCH, RANK, IDENT, false>(keys_in, keys_out, vals_in_v, vals_out_v, digit_base, lookback,
-                                                                          epoch, n, shift, tf, tile, smem_raw, key, ticket, ticket_base,
+                                                                          epoch, n, shift, tf, tile, smem_raw, key,
                                                                           num_tiles);
         __syncthreads();  // all stores of this tile issued, shared memory free for the next one
     }
@@ -619,10 +618,9 @@ static int launch_pass_impl(StreamState *st, const void *kin, void *kout, const 
     if (grid > tiles) grid = tiles;
     unsigned epoch;
     BCB_TRY(next_epoch(st, &epoch));
-    const unsigned long long tbase = st->ticket_base;  // (tickets are no longer drawn by this kernel)
     LaunchTimer timer(st, BCB_K_ONESWEEP_PASS);
     kernel<<<(unsigned)grid, THREADS, kSmemBytes, st->stream>>>((const K *)kin, (K *)kout, vin, vout, base, lookback, epoch,
-                                                               st->control + kControlTicket, tbase, n, tiles, shift, tf);
+                                                               n, tiles, shift, tf);
     BCB_CUDA_TRY(cudaGetLastError());
     return BCB_SUCCESS;
 }
