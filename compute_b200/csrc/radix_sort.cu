@@ -931,7 +931,7 @@ static int partition_scatter_shape(StreamState *st, const void *kin, const void 
     const size_t tiles = (n + tile - 1) / tile;
     void *lb;
     BCB_TRY(lookback_reserve(st, tiles * kRadixSize * sizeof(unsigned long long), &lb));
-    return launch_pass_impl<K, VB, THREADS, ITEMS, kLookbackBatch, kRankBallot, kDigitSplit, MINB>(st, kin, nullptr, vin, nullptr, base,
+    return launch_pass_impl<K, VB, THREADS, ITEMS, 4, kRankBallot, kDigitSplit, MINB>(st, kin, nullptr, vin, nullptr, base,
                                                                                                   (unsigned long long *)lb, n, 0, tf);
 }
 
