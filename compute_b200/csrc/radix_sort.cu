@@ -1319,9 +1319,12 @@ int bcb_partition_scatter(bcb_stream stream, int key_dtype, int ascending, const
     if (n >= 0xffff0000ull) return BCB_ETOOLARGE;
     const size_t vb = values_in ? value_bytes : 0;
     if (vb && !dst_values) return BCB_EINVAL;
+    if (vb != 0 && vb != 4 && vb != 8) return BCB_EUNSUPPORTED;
     for (size_t j = 0; j <= num_splitters; j++) {
         tf.dst_keys[j] = (unsigned long long)(uintptr_t)dst_keys[j];
         tf.dst_vals[j] = vb ? (unsigned long long)(uintptr_t)dst_values[j] : 0ull;
+        // destinations must be element aligned (the kernel derives the lane alignment of a run from its address)
+        if (!dst_keys[j] || tf.dst_keys[j] % dtype_size(key_dtype) || (vb && (!dst_values[j] || tf.dst_vals[j] % vb))) return BCB_EINVAL;
     }
     StreamState *st;
     BCB_TRY(stream_state((cudaStream_t)stream, &st));

@@ -4,11 +4,15 @@ no multi-device path, so this is new functionality with the single-GPU results a
 
 Data model: a range is block-distributed -- rank r holds the r-th contiguous block of the global range.
 
-* ``sort`` / ``sort_by_key`` (sample sort): local stable radix sort -> regular samples of the transformed keys ->
-  all-gather, common splitters -> partition points by binary search on the sorted shard -> all-to-all of contiguous
-  slices (keys, then values) -> local stable radix sort of the received runs (they arrive in source-rank order, so
-  equal keys keep their global input order).  The concatenation of the per-rank outputs in rank order is
-  bit-identical to the single-GPU sort.
+* ``sort`` / ``sort_by_key`` (sample sort, one exchange step): regular samples of the UNSORTED shard's transformed
+  keys -> all-gather, common splitters -> bucket sizes of the shard (``bcb_partition_counts``) -> all-gather of the
+  P x P count matrix -> ONE stable partition pass (``bcb_partition_scatter``) whose stores go straight into the
+  destination ranks' receive buffers, which every rank has mapped through CUDA IPC (NVLink / NVSwitch peer stores, no
+  all-to-all) -> stream-ordered barrier -> local stable radix sort out of the receive buffer.  The runs lie in
+  source-rank order there, so equal keys keep their global input order and the concatenation of the per-rank outputs
+  in rank order is bit-identical to the single-GPU sort.  Fallback plans (chosen collectively): the same partition
+  into a local buffer + ``all_to_all_single`` when peer mapping is unavailable; local sort + binary-search cuts +
+  all-to-all for payload sizes / rank counts the partition kernel does not cover.
 * scans: local reduce -> all-gather of P partials -> carry = init op partial_0 op ... op partial_(r-1), folded in
   rank order -> local single-pass scan seeded with the carry.  Integer results are bit-exact; float results are
   deterministic (fixed fold order).
@@ -501,5 +505,3 @@ class Context:
         with np.errstate(over="ignore"):
             return np_dt(_NP_OPS[op](np_dt(init), r))
 
-
-_ = ctypes
