@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Builds profiles/traffic.json (DRAM bytes per launch of the dominant kernel, from the ncu CSVs that
-scripts/gpu_profiles.sh writes into gpurun_out/traffic_<workload>.csv)."""
+scripts/gpu_final.sh writes into gpurun_out/traffic_<workload>.csv)."""
 import csv, json, os, sys
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sizes = {"sort_u32": 1 << 30, "scan_i32": 1 << 28, "reduce_i32": 1 << 28}
