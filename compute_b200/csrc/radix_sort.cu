@@ -83,7 +83,7 @@ radix_histogram(const K *__restrict__ keys, size_t n, unsigned *__restrict__ his
 // bank l -- the 32 atomics of a warp instruction never share a bank, whatever the digits are (the plain layout above
 // pays ~3 wavefronts per instruction for random digits).  One 1024-thread CTA per SM owns NPASS x 256 x COLS counters
 // (128 KB for 32- and 64-bit keys); the columns are summed when the CTA flushes.
-template <typename K, int COLS>
+template <typename K, int COLS, bool IDENT>
 __global__ void __launch_bounds__(1024, 1)
 radix_histogram_columns(const K *__restrict__ keys, size_t n, unsigned *__restrict__ hist, Transform tf)
 {
@@ -105,7 +105,10 @@ radix_histogram_columns(const K *__restrict__ keys, size_t n, unsigned *__restri
 
     auto count_key = [&](K k) {
 #pragma unroll
-        for (int p = 0; p < NPASS; p++) atomicAdd(mine + (p * kRadixSize + digit_of<K>(k, p * kRadixBits, tf)) * COLS, 1u);
+        for (int p = 0; p < NPASS; p++) {
+            const unsigned d = IDENT ? ((unsigned)(k >> (p * kRadixBits)) & (kRadixSize - 1)) : digit_of<K>(k, p * kRadixBits, tf);
+            atomicAdd(mine + (p * kRadixSize + d) * COLS, 1u);
+        }
     };
     size_t v = gid;
     for (; v + gthreads < nvec; v += 2 * gthreads) {  // two independent 128-bit loads in flight
@@ -443,6 +446,13 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
     }
     __syncthreads();
 
+    // the digit tables are dead from here on (ranking and reorder are complete in every warp): zero them for the next
+    // tile now, overlapped with the memory-bound write phase, instead of behind an extra barrier at the top of the loop
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(smem_raw);
+        for (unsigned i = tid; i < L::kWarpTab / 16; i += THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    }
+
     // ---- write keys: consecutive threads -> consecutive addresses inside each digit run ----
     if constexpr (IDENT == kDigitSplit) {
         // Few, long runs (<= 8 buckets).  Walk them one by one with the lanes aligned to the DESTINATION: lane l of a
@@ -534,13 +544,13 @@ onesweep_pass(const K *__restrict__ keys_in, K *__restrict__ keys_out, const voi
     size_t tile = blockIdx.x;
     K key[ITEMS];
     if (tile < num_tiles) load_tile_keys<K, THREADS, ITEMS, L::VWL>(keys_in, n, tile, key);
+    // the digit tables start out zero; every tile zeroes them again once it is done with them (during its write phase)
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(smem_raw);
+        for (unsigned i = threadIdx.x; i < L::kWarpTab / 16; i += THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
     for (; tile < num_tiles; tile += gridDim.x) {
-        // zero the digit tables (the previous tile left offsets in them)
-        {
-            uint4 *z = reinterpret_cast<uint4 *>(smem_raw);
-            for (unsigned i = threadIdx.x; i < L::kWarpTab / 16; i += THREADS) z[i] = make_uint4(0, 0, 0, 0);
-        }
-        __syncthreads();
         if ((tile + 1) * (size_t)L::TILE <= n)
             pass_tile<K, VB, THREADS, ITEMS, LBATCH, RANK, IDENT, true>(keys_in, keys_out, vals_in_v, vals_out_v, digit_base, lookback,
                                                                          epoch, n, shift, tf, tile, smem_raw, key,
@@ -1031,11 +1041,12 @@ static int sort_typed(StreamState *st, void *keys, void *values, size_t n, const
         if (hist_variant == 1 && n >= ((size_t)1 << 22)) {
             constexpr int COLS = sizeof(K) == 8 ? 16 : 32;
             constexpr size_t kSmem = sizeof(K) * kRadixSize * COLS * sizeof(unsigned);
-            auto kernel = radix_histogram_columns<K, COLS>;
-            static bool configured[64] = {};
-            if (st->device >= 64 || !configured[st->device]) {
+            const bool ident = (tf.nm | tf.xc | tf.fa) == 0;
+            auto kernel = ident ? radix_histogram_columns<K, COLS, true> : radix_histogram_columns<K, COLS, false>;
+            static bool configured[2][64] = {};
+            if (st->device >= 64 || !configured[ident][st->device]) {
                 BCB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
-                if (st->device < 64) configured[st->device] = true;
+                if (st->device < 64) configured[ident][st->device] = true;
             }
             LaunchTimer timer(st, BCB_K_RADIX_HISTOGRAM);
             kernel<<<(unsigned)st->sm_count, 1024, kSmem, st->stream>>>((const K *)src_keys, n, hist, tf);
