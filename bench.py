@@ -47,6 +47,8 @@ WORKLOADS = {
     "sort_f32": ("sort", "float", 0, 29, 36, "radix sort throughput, float32 keys", "Gkeys/s"),
     "sort_u64": ("sort", "ulong", 0, 28, 136, "radix sort throughput, uint64 keys", "Gkeys/s"),
     "sort_pairs_u32": ("sort", "uint", 4, 28, 68, "sort_by_key throughput, uint32 keys + uint32 values", "Gkeys/s"),
+    # the reference's own perf_sort_by_key types (perf/perf_sort_by_key.cpp:39-42): 32-bit keys, 64-bit values
+    "sort_pairs_u32_u64": ("sort", "uint", 8, 28, 100, "sort_by_key throughput, uint32 keys + uint64 values", "Gkeys/s"),
     "scan_i32": ("scan", "int", 0, 28, 8, "exclusive_scan bandwidth, int32", "GB/s"),
     "scan_f32": ("scan", "float", 0, 28, 8, "exclusive_scan bandwidth, float32", "GB/s"),
     "reduce_i32": ("reduce", "int", 0, 28, 4, "reduce bandwidth, int32", "GB/s"),
@@ -242,7 +244,11 @@ def ours(args):
         else:
             pristine = torch.randint(-2**31, 2**31 - 1, (n_local,), dtype=torch.int32, device="cuda", generator=gen).view(tdt)
         work = torch.empty_like(pristine)
-        vals_pristine = torch.arange(n_local, dtype=torch.int32, device="cuda").view(torch.uint32) if vb else None
+        vals_pristine = None
+        if vb == 4:
+            vals_pristine = torch.arange(n_local, dtype=torch.int32, device="cuda").view(torch.uint32)
+        elif vb == 8:
+            vals_pristine = torch.arange(n_local, dtype=torch.int64, device="cuda")
         vals = torch.empty_like(vals_pristine) if vb else None
     else:
         scaling = "weak"  # every rank scans / reduces its own 2^28 block; carries are P scalars
