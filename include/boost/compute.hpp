@@ -1,6 +1,6 @@
 // boost/compute.hpp -- umbrella header of the B200-native subset: core + vector + the sort / scan / reduce path.
-#ifndef BOOST_COMPUTE_HPP
-#define BOOST_COMPUTE_HPP
+#ifndef B200_BOOST_COMPUTE_HPP
+#define B200_BOOST_COMPUTE_HPP
 #include <boost/compute/algorithm.hpp>
 #include <boost/compute/container.hpp>
 #include <boost/compute/core.hpp>

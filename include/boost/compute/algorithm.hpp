@@ -1,5 +1,5 @@
-#ifndef BOOST_COMPUTE_ALGORITHM_HPP
-#define BOOST_COMPUTE_ALGORITHM_HPP
+#ifndef B200_BOOST_COMPUTE_ALGORITHM_HPP
+#define B200_BOOST_COMPUTE_ALGORITHM_HPP
 #include <boost/compute/algorithm/accumulate.hpp>
 #include <boost/compute/algorithm/copy.hpp>
 #include <boost/compute/algorithm/copy_n.hpp>

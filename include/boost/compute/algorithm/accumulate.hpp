@@ -4,8 +4,8 @@
 // a single-work-item left fold.  Here every associative functor whose type equals T runs the parallel kernel
 // with init folded in afterwards (exact for integers; float sums differ from the serial fold by summation
 // order only); minus / divides and mixed T keep the strict serial left fold (serial_accumulate.hpp:22-50).
-#ifndef BOOST_COMPUTE_ALGORITHM_ACCUMULATE_HPP
-#define BOOST_COMPUTE_ALGORITHM_ACCUMULATE_HPP
+#ifndef B200_BOOST_COMPUTE_ALGORITHM_ACCUMULATE_HPP
+#define B200_BOOST_COMPUTE_ALGORITHM_ACCUMULATE_HPP
 
 #include <iterator>
 #include <type_traits>

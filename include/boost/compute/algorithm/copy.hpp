@@ -1,8 +1,8 @@
 // copy / copy_n (algorithm/copy.hpp:178-735, copy_n.hpp of the reference) for the three directions the path
 // needs: host -> device, device -> host (both blocking, like enqueue_*_buffer in the reference) and
 // device -> device (enqueued).  Host ranges that are not plain pointers are staged through a std::vector.
-#ifndef BOOST_COMPUTE_ALGORITHM_COPY_HPP
-#define BOOST_COMPUTE_ALGORITHM_COPY_HPP
+#ifndef B200_BOOST_COMPUTE_ALGORITHM_COPY_HPP
+#define B200_BOOST_COMPUTE_ALGORITHM_COPY_HPP
 
 #include <iterator>
 #include <type_traits>

@@ -1,7 +1,7 @@
 // detail::serial_insertion_sort(_by_key) (algorithm/detail/insertion_sort.hpp:25-159 of the reference):
 // single-thread stable insertion sort with the native compare, used below the radix-sort size thresholds.
-#ifndef BOOST_COMPUTE_ALGORITHM_DETAIL_INSERTION_SORT_HPP
-#define BOOST_COMPUTE_ALGORITHM_DETAIL_INSERTION_SORT_HPP
+#ifndef B200_BOOST_COMPUTE_ALGORITHM_DETAIL_INSERTION_SORT_HPP
+#define B200_BOOST_COMPUTE_ALGORITHM_DETAIL_INSERTION_SORT_HPP
 
 #include <boost/compute/command_queue.hpp>
 #include <boost/compute/detail/dtype.hpp>

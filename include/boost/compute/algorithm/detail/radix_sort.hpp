@@ -1,8 +1,8 @@
 // detail::radix_sort / radix_sort_by_key (algorithm/detail/radix_sort.hpp:428-462 of the reference).
 // The reference builds and runs 3 OpenCL kernels per 4-bit pass here; this header only turns the iterator
 // arguments into (device pointer, count, dtype code) and calls the ahead-of-time compiled onesweep sort.
-#ifndef BOOST_COMPUTE_ALGORITHM_DETAIL_RADIX_SORT_HPP
-#define BOOST_COMPUTE_ALGORITHM_DETAIL_RADIX_SORT_HPP
+#ifndef B200_BOOST_COMPUTE_ALGORITHM_DETAIL_RADIX_SORT_HPP
+#define B200_BOOST_COMPUTE_ALGORITHM_DETAIL_RADIX_SORT_HPP
 
 #include <iterator>
 

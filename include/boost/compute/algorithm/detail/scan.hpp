@@ -2,8 +2,8 @@
 // The reference switches between scan_on_cpu and the recursive scan_on_gpu; here it is one launch of the
 // single-pass decoupled look-back kernel behind bcb_scan.  Arithmetic happens in the OUTPUT value type
 // (exclusive_scan.hpp:80-85); `first == result` (in place) is allowed.
-#ifndef BOOST_COMPUTE_ALGORITHM_DETAIL_SCAN_HPP
-#define BOOST_COMPUTE_ALGORITHM_DETAIL_SCAN_HPP
+#ifndef B200_BOOST_COMPUTE_ALGORITHM_DETAIL_SCAN_HPP
+#define B200_BOOST_COMPUTE_ALGORITHM_DETAIL_SCAN_HPP
 
 #include <boost/compute/command_queue.hpp>
 #include <boost/compute/detail/dtype.hpp>

@@ -1,7 +1,7 @@
 // exclusive_scan() (algorithm/exclusive_scan.hpp:55-104 of the reference):
 // result[i] = init op first[0] op ... op first[i-1]; default init 0, default op plus<output value type>.
-#ifndef BOOST_COMPUTE_ALGORITHM_EXCLUSIVE_SCAN_HPP
-#define BOOST_COMPUTE_ALGORITHM_EXCLUSIVE_SCAN_HPP
+#ifndef B200_BOOST_COMPUTE_ALGORITHM_EXCLUSIVE_SCAN_HPP
+#define B200_BOOST_COMPUTE_ALGORITHM_EXCLUSIVE_SCAN_HPP
 
 #include <iterator>
 

@@ -1,6 +1,6 @@
 // fill / fill_n (algorithm/fill.hpp, fill_n.hpp of the reference): one trivial kernel behind bcb_fill.
-#ifndef BOOST_COMPUTE_ALGORITHM_FILL_HPP
-#define BOOST_COMPUTE_ALGORITHM_FILL_HPP
+#ifndef B200_BOOST_COMPUTE_ALGORITHM_FILL_HPP
+#define B200_BOOST_COMPUTE_ALGORITHM_FILL_HPP
 
 #include <boost/compute/command_queue.hpp>
 #include <boost/compute/detail/default_queue.hpp>

@@ -1,4 +1,4 @@
-#ifndef BOOST_COMPUTE_ALGORITHM_FILL_N_HPP
-#define BOOST_COMPUTE_ALGORITHM_FILL_N_HPP
+#ifndef B200_BOOST_COMPUTE_ALGORITHM_FILL_N_HPP
+#define B200_BOOST_COMPUTE_ALGORITHM_FILL_N_HPP
 #include <boost/compute/algorithm/fill.hpp>
 #endif

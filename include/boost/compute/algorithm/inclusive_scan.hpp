@@ -1,6 +1,6 @@
 // inclusive_scan() (algorithm/inclusive_scan.hpp:53-87 of the reference): result[i] = first[0] op ... op first[i].
-#ifndef BOOST_COMPUTE_ALGORITHM_INCLUSIVE_SCAN_HPP
-#define BOOST_COMPUTE_ALGORITHM_INCLUSIVE_SCAN_HPP
+#ifndef B200_BOOST_COMPUTE_ALGORITHM_INCLUSIVE_SCAN_HPP
+#define B200_BOOST_COMPUTE_ALGORITHM_INCLUSIVE_SCAN_HPP
 
 #include <iterator>
 

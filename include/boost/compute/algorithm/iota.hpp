@@ -1,6 +1,6 @@
 // iota (algorithm/iota.hpp of the reference): first[i] = value + i.
-#ifndef BOOST_COMPUTE_ALGORITHM_IOTA_HPP
-#define BOOST_COMPUTE_ALGORITHM_IOTA_HPP
+#ifndef B200_BOOST_COMPUTE_ALGORITHM_IOTA_HPP
+#define B200_BOOST_COMPUTE_ALGORITHM_IOTA_HPP
 
 #include <boost/compute/command_queue.hpp>
 #include <boost/compute/detail/default_queue.hpp>

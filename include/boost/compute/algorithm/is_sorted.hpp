@@ -1,7 +1,7 @@
 // is_sorted (algorithm/is_sorted.hpp:39-68 of the reference): true when no adjacent pair is out of order
 // under less<T> (default) or greater<T>.  Blocks (returns a host bool).
-#ifndef BOOST_COMPUTE_ALGORITHM_IS_SORTED_HPP
-#define BOOST_COMPUTE_ALGORITHM_IS_SORTED_HPP
+#ifndef B200_BOOST_COMPUTE_ALGORITHM_IS_SORTED_HPP
+#define B200_BOOST_COMPUTE_ALGORITHM_IS_SORTED_HPP
 
 #include <boost/compute/command_queue.hpp>
 #include <boost/compute/detail/default_queue.hpp>

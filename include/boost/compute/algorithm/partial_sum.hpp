@@ -1,6 +1,6 @@
 // partial_sum() (algorithm/partial_sum.hpp:31-41 of the reference) == inclusive_scan with plus.
-#ifndef BOOST_COMPUTE_ALGORITHM_PARTIAL_SUM_HPP
-#define BOOST_COMPUTE_ALGORITHM_PARTIAL_SUM_HPP
+#ifndef B200_BOOST_COMPUTE_ALGORITHM_PARTIAL_SUM_HPP
+#define B200_BOOST_COMPUTE_ALGORITHM_PARTIAL_SUM_HPP
 
 #include <boost/compute/algorithm/inclusive_scan.hpp>
 

@@ -5,8 +5,8 @@
 //   * the arithmetic type is the functor's type U for plus<U> etc. (result_of<F(T,T)>), so plus<float> over a
 //     uchar range accumulates in float (test_reduce.cpp:269-277).
 // One kernel launch (vectorised loads + warp shuffles + last-block fold) replaces reduce_on_gpu's three.
-#ifndef BOOST_COMPUTE_ALGORITHM_REDUCE_HPP
-#define BOOST_COMPUTE_ALGORITHM_REDUCE_HPP
+#ifndef B200_BOOST_COMPUTE_ALGORITHM_REDUCE_HPP
+#define B200_BOOST_COMPUTE_ALGORITHM_REDUCE_HPP
 
 #include <iterator>
 #include <type_traits>

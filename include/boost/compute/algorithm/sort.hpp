@@ -5,8 +5,8 @@
 //                                                          reference maps the range with a mapped_view (:125-148)
 // Custom comparison functions need run-time OpenCL code generation in the reference (merge sort path) and are
 // outside the hot path: they fail to compile with a clear message.
-#ifndef BOOST_COMPUTE_ALGORITHM_SORT_HPP
-#define BOOST_COMPUTE_ALGORITHM_SORT_HPP
+#ifndef B200_BOOST_COMPUTE_ALGORITHM_SORT_HPP
+#define B200_BOOST_COMPUTE_ALGORITHM_SORT_HPP
 
 #include <iterator>
 #include <type_traits>

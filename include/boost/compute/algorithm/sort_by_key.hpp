@@ -1,7 +1,7 @@
 // sort_by_key() (algorithm/sort_by_key.hpp:135-163 of the reference) and dispatch_gpu_sort_by_key (:33-86):
 // fewer than 32 keys -> serial insertion sort by key, otherwise stable radix sort carrying the values.
-#ifndef BOOST_COMPUTE_ALGORITHM_SORT_BY_KEY_HPP
-#define BOOST_COMPUTE_ALGORITHM_SORT_BY_KEY_HPP
+#ifndef B200_BOOST_COMPUTE_ALGORITHM_SORT_BY_KEY_HPP
+#define B200_BOOST_COMPUTE_ALGORITHM_SORT_BY_KEY_HPP
 
 #include <iterator>
 

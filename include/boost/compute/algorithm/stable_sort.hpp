@@ -1,7 +1,7 @@
 // stable_sort() (algorithm/stable_sort.hpp:52-110 of the reference): with less<T> / greater<T> on a
 // radix-sortable T it goes straight to the (stable) radix sort, with no small-n branch.
-#ifndef BOOST_COMPUTE_ALGORITHM_STABLE_SORT_HPP
-#define BOOST_COMPUTE_ALGORITHM_STABLE_SORT_HPP
+#ifndef B200_BOOST_COMPUTE_ALGORITHM_STABLE_SORT_HPP
+#define B200_BOOST_COMPUTE_ALGORITHM_STABLE_SORT_HPP
 
 #include <iterator>
 

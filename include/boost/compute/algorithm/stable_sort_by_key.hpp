@@ -1,7 +1,7 @@
 // stable_sort_by_key() (algorithm/stable_sort_by_key.hpp:29-163 of the reference): radix_sort_by_key for
 // less<T> / greater<T> on radix-sortable keys.
-#ifndef BOOST_COMPUTE_ALGORITHM_STABLE_SORT_BY_KEY_HPP
-#define BOOST_COMPUTE_ALGORITHM_STABLE_SORT_BY_KEY_HPP
+#ifndef B200_BOOST_COMPUTE_ALGORITHM_STABLE_SORT_BY_KEY_HPP
+#define B200_BOOST_COMPUTE_ALGORITHM_STABLE_SORT_BY_KEY_HPP
 
 #include <iterator>
 

@@ -1,8 +1,8 @@
 // buffer (buffer.hpp:54-191 + memory_object.hpp of the reference): a reference-counted block of device
 // memory.  Copies share the allocation (the reference retains the cl_mem); the memory is released when
 // the last copy goes away.
-#ifndef BOOST_COMPUTE_BUFFER_HPP
-#define BOOST_COMPUTE_BUFFER_HPP
+#ifndef B200_BOOST_COMPUTE_BUFFER_HPP
+#define B200_BOOST_COMPUTE_BUFFER_HPP
 
 #include <cstddef>
 #include <memory>

@@ -1,7 +1,7 @@
 // command_queue (command_queue.hpp:78-1960 of the reference): an in-order queue = one CUDA stream.
 // Algorithms enqueue work and return; finish() waits (command_queue.hpp:1564-1572).
-#ifndef BOOST_COMPUTE_COMMAND_QUEUE_HPP
-#define BOOST_COMPUTE_COMMAND_QUEUE_HPP
+#ifndef B200_BOOST_COMPUTE_COMMAND_QUEUE_HPP
+#define B200_BOOST_COMPUTE_COMMAND_QUEUE_HPP
 
 #include <cstddef>
 #include <memory>

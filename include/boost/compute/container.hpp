@@ -1,5 +1,5 @@
-#ifndef BOOST_COMPUTE_CONTAINER_HPP
-#define BOOST_COMPUTE_CONTAINER_HPP
+#ifndef B200_BOOST_COMPUTE_CONTAINER_HPP
+#define B200_BOOST_COMPUTE_CONTAINER_HPP
 #include <boost/compute/container/array.hpp>
 #include <boost/compute/container/mapped_view.hpp>
 #include <boost/compute/container/vector.hpp>

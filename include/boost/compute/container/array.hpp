@@ -1,7 +1,7 @@
 // array<T, N> (container/array.hpp:48-281 of the reference): a fixed-size device array with the std::array surface.
 // Host-side construction takes std::array (the reference takes boost::array; Boost is not a dependency here).
-#ifndef BOOST_COMPUTE_CONTAINER_ARRAY_HPP
-#define BOOST_COMPUTE_CONTAINER_ARRAY_HPP
+#ifndef B200_BOOST_COMPUTE_CONTAINER_ARRAY_HPP
+#define B200_BOOST_COMPUTE_CONTAINER_ARRAY_HPP
 
 #include <array>
 #include <cstddef>

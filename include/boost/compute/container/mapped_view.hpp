@@ -1,8 +1,8 @@
 // mapped_view<T> (container/mapped_view.hpp:43-245 of the reference): a device-iterable view of an existing host
 // range.  The reference creates a CL_MEM_USE_HOST_PTR buffer; here the range is registered with the CUDA driver and
 // kernels address it in place over PCIe (zero copy).  The host range must outlive the view.
-#ifndef BOOST_COMPUTE_CONTAINER_MAPPED_VIEW_HPP
-#define BOOST_COMPUTE_CONTAINER_MAPPED_VIEW_HPP
+#ifndef B200_BOOST_COMPUTE_CONTAINER_MAPPED_VIEW_HPP
+#define B200_BOOST_COMPUTE_CONTAINER_MAPPED_VIEW_HPP
 
 #include <cstddef>
 

@@ -3,8 +3,8 @@
 // perf harness use: construction from counts / fill values / host ranges / std::vector, size bookkeeping with
 // the reference's growth policy (minimum capacity 4, x1.5), element access through buffer_value proxies,
 // push_back / resize / assign and begin()/end() buffer_iterators.
-#ifndef BOOST_COMPUTE_CONTAINER_VECTOR_HPP
-#define BOOST_COMPUTE_CONTAINER_VECTOR_HPP
+#ifndef B200_BOOST_COMPUTE_CONTAINER_VECTOR_HPP
+#define B200_BOOST_COMPUTE_CONTAINER_VECTOR_HPP
 
 #include <algorithm>
 #include <cstddef>

@@ -1,6 +1,6 @@
 // context (context.hpp:79-98 of the reference): here simply "the primary CUDA context of one device".
-#ifndef BOOST_COMPUTE_CONTEXT_HPP
-#define BOOST_COMPUTE_CONTEXT_HPP
+#ifndef B200_BOOST_COMPUTE_CONTEXT_HPP
+#define B200_BOOST_COMPUTE_CONTEXT_HPP
 
 #include <boost/compute/device.hpp>
 

@@ -1,5 +1,5 @@
-#ifndef BOOST_COMPUTE_CORE_HPP
-#define BOOST_COMPUTE_CORE_HPP
+#ifndef B200_BOOST_COMPUTE_CORE_HPP
+#define B200_BOOST_COMPUTE_CORE_HPP
 #include <boost/compute/buffer.hpp>
 #include <boost/compute/command_queue.hpp>
 #include <boost/compute/context.hpp>

@@ -1,5 +1,5 @@
-#ifndef BOOST_COMPUTE_DETAIL_DEFAULT_QUEUE_HPP
-#define BOOST_COMPUTE_DETAIL_DEFAULT_QUEUE_HPP
+#ifndef B200_BOOST_COMPUTE_DETAIL_DEFAULT_QUEUE_HPP
+#define B200_BOOST_COMPUTE_DETAIL_DEFAULT_QUEUE_HPP
 
 #include <boost/compute/system.hpp>
 

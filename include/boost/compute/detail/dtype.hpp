@@ -1,8 +1,8 @@
 // Maps C++ scalar types and functor tags onto the integer codes of the C ABI (include/compute_b200.h).
 // This replaces type_name<T>() + "-DT=..." JIT options of the reference (type_traits/type_name.hpp:95-99,
 // algorithm/detail/radix_sort.hpp:289-311): kernels are compiled ahead of time, the header only picks one.
-#ifndef BOOST_COMPUTE_DETAIL_DTYPE_HPP
-#define BOOST_COMPUTE_DETAIL_DTYPE_HPP
+#ifndef B200_BOOST_COMPUTE_DETAIL_DTYPE_HPP
+#define B200_BOOST_COMPUTE_DETAIL_DTYPE_HPP
 
 #include <type_traits>
 

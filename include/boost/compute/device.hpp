@@ -1,7 +1,7 @@
 // device (device.hpp:49-157 of the reference): identifies one CUDA device; only the queries the
 // sort / scan / reduce path and its tests use.
-#ifndef BOOST_COMPUTE_DEVICE_HPP
-#define BOOST_COMPUTE_DEVICE_HPP
+#ifndef B200_BOOST_COMPUTE_DEVICE_HPP
+#define B200_BOOST_COMPUTE_DEVICE_HPP
 
 #include <cstddef>
 #include <string>

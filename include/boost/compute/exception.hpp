@@ -1,4 +1,4 @@
-#ifndef BOOST_COMPUTE_EXCEPTION_HPP
-#define BOOST_COMPUTE_EXCEPTION_HPP
+#ifndef B200_BOOST_COMPUTE_EXCEPTION_HPP
+#define B200_BOOST_COMPUTE_EXCEPTION_HPP
 #include <boost/compute/exception/opencl_error.hpp>
 #endif

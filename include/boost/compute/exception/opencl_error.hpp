@@ -1,7 +1,7 @@
 // opencl_error (exception/opencl_error.hpp:30-61): the exception every failing runtime call turns into.
 // The error code is a cudaError_t value or a BCB_E* code of the C ABI instead of a CL_* constant.
-#ifndef BOOST_COMPUTE_EXCEPTION_OPENCL_ERROR_HPP
-#define BOOST_COMPUTE_EXCEPTION_OPENCL_ERROR_HPP
+#ifndef B200_BOOST_COMPUTE_EXCEPTION_OPENCL_ERROR_HPP
+#define B200_BOOST_COMPUTE_EXCEPTION_OPENCL_ERROR_HPP
 
 #include <exception>
 #include <string>

@@ -1,4 +1,4 @@
-#ifndef BOOST_COMPUTE_FUNCTIONAL_HPP
-#define BOOST_COMPUTE_FUNCTIONAL_HPP
+#ifndef B200_BOOST_COMPUTE_FUNCTIONAL_HPP
+#define B200_BOOST_COMPUTE_FUNCTIONAL_HPP
 #include <boost/compute/functional/operator.hpp>
 #endif

@@ -1,8 +1,8 @@
 // Functor tags (functional/operator.hpp:57-96 of the reference).  In the reference these generate OpenCL C
 // source at run time; here they are empty tag types that select an ahead-of-time compiled kernel through
 // the bcb_op code, and remain callable on the host.
-#ifndef BOOST_COMPUTE_FUNCTIONAL_OPERATOR_HPP
-#define BOOST_COMPUTE_FUNCTIONAL_OPERATOR_HPP
+#ifndef B200_BOOST_COMPUTE_FUNCTIONAL_OPERATOR_HPP
+#define B200_BOOST_COMPUTE_FUNCTIONAL_OPERATOR_HPP
 
 #include <compute_b200.h>
 

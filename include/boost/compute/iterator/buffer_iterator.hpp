@@ -1,8 +1,8 @@
 // buffer_iterator<T> (iterator/buffer_iterator.hpp:136-271 of the reference): random-access iterator over
 // a device buffer = (buffer, element index).  It does not keep the buffer alive on its own in the reference
 // either; here it shares ownership, which is harmless.
-#ifndef BOOST_COMPUTE_ITERATOR_BUFFER_ITERATOR_HPP
-#define BOOST_COMPUTE_ITERATOR_BUFFER_ITERATOR_HPP
+#ifndef B200_BOOST_COMPUTE_ITERATOR_BUFFER_ITERATOR_HPP
+#define B200_BOOST_COMPUTE_ITERATOR_BUFFER_ITERATOR_HPP
 
 #include <cstddef>
 #include <iterator>

@@ -1,8 +1,8 @@
 // system (system.hpp:92-440 of the reference): default device / context / queue and device enumeration.
 // Device selection honours BOOST_COMPUTE_DEFAULT_DEVICE (substring of the device name, system.hpp:244-248),
 // otherwise device 0 of CUDA_VISIBLE_DEVICES.
-#ifndef BOOST_COMPUTE_SYSTEM_HPP
-#define BOOST_COMPUTE_SYSTEM_HPP
+#ifndef B200_BOOST_COMPUTE_SYSTEM_HPP
+#define B200_BOOST_COMPUTE_SYSTEM_HPP
 
 #include <cstdlib>
 #include <string>

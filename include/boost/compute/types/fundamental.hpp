@@ -1,7 +1,7 @@
 // Scalar type aliases of the reference (boost/compute/types/fundamental.hpp:30-39): char_ ... double_,
 // here plain fixed-width C++ types instead of cl_* typedefs.
-#ifndef BOOST_COMPUTE_TYPES_FUNDAMENTAL_HPP
-#define BOOST_COMPUTE_TYPES_FUNDAMENTAL_HPP
+#ifndef B200_BOOST_COMPUTE_TYPES_FUNDAMENTAL_HPP
+#define B200_BOOST_COMPUTE_TYPES_FUNDAMENTAL_HPP
 
 #include <cstdint>
 
