@@ -21,7 +21,8 @@ def _compile(src, out, extra=()):
 def binaries(tmp_path_factory):
     d = tmp_path_factory.mktemp("cpp")
     out = {}
-    for name, src in (("test_api", "tests/cpp/test_api.cpp"), ("sort_vector", "examples/sort_vector.cpp")):
+    for name, src in (("test_api", "tests/cpp/test_api.cpp"), ("sort_vector", "examples/sort_vector.cpp"),
+                      ("perf_primitives", "examples/perf_primitives.cpp")):
         r = _compile(os.path.join(ROOT, src), str(d / name))
         assert r.returncode == 0, r.stderr
         out[name] = str(d / name)
@@ -61,3 +62,9 @@ def test_cpp_api_on_gpu(binaries):
 def test_sort_vector_example_on_gpu(binaries):
     r = subprocess.run([binaries["sort_vector"]], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "sorted" in r.stdout and "NOT" not in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_perf_harness_example_on_gpu(binaries):
+    r = subprocess.run([binaries["perf_primitives"], "22", "2"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "results ok" in r.stdout, r.stdout + r.stderr
