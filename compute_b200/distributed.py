@@ -427,7 +427,7 @@ class Context:
         max_recv = int(recv_tot.max())
         val_off = (max_recv * ksize + 255) & ~255                        # values region of every receive buffer
         # the all-gather above also orders this call after every rank's previous use of its receive buffer
-        if not self.peer.ensure(val_off + max_recv * vb):
+        if not self.peer.ensure(max(256, val_off + max_recv * vb)):  # (at least a token buffer: an all-empty range still maps peers)
             return None
         offs = np.cumsum(counts, axis=0) - counts                        # offs[src][dst]: where src's slice starts at dst
         dst_k = [self.peer.peers[d] + int(offs[me][d]) * ksize for d in range(P)]

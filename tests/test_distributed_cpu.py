@@ -233,6 +233,10 @@ def _worker(rank, world, port, results):
         out["sum"] = ctx.reduce(mine)
         out["min"] = ctx.reduce(mine, "min")
         out["acc"] = ctx.accumulate(mine, 5)
+        # globally empty range, on a fresh Context (no receive buffers yet)
+        ctx0 = cbd.Context(local_ops=ops, samples_per_rank=64)
+        out["empty"] = ctx0.sort(torch.empty(0, dtype=torch.int32)).numel()
+        ctx0.peer.release()
         # peer mapping unavailable on one rank only: every rank must fall back together
         ctx2 = cbd.Context(local_ops=ops, samples_per_rank=64)
         ops.fail_peer_alloc = (rank == 1)
@@ -273,6 +277,7 @@ def test_gloo_ranks_match_single_device_oracle(world):
     assert np.concatenate([r["big"] for r in res]).tobytes() == oracle.radix_sort(big, False).tobytes()
     assert np.concatenate([r["fb"] for r in res]).tobytes() == oracle.radix_sort(allk, True).tobytes()
     assert [r["stats_fb"]["plan"] for r in res] == ["partition"] * world
+    assert all(r["empty"] == 0 for r in res)
     assert res[0]["stats"]["plan"] == "peer-scatter" and res[0]["stats1"]["plan"] == "partition"
     assert res[0]["stats2"]["plan"] == "sort-and-cut"
     assert res[0]["stats"]["imbalance"] < 1.6
