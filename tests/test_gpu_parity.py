@@ -444,3 +444,12 @@ def test_large_descending_float_sort_with_colliding_keys_stays_deterministic(dty
     assert gpu.radix_sort(k, False).tobytes() == oracle.radix_sort(k, False).tobytes()
     cb.lib().bcb_sort_speculation_stats(q.handle, ctypes.byref(runs1), ctypes.byref(falls))
     assert runs1.value == runs0.value + 1 and falls.value == 0  # ascending: injective transform, speculative + verified
+
+
+@pytest.mark.parametrize("dtype", ["uchar", "char", "short", "ushort"])
+def test_large_narrow_key_sorts_use_the_column_histogram(dtype, gpu):
+    """8- and 16-bit keys never speculate, but from 2^22 keys on they share the lane-column histogram kernel."""
+    n = (1 << 22) + 5
+    k = random_keys(dtype, n, seed=23, mode="bits")
+    for desc in (False, True):
+        assert gpu.radix_sort(k, desc).tobytes() == oracle.radix_sort(k, desc).tobytes(), (dtype, desc)
