@@ -30,7 +30,6 @@ SIGNATURES = {
     "bcb_memcpy_h2d": ([_vp, _vp, _vp, _sz], _i),
     "bcb_memcpy_d2h": ([_vp, _vp, _vp, _sz], _i),
     "bcb_memcpy_d2d": ([_vp, _vp, _vp, _sz], _i),
-    "bcb_copy_kernel": ([_vp, _vp, _vp, _sz, _i], _i),
     "bcb_fill": ([_vp, _vp, _sz, _vp, _sz], _i),
     "bcb_iota": ([_vp, _i, _vp, _sz, _vp], _i),
     "bcb_is_sorted": ([_vp, _i, _i, _vp, _sz, _pi], _i),

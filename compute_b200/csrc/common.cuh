@@ -45,20 +45,27 @@ struct StreamState {
     size_t scratch_bytes = 0;
     // small persistent control block, zeroed once at creation:
     //   [0]   u64 ticket counter (monotonic across calls; launchers pass the base)
-    //   [1..] reserved
+    //   [1]   int flag of the speculative sort: set by the verification kernel when the result is not sorted
+    //   [2]   u64 number of speculative sorts that fell back to the deterministic kernel
     unsigned long long *control = nullptr;
     unsigned long long ticket_base = 0;
-    // decoupled look-back descriptors (scan + sort); zeroed at (re)allocation, validated by epoch tags
-    void *lookback = nullptr;
-    size_t lookback_bytes = 0;
-    uint32_t epoch = 0;  // 30-bit generation tag, bumped once per launch that uses `lookback`
+    // decoupled look-back descriptors (scan + sort); zeroed at (re)allocation, validated by epoch tags.  One arena per
+    // descriptor LAYOUT, each with its own epoch counter: a slot is only ever read under the layout it was written in,
+    // so a stale word can never alias a valid tag of another layout (kArenaPacked: u64 {tag:32 | payload:32} words of
+    // the sort and the <= 4-byte scans; kArenaWide: 32-byte {status, partial, inclusive} records of the 8-byte scans)
+    struct LookbackArena {
+        void *mem = nullptr;
+        size_t bytes = 0;
+        uint32_t epoch = 0;  // 30-bit generation tag, bumped once per launch that uses the arena
+    };
+    LookbackArena arena[2];
     // radix digit histograms / bases
     uint32_t *hist = nullptr;  // [8 passes][256]
     // pinned, device-mapped result slot for host-returning calls
     void *pinned_slot = nullptr;      // host address
     void *pinned_slot_dev = nullptr;  // device alias
     int sm_count = 0;
-    unsigned long long spec_runs = 0, spec_fallbacks = 0;  // speculative keys-only sorts: verified runs / re-sorts
+    unsigned long long spec_runs = 0;  // speculative keys-only sorts enqueued (fallbacks are counted on the device)
     // optional per-kernel timing (bcb_timing_*): CUDA event pairs recorded around each launch
     bool timing = false;
     struct TimedLaunch { int kind; cudaEvent_t start, stop; };
@@ -76,11 +83,16 @@ struct LaunchTimer {
 
 int stream_state(cudaStream_t stream, StreamState **out);
 int scratch_reserve(StreamState *st, size_t bytes, void **out);
-int lookback_reserve(StreamState *st, size_t bytes, void **out);
-// next epoch tag in [1, 2^30): wraps by zeroing the look-back array
-int next_epoch(StreamState *st, uint32_t *epoch);
+enum { kArenaPacked = 0, kArenaWide = 1, kArenaCount = 2 };
+// Reserve FIRST, then draw the epoch: a (re)allocation zeroes the arena and restarts its epoch counter, so an epoch
+// drawn before the last reserve of a launch could be handed out again later.
+int lookback_reserve(StreamState *st, int arena, size_t bytes, void **out);
+// next epoch tag in [1, 2^30) of the arena: wraps by zeroing the arena
+int next_epoch(StreamState *st, int arena, uint32_t *epoch);
+// persistent kernels draw tile ids from the per-stream ticket counter: returns the base of `draws` fresh tickets
+unsigned long long ticket_reserve(StreamState *st, unsigned long long draws);
 
-constexpr int kControlTicket = 0;
+constexpr int kControlTicket = 0, kControlSpecFlag = 1, kControlSpecFallbacks = 2;
 
 // ---- device helpers ------------------------------------------------------------------------
 #ifdef __CUDACC__
@@ -128,6 +140,41 @@ __device__ __forceinline__ void st_stream_v4(void *p, uint4 v)
 {
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                  : "memory");
+}
+
+
+// L2 eviction-priority policies for loads that carry a cache hint (createpolicy, PTX 7.4+)
+__device__ __forceinline__ unsigned long long l2_policy_evict_last()
+{
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first()
+{
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint4 ld_hint_v4(const void *p, unsigned long long policy)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(policy));
+    return r;
+}
+__device__ __forceinline__ unsigned ld_hint(const unsigned *p, unsigned long long policy)
+{
+    unsigned r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(policy));
+    return r;
+}
+__device__ __forceinline__ unsigned long long ld_hint(const unsigned long long *p, unsigned long long policy)
+{
+    unsigned long long r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(r) : "l"(p), "l"(policy));
+    return r;
 }
 
 #endif  // __CUDACC__

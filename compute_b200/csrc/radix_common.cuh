@@ -1,4 +1,4 @@
-// radix_common.cuh -- pieces shared by the radix-sort translation units (radix_sort.cu, radix_sort_ns.cu)
+// radix_common.cuh -- pieces shared by the radix-sort translation units (radix_sort.cu, radix_pass_ws.cu)
 #pragma once
 
 #include "ops.cuh"
@@ -124,9 +124,10 @@ __device__ __forceinline__ unsigned pass_digit(K raw, int shift, const Transform
 }
 
 
-// nibble-split pass kernel (radix_sort_ns.cu): keys only.  Returns BCB_EUNSUPPORTED for shapes it does not cover.
-int ns_launch_pass(StreamState *st, int key_bytes, const void *kin, void *kout, const unsigned *base, unsigned long long *lookback,
-                   size_t n, int shift, const Transform &tf, int digit_mode);
-size_t ns_tile_size();
+// warp-specialised bulk-copy pass kernel (radix_pass_ws.cu): large keys-only sorts of 32- / 64-bit keys, speculative
+// two-sweep ranking.  Returns BCB_EUNSUPPORTED for shapes it does not cover (arrays not 16-byte aligned).
+int ws_launch_pass(StreamState *st, int key_bytes, const void *kin, void *kout, const unsigned *base, unsigned long long *lookback,
+                   size_t n, int shift, const Transform &tf);
+size_t ws_tile_size(int key_bytes);
 
 }  // namespace bcb

@@ -1,0 +1,414 @@
+// radix_pass_ws.cu -- warp-specialised onesweep pass for large keys-only sorts of 32- and 64-bit keys on sm_100a.
+//
+// Replaces one (count + scan + scatter) round of the reference's radix_sort_impl (algorithm/detail/radix_sort.hpp:
+// 186-250, 347-425) with ONE launch per 8-bit digit.  What shaped it (bench/tma_scatter.cu, bench/tma_issue.cu,
+// measured on B200):
+//   * the scatter phase of a radix pass is bound by the memory system, not by the SM: a write whose ends do not fall on
+//     32-byte sector boundaries costs far more than its bytes.  256 runs of 48 keys per tile (12288-key tiles, r01)
+//     move 2 x 4.3 GB in 3.0 ms, runs of 96 keys in 2.0 ms, runs of 192 keys in 1.8 ms.  So: ONE tile buffer as large
+//     as shared memory allows (49152 u32 keys = 192 KB), and every digit run leaves the SM as one cp.async.bulk
+//     shared->global copy of its 16-byte aligned body (only the <= 3 + 3 edge keys of a run are stored by the LSU);
+//   * a bulk copy needs 16-byte aligned addresses on both sides, so the digit-sorted tile is laid out in shared memory
+//     with every run shifted to the alignment of its destination (3 pad keys per digit at most).  The global position
+//     must therefore be known BEFORE the keys are scattered into shared memory: the decoupled look-back runs between
+//     the counting sweep and the scatter sweep of a tile, in helper warps, while the workers scatter the previous tile;
+//   * issuing a small bulk copy costs a warp ~70-130 cycles (per-lane ELECT / R2UR loop), so the copies are issued by
+//     8 helper warps (one digit run per thread), never by the workers;
+//   * the counting sweep reads the keys straight from global memory (128-bit loads, nothing kept), the scatter sweep
+//     reads them again one tile later (an L2 hit: ~40 MB pass through the 126 MB L2 in between) -- no landing buffer,
+//     no registers held across the look-back;
+//   * ranking is the two-sweep scheme of radix_sort.cu (sweep 1: shared-memory atomicAdd per (warp, digit), sweep 2: the
+//     same atomics in the same order return the position), with 16-bit counters packed two per word.  Like
+//     kRankTwoSweep it relies on same-address shared atomics of one warp instruction being applied in lane order;
+//     sort_typed verifies the result (verify_sorted_kernel) and falls back on the device if that ever fails.
+// One CTA per SM: 24 worker warps + 8 helper warps.  Tiles are drawn from a ticket (atomic counter) so forward
+// progress never depends on which CTAs are resident.
+//   workers:  count(t0) | count(t1) scatter(t0) | count(t2) scatter(t1) | ...
+//   helpers:            | offsets+look-back(t0) | offsets(t1) store(t0) | offsets(t2) store(t1) | ...
+#include "radix_common.cuh"
+#include "tma.cuh"
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <type_traits>
+
+namespace bcb {
+
+// -DBCB_WS_PROFILE: per-CTA cycle counters of the phases (thread 0 of each role), printed by the launcher
+#ifdef BCB_WS_PROFILE
+#define WS_PROF_DECL unsigned long long prof_t0 = 0, prof_acc[8] = {}
+#define WS_PROF_BEGIN() prof_t0 = clock64()
+#define WS_PROF_END(k) do { const unsigned long long now_ = clock64(); prof_acc[k] += now_ - prof_t0; prof_t0 = now_; } while (0)
+#define WS_PROF_DUMP(base) do { for (int q = 0; q < 8; q++) g_ws_prof[(size_t)blockIdx.x * 16 + (base) + q] = prof_acc[q]; } while (0)
+__device__ unsigned long long g_ws_prof[148 * 16 * 4];
+#else
+#define WS_PROF_DECL
+#define WS_PROF_BEGIN()
+#define WS_PROF_END(k)
+#define WS_PROF_DUMP(base)
+#endif
+
+constexpr int kWsWorkerWarps = 24;
+constexpr int kWsWorkers = kWsWorkerWarps * 32;  // 768
+constexpr int kWsHelpers = kRadixSize;           // one per digit value
+constexpr int kWsThreads = kWsWorkers + kWsHelpers;
+constexpr unsigned kWsNoTile = 0xffffffffu;
+// named barriers (0 is __syncthreads); p = parity of the tile's sequence number inside the CTA
+enum { kBarCounted = 1 /* +p */, kBarOffsets = 3 /* +p */, kBarScattered = 5, kBarDrained = 6, kBarHelpers = 7, kBarWorkers = 8 };
+
+template <typename K> struct WsShape {
+    static constexpr int A = 16 / (int)sizeof(K);          // keys per 16-byte chunk
+    static constexpr int ITEMS = 224 / (int)sizeof(K);     // keys per worker thread: 168 KB tiles
+    static constexpr int CHUNK = 56 / (int)sizeof(K);      // keys a worker holds in registers at a time (+ as many in flight)
+    static constexpr int SEG = ITEMS * 32;                 // keys per worker warp (one contiguous segment)
+    static constexpr int TILE = kWsWorkers * ITEMS;        // 43008 (u32) / 21504 (u64)
+    static constexpr int PAD = (A - 1) * kRadixSize;       // alignment shifts: run d starts (A-1)*d + [0, A) later
+    static constexpr size_t BUF_BYTES = (size_t)(TILE + PAD) * sizeof(K);
+    static constexpr size_t TAB_BYTES = 2 * (size_t)kWsWorkerWarps * kRadixSize * sizeof(unsigned);  // [2][24][256]
+    static constexpr size_t MISC_BYTES = 128;
+    static constexpr size_t SMEM_BYTES = BUF_BYTES + TAB_BYTES + MISC_BYTES;
+    static_assert(BUF_BYTES % 128 == 0, "the tables stay aligned");
+    static_assert(ITEMS % CHUNK == 0, "whole chunks");
+    static_assert(SMEM_BYTES <= 232448, "one CTA per SM: 227 KB of shared memory");
+};
+
+template <typename K, int IDENT, int LB>
+__global__ void __launch_bounds__(kWsThreads, 1)
+onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const unsigned *__restrict__ digit_base,
+            unsigned long long *lookback, unsigned epoch, size_t n, unsigned num_tiles, int shift,
+            const __grid_constant__ Transform tf, unsigned long long *ticket, unsigned long long ticket_base, int flags)
+{
+    typedef WsShape<K> C;
+    constexpr int ITEMS = C::ITEMS, TILE = C::TILE, A = C::A, SEG = C::SEG, CHUNK = C::CHUNK;
+    constexpr int ROW = kRadixSize;  // words per (warp, tile) table row.  (16-bit counters packed two per word would let
+                                     // the tile grow to 49152 keys, but measured 4.0 instead of 3.35 wavefronts per atomic:
+                                     // twice as many lanes share a word -- and five more ALU instructions per key)
+    extern __shared__ __align__(128) unsigned char smem[];
+    K *buf = reinterpret_cast<K *>(smem);
+    unsigned *tab = reinterpret_cast<unsigned *>(smem + C::BUF_BYTES);                          // [2][24][ROW]
+    volatile unsigned *ring = reinterpret_cast<volatile unsigned *>(smem + C::BUF_BYTES + C::TAB_BYTES);  // [4] tile ids
+    unsigned *hscan = const_cast<unsigned *>(ring) + 4;                                        // [2][8] helper warp sums
+    const unsigned tid = threadIdx.x;
+
+    for (unsigned i = tid; i < 2 * kWsWorkerWarps * ROW; i += kWsThreads) tab[i] = 0;
+    __syncthreads();
+
+    if (tid < kWsWorkers) {
+        // ======================= workers: counting sweep, scatter sweep =======================
+        const unsigned w = tid >> 5, lane = tid & 31u;
+        const unsigned long long keep = l2_policy_evict_last(), drop = l2_policy_evict_first();
+        WS_PROF_DECL;
+        auto draw = [&](unsigned i) {  // tile id of the CTA's i-th tile -> ring[i & 3], visible after the workers' barrier
+            if (tid == 0) {
+                const unsigned long long t = atomicAdd(ticket, 1ull) - ticket_base;
+                ring[i & 3u] = t < num_tiles ? (unsigned)t : kWsNoTile;
+                // BCB_WS_FLAGS=1 (experiment, measured 5 % SLOWER): pull the tile that will be drawn one round from now into
+                // L2 with the bulk-copy engine.  The counting sweep gets faster, but the pass is bound by the memory
+                // system (scattered writes), and the stores of the previous tile then simply drain later.
+                const unsigned long long ahead = t + gridDim.x;
+                if ((flags & 1) && (ahead + 1) * TILE <= n) tma_prefetch_l2(keys_in + ahead * TILE, (unsigned)(TILE * sizeof(K)), keep);
+                if ((flags & 1) && i == 0 && (t + 1) * TILE <= n) tma_prefetch_l2(keys_in + t * TILE, (unsigned)(TILE * sizeof(K)), keep);
+            }
+            named_bar_sync(kBarWorkers, kWsWorkers);
+            return ring[i & 3u];
+        };
+        auto count = [&](unsigned p, unsigned t) {
+            const size_t base = (size_t)t * TILE + (size_t)w * SEG;
+            unsigned *row = tab + (p * kWsWorkerWarps + w) * ROW;
+            if ((size_t)t * TILE + TILE <= n) {
+                // any order inside the warp's segment: 128-bit loads, a window of WIN per lane in flight.  The lines are
+                // asked to STAY in L2 (evict_last): the scatter sweep reads them again one tile later.
+                const uint4 *src = reinterpret_cast<const uint4 *>(keys_in + base) + lane;
+                constexpr int NV = SEG / A / 32, WIN = 7;  // vectors per lane
+                static_assert(NV % WIN == 0, "whole windows");
+                uint4 v[WIN];
+#pragma unroll
+                for (int u = 0; u < WIN; u++) v[u] = ld_hint_v4(src + u * 32, keep);
+#pragma unroll
+                for (int j = 0; j < NV; j++) {
+                    const K *e = reinterpret_cast<const K *>(&v[j % WIN]);
+#pragma unroll
+                    for (int c = 0; c < A; c++) atomicAdd(&row[pass_digit<K, IDENT>(e[c], shift, tf)], 1u);
+                    if (j + WIN < NV) v[j % WIN] = ld_hint_v4(src + (j + WIN) * 32, keep);
+                }
+            } else {
+#pragma unroll 4
+                for (int i = 0; i < ITEMS; i++) {
+                    const size_t idx = base + (size_t)i * 32 + lane;
+                    // padding counts as digit 255: sorts last
+                    atomicAdd(&row[idx < n ? pass_digit<K, IDENT>(__ldg(keys_in + idx), shift, tf) : (unsigned)(kRadixSize - 1)], 1u);
+                }
+            }
+            named_bar_arrive(kBarCounted + p, kWsThreads);
+        };
+        auto scatter_tile = [&](unsigned p, unsigned t, bool first, auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
+            const size_t base = (size_t)t * TILE + (size_t)w * SEG + lane;
+            unsigned *row = tab + (p * kWsWorkerWarps + w) * ROW;
+            K cur[CHUNK], nxt[CHUNK];
+            auto load = [&](K (&dst)[CHUNK], int c) {
+#pragma unroll
+                for (int i = 0; i < CHUNK; i++) {
+                    const size_t idx = base + (size_t)(c * CHUNK + i) * 32;
+                    dst[i] = (FULL || idx < n) ? ld_hint(keys_in + idx, drop) : (K)0;  // last use: first in line for eviction
+                }
+            };
+            load(cur, 0);  // second read of the tile (the counting sweep was the first): flies during the waits below
+            WS_PROF_BEGIN();
+            named_bar_sync(kBarOffsets + p, kWsThreads);          // the tables hold the start of every (warp, digit) run
+            WS_PROF_END(2);
+            if (!first) named_bar_sync(kBarDrained, kWsThreads);  // the previous tile's bulk copies have read the buffer
+            WS_PROF_END(3);
+#pragma unroll 1
+            for (int c = 0; c < ITEMS / CHUNK; c++) {
+                if (c + 1 < ITEMS / CHUNK) load(nxt, c + 1);
+#pragma unroll
+                for (int i = 0; i < CHUNK; i++) {
+                    unsigned d = pass_digit<K, IDENT>(cur[i], shift, tf);
+                    if (!FULL && base + (size_t)(c * CHUNK + i) * 32 >= n) d = kRadixSize - 1;
+                    // same atomics, same order as count(): start of the run + rank.  (Issuing all atomics of the chunk
+                    // before the first store was measured 3 % slower: the LSU queue, not the latency, is the limit.)
+                    buf[atomicAdd(&row[d], 1u)] = cur[i];
+                }
+#pragma unroll
+                for (int i = 0; i < CHUNK; i++) cur[i] = nxt[i];
+            }
+            __syncwarp();
+            {  // the row is this warp's own: zero it for the warp's next tile
+                uint4 *z = reinterpret_cast<uint4 *>(row);
+                z[lane] = make_uint4(0, 0, 0, 0);
+                z[lane + 32] = make_uint4(0, 0, 0, 0);
+            }
+            fence_proxy_async();
+            named_bar_arrive(kBarScattered, kWsThreads);
+            WS_PROF_END(4);
+        };
+        auto scatter = [&](unsigned p, unsigned t, bool first) {
+            if ((size_t)t * TILE + TILE <= n) scatter_tile(p, t, first, std::true_type());
+            else scatter_tile(p, t, first, std::false_type());
+        };
+        unsigned t_cur = draw(0);
+        if (t_cur != kWsNoTile) count(0, t_cur);
+        else named_bar_arrive(kBarCounted + 0, kWsThreads);
+        for (unsigned i = 0; t_cur != kWsNoTile; ++i) {
+            WS_PROF_BEGIN();
+            const unsigned t_next = draw(i + 1);
+            WS_PROF_END(0);
+            if (t_next != kWsNoTile) count((i + 1) & 1u, t_next);
+            else named_bar_arrive(kBarCounted + ((i + 1) & 1u), kWsThreads);  // the helpers learn from the ring that it is void
+            WS_PROF_END(1);
+            scatter(i & 1u, t_cur, i == 0);
+            t_cur = t_next;
+        }
+        if (tid == 0) WS_PROF_DUMP(0);
+    } else {
+        // ======================= helpers: digit scan, look-back, bulk stores (one digit value per thread) =======================
+        const unsigned d = tid - kWsWorkers, lane = d & 31u, hw = d >> 5;
+        const unsigned gbase = __ldg(digit_base + d);
+        const unsigned long long drop = l2_policy_evict_first();  // written lines are not read again in this pass
+        const unsigned long long tag_p = (unsigned long long)((epoch << 2) | kLbPartial) << 32;
+        const unsigned long long tag_i = (unsigned long long)((epoch << 2) | kLbInclusive) << 32;
+        struct Run { unsigned g, s, c; };  // first index in keys_out, first index in the tile buffer, length
+        WS_PROF_DECL;
+        auto offsets = [&](unsigned p, unsigned t) -> Run {
+            WS_PROF_BEGIN();
+            unsigned *col = tab + p * kWsWorkerWarps * ROW + d;
+            unsigned short cw[kWsWorkerWarps];  // (a warp's segment has < 65536 keys)
+            unsigned count = 0;
+#pragma unroll
+            for (int w = 0; w < kWsWorkerWarps; w++) {
+                cw[w] = (unsigned short)col[w * ROW];
+                count += cw[w];
+            }
+            unsigned pub = count;  // without the padding of a partial tile (counted as digit 255)
+            const size_t tile_end = (size_t)t * TILE + TILE;
+            if (tile_end > n && d == kRadixSize - 1) pub -= (unsigned)(tile_end - n);
+            // exclusive scan over the 256 digit values -> start of each run in the digit-sorted tile
+            unsigned incl = count;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned o = __shfl_up_sync(0xffffffffu, incl, off);
+                if ((int)lane >= off) incl += o;
+            }
+            if (lane == 31) hscan[p * 8 + hw] = incl;
+            named_bar_sync(kBarHelpers, kWsHelpers);
+            unsigned add = 0;
+#pragma unroll
+            for (int j = 0; j < 7; j++) add += (j < (int)hw) ? hscan[p * 8 + j] : 0u;
+            const unsigned e = incl - count + add;
+
+            // publish the tile's digit count, then walk back over the earlier tiles (LB descriptors in flight per step)
+            unsigned long long *mine = lookback + (size_t)t * kRadixSize + d;
+            unsigned excl = 0;
+            WS_PROF_END(0);
+            if (t == 0) {
+                st_relaxed_u64(mine, tag_i | pub);
+            } else {
+                st_relaxed_u64(mine, tag_p | pub);
+                long long j = (long long)t - 1;
+                bool done = false;
+                while (!done) {
+                    unsigned long long v[LB];
+#pragma unroll
+                    for (int k = 0; k < LB; k++) {
+                        const long long idx = j - k;
+                        v[k] = idx >= 0 ? ld_relaxed_u64(lookback + (size_t)idx * kRadixSize + d) : tag_i;  // before tile 0: inclusive zero
+                    }
+                    int consumed = 0;
+#pragma unroll
+                    for (int k = 0; k < LB; k++) {
+                        if (!done && consumed == k) {
+                            const unsigned tag = (unsigned)(v[k] >> 32);
+                            if ((tag >> 2) == epoch) {  // published
+                                excl += (unsigned)v[k];
+                                consumed = k + 1;
+                                done = (tag & 3u) == kLbInclusive;
+                            }
+                        }
+                    }
+                    j -= consumed;
+                    if (consumed == 0) __nanosleep(40);
+                }
+                st_relaxed_u64(mine, tag_i | (unsigned)(excl + pub));
+            }
+            WS_PROF_END(1);
+            // shared-memory start of the run: after the runs before it, shifted to its destination's 16-byte phase
+            Run r;
+            r.g = gbase + excl;
+            const unsigned nat = e + (A - 1) * d;
+            r.s = nat + ((r.g - nat) & (A - 1));
+            r.c = pub;
+            unsigned run = r.s;
+#pragma unroll
+            for (int w = 0; w < kWsWorkerWarps; w++) {
+                col[w * ROW] = run;
+                run += cw[w];
+            }
+            named_bar_arrive(kBarOffsets + p, kWsThreads);
+            WS_PROF_END(2);
+            return r;
+        };
+        auto store = [&](const Run r, bool more) {
+            WS_PROF_BEGIN();
+            named_bar_sync(kBarScattered, kWsThreads);
+            WS_PROF_END(3);
+            // body: the 16-byte chunks that lie entirely inside the run, as one bulk copy
+            const unsigned m = r.g & (A - 1), end = m + r.c;  // the run covers keys [m, end) counted from the chunk-aligned base
+            const K *src0 = buf + (r.s - m);
+            K *dst0 = keys_out + ((size_t)r.g - m);
+            const unsigned first = (m + A - 1) / A, last = end / A;  // full chunks [first, last)
+            if (r.c && last > first) {
+                if (flags & 2) tma_store_issue(dst0 + first * A, src0 + first * A, (last - first) * 16u);
+                else tma_store_issue_hint(dst0 + first * A, src0 + first * A, (last - first) * 16u, drop);
+            }
+            WS_PROF_END(4);
+            tma_commit();
+            // edges: keys [m, min(first * A, end)) and [last * A, end), at most A - 1 each, by the LSU.  Lane = (run, slot):
+            // 32 / (2 * (A - 1)) runs per instruction, so a warp store touches a handful of sectors instead of 32 lines.
+            // (As byte-masked bulk copies -- cp.async.bulk .cp_mask, two more copies per run -- the pass was 7 % slower:
+            // issuing a bulk copy costs a warp 70-300 cycles.)
+            if constexpr (A > 1) {
+                constexpr int SLOTS = 2 * (A - 1), PER = 32 / SLOTS;  // 6 slots x 5 runs (u32), 2 slots x 16 runs (u64)
+                const unsigned sub = lane / SLOTS, slot = lane - sub * SLOTS;
+                for (unsigned r0 = 0; r0 < 32; r0 += PER) {
+                    const unsigned srcl = (r0 + sub) & 31u;
+                    const unsigned og = __shfl_sync(0xffffffffu, r.g, srcl), os = __shfl_sync(0xffffffffu, r.s, srcl),
+                                   oc = __shfl_sync(0xffffffffu, r.c, srcl);
+                    if (sub < (unsigned)PER && r0 + sub < 32 && oc) {
+                        const unsigned om = og & (A - 1), oend = om + oc;
+                        const unsigned ofirst = (om + A - 1) / A, olast = oend / A;
+                        unsigned k;  // position of this lane's key, counted from the chunk-aligned base
+                        bool on;
+                        if (slot < (unsigned)(A - 1)) {  // head: [om, min(ofirst * A, oend))
+                            k = om + slot;
+                            on = k < ofirst * A && k < oend;
+                        } else {                         // tail: [olast * A, oend), unless the run ends inside its first chunk
+                            k = olast * A + (slot - (A - 1));
+                            on = olast >= ofirst && k < oend;
+                        }
+                        if (on) keys_out[(size_t)og - om + k] = buf[os - om + k];
+                    }
+                }
+            }
+            WS_PROF_END(5);
+            tma_store_wait_read<0>();
+            if (more) named_bar_arrive(kBarDrained, kWsThreads);  // the buffer can be scattered into again
+            WS_PROF_END(6);
+        };
+        named_bar_sync(kBarCounted + 0, kWsThreads);
+        unsigned t_cur = ring[0];
+        Run r_cur{0, 0, 0};
+        if (t_cur != kWsNoTile) r_cur = offsets(0, t_cur);
+        for (unsigned i = 0; t_cur != kWsNoTile; ++i) {
+            WS_PROF_BEGIN();
+            named_bar_sync(kBarCounted + ((i + 1) & 1u), kWsThreads);
+            WS_PROF_END(7);
+            const unsigned t_next = ring[(i + 1) & 3u];
+            Run r_next{0, 0, 0};
+            if (t_next != kWsNoTile) r_next = offsets((i + 1) & 1u, t_next);
+            store(r_cur, t_next != kWsNoTile);
+            t_cur = t_next;
+            r_cur = r_next;
+        }
+        if (d == 0) WS_PROF_DUMP(8);
+    }
+}
+
+template <typename K, int IDENT>
+static int ws_launch_typed(StreamState *st, const void *kin, void *kout, const unsigned *base, unsigned long long *lookback, size_t n,
+                           int shift, const Transform &tf)
+{
+    typedef WsShape<K> C;
+    auto kernel = onesweep_ws<K, IDENT, 8>;
+    static std::atomic<unsigned long long> configured{0};  // bit per device: > 48 KB dynamic shared memory opted in
+    const unsigned long long bit = st->device < 64 ? (1ull << st->device) : 0ull;
+    if (!(configured.load(std::memory_order_acquire) & bit) || !bit) {
+        BCB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+        configured.fetch_or(bit, std::memory_order_release);
+    }
+    const size_t tiles = (n + C::TILE - 1) / C::TILE;
+    size_t grid = (size_t)st->sm_count;
+    if (grid > tiles) grid = tiles;
+    unsigned epoch;
+    BCB_TRY(next_epoch(st, kArenaPacked, &epoch));
+    const unsigned long long ticket_base = ticket_reserve(st, tiles + grid);  // every CTA draws one void ticket
+    static const int ws_flags = [] { const char *e = std::getenv("BCB_WS_FLAGS"); return e ? std::atoi(e) : 0; }();  // experiments
+    LaunchTimer timer(st, BCB_K_ONESWEEP_PASS);
+    kernel<<<(unsigned)grid, kWsThreads, C::SMEM_BYTES, st->stream>>>((const K *)kin, (K *)kout, base, lookback, epoch, n, (unsigned)tiles,
+                                                                      shift, tf, st->control + kControlTicket, ticket_base, ws_flags);
+    BCB_CUDA_TRY(cudaGetLastError());
+#ifdef BCB_WS_PROFILE
+    {
+        static unsigned long long host[148 * 16 * 4];
+        cudaStreamSynchronize(st->stream);
+        cudaMemcpyFromSymbol(host, g_ws_prof, sizeof(unsigned long long) * grid * 16);
+        double avg[16] = {};
+        for (size_t b = 0; b < grid; b++) for (int q = 0; q < 16; q++) avg[q] += (double)host[b * 16 + q] / grid;
+        const double per = (double)grid / tiles;  // -> cycles per tile
+        fprintf(stderr, "[ws prof] cycles/tile  workers: draw %.0f count %.0f waitOffsets %.0f waitDrained %.0f scatter %.0f | "
+                        "helpers: waitCounted %.0f sums+scan %.0f lookback %.0f offsets %.0f waitScattered %.0f issue %.0f edges %.0f drain %.0f\n",
+                avg[0] * per, avg[1] * per, avg[2] * per, avg[3] * per, avg[4] * per,
+                avg[15] * per, avg[8] * per, avg[9] * per, avg[10] * per, avg[11] * per, avg[12] * per, avg[13] * per, avg[14] * per);
+    }
+#endif
+    return BCB_SUCCESS;
+}
+
+size_t ws_tile_size(int key_bytes) { return key_bytes == 8 ? (size_t)WsShape<unsigned long long>::TILE : (size_t)WsShape<unsigned>::TILE; }
+
+int ws_launch_pass(StreamState *st, int key_bytes, const void *kin, void *kout, const unsigned *base, unsigned long long *lookback,
+                   size_t n, int shift, const Transform &tf)
+{
+    if ((((uintptr_t)kin | (uintptr_t)kout) & 15) != 0) return BCB_EUNSUPPORTED;  // bulk copies need 16-byte aligned arrays
+    const bool ident = (tf.nm | tf.xc | tf.fa) == 0;
+    if (key_bytes == 4)
+        return ident ? ws_launch_typed<unsigned, kDigitIdent>(st, kin, kout, base, lookback, n, shift, tf)
+                     : ws_launch_typed<unsigned, kDigitTransform>(st, kin, kout, base, lookback, n, shift, tf);
+    if (key_bytes == 8)
+        return ident ? ws_launch_typed<unsigned long long, kDigitIdent>(st, kin, kout, base, lookback, n, shift, tf)
+                     : ws_launch_typed<unsigned long long, kDigitTransform>(st, kin, kout, base, lookback, n, shift, tf);
+    return BCB_EUNSUPPORTED;
+}
+
+}  // namespace bcb

@@ -23,6 +23,7 @@
 // 2^32-1 fit.
 #include "radix_common.cuh"
 
+#include <atomic>
 #include <cstdlib>
 #include <type_traits>
 #include <cstring>
@@ -32,8 +33,9 @@ namespace bcb {
 // ---- 1. histogram of all digit positions in one read ------------------------------------------
 template <typename K>
 __global__ void __launch_bounds__(kHistThreads)
-radix_histogram(const K *__restrict__ keys, size_t n, unsigned *__restrict__ hist, Transform tf)
+radix_histogram(const K *__restrict__ keys, size_t n, unsigned *__restrict__ hist, Transform tf, const int *__restrict__ gate)
 {
+    if (gate && *gate == 0) return;  // fallback launch of a speculative sort whose verification passed
     constexpr int NPASS = sizeof(K);
     constexpr int VEC = 16 / sizeof(K);
     __shared__ unsigned sh[NPASS][kRadixSize];
@@ -85,8 +87,9 @@ radix_histogram(const K *__restrict__ keys, size_t n, unsigned *__restrict__ his
 // (128 KB for 32- and 64-bit keys); the columns are summed when the CTA flushes.
 template <typename K, int COLS, bool IDENT>
 __global__ void __launch_bounds__(1024, 1)
-radix_histogram_columns(const K *__restrict__ keys, size_t n, unsigned *__restrict__ hist, Transform tf)
+radix_histogram_columns(const K *__restrict__ keys, size_t n, unsigned *__restrict__ hist, Transform tf, const int *__restrict__ gate)
 {
+    if (gate && *gate == 0) return;
     constexpr int NPASS = sizeof(K);
     constexpr int VEC = 16 / sizeof(K);
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -140,8 +143,11 @@ radix_histogram_columns(const K *__restrict__ keys, size_t n, unsigned *__restri
 }
 
 // ---- 2. exclusive scan of each digit histogram: hist[p][d] -> base[p][d] -------------------------
-__global__ void __launch_bounds__(kRadixSize) digit_scan(const unsigned *__restrict__ hist, unsigned *__restrict__ base)
+__global__ void __launch_bounds__(kRadixSize) digit_scan(const unsigned *__restrict__ hist, unsigned *__restrict__ base,
+                                                         const int *__restrict__ gate = nullptr, unsigned long long *fallbacks = nullptr)
 {
+    if (gate && *gate == 0) return;
+    if (fallbacks && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(fallbacks, 1ull);  // a gated launch that runs IS a fallback
     __shared__ unsigned wsum[kRadixSize / 32];
     const unsigned d = threadIdx.x, lane = d & 31u, warp = d >> 5;
     const unsigned c = hist[blockIdx.x * kRadixSize + d];
@@ -167,19 +173,16 @@ __global__ void __launch_bounds__(kRadixSize) digit_scan(const unsigned *__restr
 //                     after a warp barrier the entry holds the full peer mask (order independent), the rank inside
 //                     the round is popc(mask & lanes below), the highest peer clears the mask and bumps the count.
 //                     Deterministic by construction: 3 shared-memory instructions per key.
-//   kRankOrderedAtoms (BCB_SORT_RANK=ordered): rank = atomicAdd(count, 1).  One instruction per key, but stable only
-//                     if same-address atomics of one warp instruction are applied in lane order, which CUDA does
-//                     not promise -- usable only where the result is verified (keys-only sorts, below).
-//                     Superseded by kRankTwoSweep.
 //   kRankBallot       splitter mode only (at most 8 buckets + padding): the peer mask of a key comes from three
 //                     ballots over the bits of its bucket, the running count of bucket b lives in a register of lane
 //                     b.  No shared memory, no atomics (same-address atomics of 2..8 buckets would serialise).
-//   kRankTwoSweep     the ordered-atomics idea without the rank registers: sweep 1 only counts (atomicAdd, result
-//                     unused), the tables turn into offsets, sweep 2 repeats the same atomicAdds in the same order
-//                     and takes the returned value as the key's position.  Same assumption, same verification;
-//                     the freed registers allow larger tiles.  Keys only.
-enum { kRankAtomicOr = 0, kRankOrderedAtoms = 1, kRankBallot = 2, kRankTwoSweep = 3 };
-static inline bool rank_is_speculative(int rank) { return rank == kRankOrderedAtoms || rank == kRankTwoSweep; }
+//   kRankTwoSweep     sweep 1 only counts (atomicAdd, result unused), the tables turn into offsets, sweep 2 repeats
+//                     the same atomicAdds in the same order and takes the returned value as the key's position.  One
+//                     instruction per key and sweep and no rank registers, but stable only if same-address atomics of
+//                     one warp instruction are applied in lane order, which CUDA does not promise -- usable only where
+//                     the result is verified (keys-only sorts, below).  Keys only.
+enum { kRankAtomicOr = 0, kRankBallot = 2, kRankTwoSweep = 3 };
+static inline bool rank_is_speculative(int rank) { return rank == kRankTwoSweep; }
 
 template <int VB> struct value_type;
 template <> struct value_type<0> { typedef unsigned char type; };
@@ -235,18 +238,18 @@ __device__ __forceinline__ void
 pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *__restrict__ vals_in_v,
           void *__restrict__ vals_out_v, const unsigned *__restrict__ digit_base, unsigned long long *lookback,
           unsigned epoch, size_t n, int shift, const Transform &tf, size_t tile, unsigned char *smem_raw,
-          K (&key)[ITEMS], size_t num_tiles)
+          K (&key)[ITEMS], size_t num_tiles, volatile unsigned *next_tile)
 {
     typedef PassSmem<K, VB, THREADS, ITEMS, RANK> L;
     typedef typename value_type<VB>::type V;
     constexpr int WARPS = L::WARPS, TILE = L::TILE;
 
     unsigned *out_base = reinterpret_cast<unsigned *>(smem_raw + L::kWarpTab);
-    unsigned *misc = out_base + kRadixSize;  // [0..1] tile id, [2..9] warp sums of the digit scan
+    unsigned *misc = out_base + kRadixSize;  // [0..1] tile ids (onesweep_pass), [2..9] warp sums of the digit scan
     unsigned char *elem_buf = smem_raw + L::kWarpTab + L::kSmall;
     K *keys_sorted = reinterpret_cast<K *>(elem_buf);
     // digit table of each 16-lane virtual warp.  kRankAtomicOr packs {count : 16 | peer mask : 16} into one word
-    // (a 32-bit entry keeps every access a single-wavefront-per-bank operation); kRankOrderedAtoms stores the count.
+    // (a 32-bit entry keeps every access a single-wavefront-per-bank operation); the other modes store the count.
     unsigned *tab = reinterpret_cast<unsigned *>(smem_raw);  // [VWARPS][256]
     constexpr int CSHIFT = (RANK == kRankAtomicOr) ? 16 : 0;
     constexpr int VWARPS = L::VWARPS, VWL = L::VWL;
@@ -326,13 +329,6 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
             if (!FULL && off0 + i * VWL >= valid) d = kRadixSize - 1;
             atomicAdd(&wt[d], 1u);  // count only; the position comes from the second sweep
         }
-    } else {
-#pragma unroll
-        for (int i = 0; i < ITEMS; i++) {
-            unsigned d = pass_digit<K, IDENT>(key[i], shift, tf);
-            if (!FULL && off0 + i * VWL >= valid) d = kRadixSize - 1;
-            rank[i] = (unsigned short)atomicAdd(&wt[d], 1u);
-        }
     }
     __syncthreads();
 
@@ -390,7 +386,7 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
     // ---- prefetch the next tile's keys into the (now dead) key registers: the loads fly during the look-back and
     // the store phase of this tile, so a tile never waits for its own input ----
     {
-        const size_t next = tile + gridDim.x;  // round-robin tile assignment (see onesweep_pass)
+        const size_t next = *next_tile;  // drawn by thread 0 at the top of this tile (see onesweep_pass)
         if (next < num_tiles) load_tile_keys<K, THREADS, ITEMS, PassSmem<K, VB, THREADS, ITEMS, RANK>::VWL>(keys_in, n, next, key);
     }
 
@@ -526,40 +522,58 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
     }
 }
 
+// Tile ids come from a ticket (atomic counter), drawn one tile ahead so that the next tile's keys can be prefetched:
+// a tile's predecessors were all drawn earlier, by CTAs that are running, so the look-back never waits for a CTA that
+// has not been scheduled -- forward progress does not depend on the whole grid being resident (other streams may hold
+// SMs).  `gate`: fallback launches of a speculative sort run only if the verification flag is set.
+__device__ __forceinline__ unsigned draw_tile(unsigned long long *ticket, unsigned long long ticket_base, size_t num_tiles)
+{
+    const unsigned long long t = atomicAdd(ticket, 1ull) - ticket_base;
+    return t < num_tiles ? (unsigned)t : 0xffffffffu;
+}
+
 template <typename K, int VB, int THREADS, int ITEMS, int LBATCH, int RANK, int IDENT, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 onesweep_pass(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *__restrict__ vals_in_v,
               void *__restrict__ vals_out_v, const unsigned *__restrict__ digit_base, unsigned long long *lookback,
-              unsigned epoch, size_t n, size_t num_tiles, int shift,
-              const __grid_constant__ Transform tf)
+              unsigned epoch, size_t n, size_t num_tiles, int shift, unsigned long long *ticket, unsigned long long ticket_base,
+              const int *__restrict__ gate, const __grid_constant__ Transform tf)
 {
-    // Persistent CTAs: the grid is sized to the number of resident CTAs and tiles are dealt round-robin (CTA b takes
-    // tiles b, b + G, b + 2G ...).  All CTAs are co-resident, so every tile a look-back can wait for is being worked
-    // on, the tiles in flight form one contiguous window of the input (their scattered writes merge in L2), and the
-    // next tile's keys are fetched while the current tile is still being processed.
+    // Persistent CTAs: the grid is sized to the number of CTAs that fit the device; the tiles in flight form one
+    // contiguous window of the input (their scattered writes merge in L2), and the next tile's keys are fetched while
+    // the current tile is still being processed.
     typedef PassSmem<K, VB, THREADS, ITEMS, RANK> L;
     static_assert(THREADS >= kRadixSize && THREADS % 32 == 0, "one look-back thread per digit value");
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    volatile unsigned *slot = reinterpret_cast<unsigned *>(smem_raw + L::kWarpTab) + kRadixSize;  // misc[0..1]: tile ids
 
-    size_t tile = blockIdx.x;
-    K key[ITEMS];
-    if (tile < num_tiles) load_tile_keys<K, THREADS, ITEMS, L::VWL>(keys_in, n, tile, key);
+    if (gate && *gate == 0) {  // not needed: keep the ticket counter in step with the host's reservation and leave
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(ticket, (unsigned long long)num_tiles + gridDim.x);
+        return;
+    }
+    if (threadIdx.x == 0) slot[0] = draw_tile(ticket, ticket_base, num_tiles);
     // the digit tables start out zero; every tile zeroes them again once it is done with them (during its write phase)
     {
         uint4 *z = reinterpret_cast<uint4 *>(smem_raw);
         for (unsigned i = threadIdx.x; i < L::kWarpTab / 16; i += THREADS) z[i] = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
-    for (; tile < num_tiles; tile += gridDim.x) {
+    size_t tile = slot[0];
+    K key[ITEMS];
+    if (tile < num_tiles) load_tile_keys<K, THREADS, ITEMS, L::VWL>(keys_in, n, tile, key);
+    for (unsigned it = 0; tile < num_tiles; ++it) {
+        volatile unsigned *next = slot + ((it + 1) & 1u);
+        if (threadIdx.x == 0) *next = draw_tile(ticket, ticket_base, num_tiles);  // read after the tile's first barrier
         if ((tile + 1) * (size_t)L::TILE <= n)
             pass_tile<K, VB, THREADS, ITEMS, LBATCH, RANK, IDENT, true>(keys_in, keys_out, vals_in_v, vals_out_v, digit_base, lookback,
                                                                          epoch, n, shift, tf, tile, smem_raw, key,
-                                                                         num_tiles);
+                                                                         num_tiles, next);
         else
             pass_tile<K, VB, THREADS, ITEMS, LBATCH, RANK, IDENT, false>(keys_in, keys_out, vals_in_v, vals_out_v, digit_base, lookback,
                                                                           epoch, n, shift, tf, tile, smem_raw, key,
-                                                                          num_tiles);
+                                                                          num_tiles, next);
         __syncthreads();  // all stores of this tile issued, shared memory free for the next one
+        tile = *next;
     }
 }
 
@@ -603,62 +617,73 @@ __global__ void insertion_sort_kernel(T *keys, size_t n, int greater, unsigned c
 // ---- launch plumbing -----------------------------------------------------------------------------------
 constexpr int default_min_blocks(int threads) { return threads <= 256 ? 3 : (threads <= 512 ? 2 : 1); }
 
+// per (kernel instantiation, device) launch facts, computed once; safe to race (all writers store the same values)
+struct PassLaunchCache {
+    std::atomic<int> per_sm[64];
+    PassLaunchCache() { for (auto &v : per_sm) v.store(0, std::memory_order_relaxed); }
+};
+
 template <typename K, int VB, int THREADS, int ITEMS, int LBATCH, int RANK, int IDENT, int MINB = default_min_blocks(THREADS)>
 static int launch_pass_impl(StreamState *st, const void *kin, void *kout, const void *vin, void *vout, const unsigned *base,
-                       unsigned long long *lookback, size_t n, int shift, const Transform &tf)
+                            unsigned long long *lookback, size_t n, int shift, const Transform &tf, const int *gate = nullptr)
 {
     typedef PassSmem<K, VB, THREADS, ITEMS, RANK> L;
     static_assert((IDENT == kDigitSplit) == (RANK == kRankBallot), "the splitter pass and the ballot ranking go together");
     constexpr size_t kSmemBytes = L::kBytes;
-    static bool configured[64] = {};  // per instantiation and device: opt in to > 48 KB dynamic shared memory once
     auto kernel = onesweep_pass<K, VB, THREADS, ITEMS, LBATCH, RANK, IDENT, MINB>;
-    if (st->device >= 64 || !configured[st->device]) {
-        BCB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        if (st->device < 64) configured[st->device] = true;
-    }
-    const size_t tiles = (n + L::TILE - 1) / L::TILE;
-    static int resident[64] = {};  // CTAs of this kernel that fit one SM
-    int per_sm = (st->device < 64) ? resident[st->device] : 0;
+    static PassLaunchCache cache;  // CTAs of this kernel that fit one SM (0 = not configured yet on that device)
+    int per_sm = st->device < 64 ? cache.per_sm[st->device].load(std::memory_order_acquire) : 0;
     if (per_sm == 0) {
+        BCB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
         BCB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, kSmemBytes));
         if (per_sm < 1) per_sm = 1;
-        if (st->device < 64) resident[st->device] = per_sm;
+        if (st->device < 64) cache.per_sm[st->device].store(per_sm, std::memory_order_release);
     }
+    const size_t tiles = (n + L::TILE - 1) / L::TILE;
     size_t grid = (size_t)st->sm_count * (size_t)per_sm;
     if (grid > tiles) grid = tiles;
     unsigned epoch;
-    BCB_TRY(next_epoch(st, &epoch));
-    LaunchTimer timer(st, BCB_K_ONESWEEP_PASS);
-    kernel<<<(unsigned)grid, THREADS, kSmemBytes, st->stream>>>((const K *)kin, (K *)kout, vin, vout, base, lookback, epoch,
-                                                               n, tiles, shift, tf);
+    BCB_TRY(next_epoch(st, kArenaPacked, &epoch));
+    const unsigned long long ticket_base = ticket_reserve(st, tiles + grid);  // every CTA draws one void ticket
+    LaunchTimer timer(st, IDENT == kDigitSplit ? BCB_K_EXCHANGE_PASS : BCB_K_ONESWEEP_PASS);
+    kernel<<<(unsigned)grid, THREADS, kSmemBytes, st->stream>>>((const K *)kin, (K *)kout, vin, vout, base, lookback, epoch, n, tiles,
+                                                               shift, st->control + kControlTicket, ticket_base, gate, tf);
     BCB_CUDA_TRY(cudaGetLastError());
     return BCB_SUCCESS;
 }
 
 // Speculative ranking for large keys-only sorts (32- and 64-bit keys).
-// The ordered-atomics pass kernel is ~25 % faster than the atomic-OR one but stable only if same-address shared
-// atomics of one warp instruction are applied in lane order (true on every B200 measured, not promised by CUDA).  For a
-// KEYS-ONLY sort that assumption can be CHECKED after the fact: every pass is a permutation whatever order the atomics
-// took, so the output is the correct result if and only if it is sorted by the transformed key.  sort_typed therefore
-// runs the fast passes, verifies sortedness in one extra read (4 B/key), and in the (never observed) failure case
-// simply sorts the buffer again with the deterministic kernel -- re-sorting a permutation of the input gives the same
-// bytes.  Key-value sorts never speculate (stability of the payload cannot be verified from the keys), and neither do
-// descending float sorts (their key transform is not injective, see sort_typed).  The shipped speculative kernel is
-// kRankTwoSweep (same assumption, no rank registers, 12288-key tiles): 2^30 u32 keys in 11.0 ms of passes against
-// 14.1 ms (ordered atomics, 7680-key tiles) and 18.6 ms (deterministic atomic-OR).
+// The two-sweep pass kernels (kRankTwoSweep here, onesweep_ws in radix_pass_ws.cu) are much faster than the atomic-OR
+// one but stable only if same-address shared atomics of one warp instruction are applied in lane order (true on every
+// B200 measured, not promised by CUDA).  For a KEYS-ONLY sort that assumption can be CHECKED after the fact: every pass
+// is a permutation whatever order the atomics took, so the output is the correct result if and only if it is sorted by
+// the transformed key.  sort_typed therefore runs the fast passes, verifies sortedness in one extra read (4 B/key)
+// into a DEVICE flag, and enqueues the deterministic sort of the same buffer behind it with every kernel gated on
+// that flag (the launches return at once when the flag is clear) -- re-sorting a permutation of the input gives the
+// same bytes.  Nothing waits on the host: the sort stays enqueue-and-return.  Key-value sorts never speculate
+// (stability of the payload cannot be verified from the keys), and neither do descending float sorts (their key
+// transform is not injective, see sort_typed).
 //   BCB_SORT_SPECULATIVE=0       always use the deterministic atomic-OR kernel
 //   BCB_SORT_FORCE_FALLBACK=1    test hook: treat every verification as failed
-constexpr size_t kSpeculativeMinKeys = (size_t)1 << 22;  // below this the sort stays fully asynchronous
-static int g_speculative = -1, g_force_fallback = -1;
-static bool speculative_enabled()
-{
-    if (g_speculative < 0) {
+//   BCB_SORT_WS=0                keep the r01 two-sweep kernel for large sorts (A/B comparison)
+constexpr size_t kSpeculativeMinKeys = (size_t)1 << 20;
+constexpr size_t kWsMinKeys = (size_t)1 << 23;  // below this too few tiles per SM for the warp-specialised pipeline
+struct SortEnv {
+    bool speculative, force_fallback, ws;
+    SortEnv()
+    {
         const char *e = std::getenv("BCB_SORT_SPECULATIVE");
-        g_speculative = (e && e[0] == '0') ? 0 : 1;
-        const char *f = std::getenv("BCB_SORT_FORCE_FALLBACK");
-        g_force_fallback = (f && f[0] == '1') ? 1 : 0;
+        speculative = !(e && e[0] == '0');
+        e = std::getenv("BCB_SORT_FORCE_FALLBACK");
+        force_fallback = e && e[0] == '1';
+        e = std::getenv("BCB_SORT_WS");
+        ws = !(e && e[0] == '0');
     }
-    return g_speculative == 1;
+};
+static const SortEnv &sort_env()
+{
+    static const SortEnv env;  // thread-safe initialisation (C++11)
+    return env;
 }
 
 // sortedness by the transformed key (the order the sort is defined by), 128-bit loads
@@ -675,7 +700,7 @@ __device__ __forceinline__ typename key_traits<K>::U verify_key(K raw, const Tra
 // lane by shuffle (lane 31: from lane 0 of the next group), only the seam after the warp's last vector touches memory again
 constexpr int kVerifyUnroll = 4;
 template <typename K, bool IDENT>
-__global__ void __launch_bounds__(256) verify_sorted_kernel(const K *__restrict__ keys, size_t n, Transform tf, int *flag)
+__global__ void __launch_bounds__(256) verify_sorted_kernel(const K *__restrict__ keys, size_t n, Transform tf, int *flag, int force)
 {
     typedef typename key_traits<K>::U U;
     constexpr int VEC = 16 / sizeof(K);
@@ -726,22 +751,16 @@ __global__ void __launch_bounds__(256) verify_sorted_kernel(const K *__restrict_
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (done ? done - 1 : 0) + gid; i + 1 < n; i += stride)  // scalar tail, including the seam into it
         bad |= verify_key<K, IDENT>(__ldg(keys + i), tf) > verify_key<K, IDENT>(__ldg(keys + i + 1), tf);
-    if (bad) *flag = 1;
+    if (bad || force) *flag = 1;
 }
 
 template <typename K, int VB, int THREADS, int ITEMS, int LBATCH = kLookbackBatch, int MINB = default_min_blocks(THREADS)>
 static int launch_pass(StreamState *st, const void *kin, void *kout, const void *vin, void *vout, const unsigned *base,
-                       unsigned long long *lookback, size_t n, int shift, const Transform &tf, int rank)
+                       unsigned long long *lookback, size_t n, int shift, const Transform &tf, const int *gate)
 {
     const bool ident = (tf.nm | tf.xc | tf.fa) == 0;  // unsigned ascending keys: the digit is a plain bit field
-    if constexpr ((sizeof(K) == 4 || sizeof(K) == 8) && VB == 0) {
-        if (rank == kRankOrderedAtoms) {
-            return ident ? launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankOrderedAtoms, kDigitIdent, MINB>(st, kin, kout, vin, vout, base, lookback, n, shift, tf)
-                         : launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankOrderedAtoms, kDigitTransform, MINB>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
-        }
-    }
-    return ident ? launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankAtomicOr, kDigitIdent, MINB>(st, kin, kout, vin, vout, base, lookback, n, shift, tf)
-                 : launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankAtomicOr, kDigitTransform, MINB>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
+    return ident ? launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankAtomicOr, kDigitIdent, MINB>(st, kin, kout, vin, vout, base, lookback, n, shift, tf, gate)
+                 : launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankAtomicOr, kDigitTransform, MINB>(st, kin, kout, vin, vout, base, lookback, n, shift, tf, gate);
 }
 
 // the speculative two-sweep pass (keys only, 32- and 64-bit keys)
@@ -771,75 +790,30 @@ template <typename K> struct SpecConfig { static constexpr int THREADS = 384, IT
 // (2^28 u64 keys, 8 passes: 384x12 10.9 ms, 384x16 9.2 ms, 384x20 8.7 ms, 384x24 8.7 ms)
 template <> struct SpecConfig<unsigned long long> { static constexpr int THREADS = 384, ITEMS = 20, LB = 4, MINB = 2; };
 
-// BCB_SORT_KERNEL=ns selects the experimental nibble-split pass kernel (radix_sort_ns.cu) for 32/64-bit keys-only
-// sorts.  It is bit-exact but measured SLOWER on B200 (34 vs 53 Gkeys/s: 147 instructions per key make it ALU bound,
-// profiles/r01_sort_pass_ns_nibble_split.txt), so the atomic-OR kernel stays the default.
-static int g_sort_kernel = -1;
-static bool want_ns_kernel()
-{
-    if (g_sort_kernel < 0) {
-        const char *e = std::getenv("BCB_SORT_KERNEL");
-        g_sort_kernel = (e && std::strcmp(e, "ns") == 0) ? 1 : 0;
-    }
-    return g_sort_kernel == 1;
-}
-
-static int g_sort_variant = -1;  // BCB_SORT_VARIANT: tuning variants of the two-sweep pass (experiments)
-static int sort_variant()
-{
-    if (g_sort_variant < 0) {
-        const char *e = std::getenv("BCB_SORT_VARIANT");
-        g_sort_variant = e ? std::atoi(e) : 0;
-    }
-    return g_sort_variant;
-}
-
-// {id, threads, items, look-back batch, min CTAs per SM}
-#define BCB_SPEC_VARIANTS_32(X) X(1, 384, 24, 4, 2) X(3, 512, 24, 4, 2) X(5, 384, 32, 2, 2)
-#define BCB_SPEC_VARIANTS_64(X) X(1, 384, 16, 4, 2) X(3, 384, 24, 4, 2) X(5, 256, 24, 4, 3)
+enum { kPassDeterministic = 0, kPassTwoSweep = 1, kPassWs = 2 };  // which pass kernel a sort uses
 
 template <typename K, int VB>
-static int tile_size_for(int rank)
+static size_t tile_size_for(int pass_kind)
 {
     if constexpr (VB == 0 && (sizeof(K) == 4 || sizeof(K) == 8)) {
-        if (want_ns_kernel() && rank == kRankAtomicOr) return (int)ns_tile_size();
-        if (rank == kRankTwoSweep) {
-#define X(ID, T, I, LBV, MB) case ID: return T * I;
-            if constexpr (sizeof(K) == 4) {
-                switch (sort_variant()) { BCB_SPEC_VARIANTS_32(X) default: break; }
-            } else {
-                switch (sort_variant()) { BCB_SPEC_VARIANTS_64(X) default: break; }
-            }
-#undef X
-            return SpecConfig<K>::THREADS * SpecConfig<K>::ITEMS;
-        }
+        if (pass_kind == kPassWs) return ws_tile_size((int)sizeof(K));
+        if (pass_kind == kPassTwoSweep) return (size_t)SpecConfig<K>::THREADS * SpecConfig<K>::ITEMS;
     }
-    return PassConfig<K, VB>::THREADS * PassConfig<K, VB>::ITEMS;
+    return (size_t)PassConfig<K, VB>::THREADS * PassConfig<K, VB>::ITEMS;
 }
 
 template <typename K, int VB>
 static int run_pass(StreamState *st, const void *kin, void *kout, const void *vin, void *vout, const unsigned *base,
-                    unsigned long long *lookback, size_t n, int shift, const Transform &tf, int rank)
+                    unsigned long long *lookback, size_t n, int shift, const Transform &tf, int pass_kind, const int *gate)
 {
     if constexpr (VB == 0 && (sizeof(K) == 4 || sizeof(K) == 8)) {
-        if (want_ns_kernel() && rank == kRankAtomicOr) {
-            const bool ident = (tf.nm | tf.xc | tf.fa) == 0;
-            return ns_launch_pass(st, (int)sizeof(K), kin, kout, base, lookback, n, shift, tf, ident ? kDigitIdent : kDigitTransform);
-        }
-        if (rank == kRankTwoSweep) {
-#define X(ID, T, I, LBV, MB) case ID: return launch_two_sweep<K, T, I, LBV, MB>(st, kin, kout, base, lookback, n, shift, tf);
-            if constexpr (sizeof(K) == 4) {
-                switch (sort_variant()) { BCB_SPEC_VARIANTS_32(X) default: break; }
-            } else {
-                switch (sort_variant()) { BCB_SPEC_VARIANTS_64(X) default: break; }
-            }
-#undef X
+        if (pass_kind == kPassWs) return ws_launch_pass(st, (int)sizeof(K), kin, kout, base, lookback, n, shift, tf);
+        if (pass_kind == kPassTwoSweep)
             return launch_two_sweep<K, SpecConfig<K>::THREADS, SpecConfig<K>::ITEMS, SpecConfig<K>::LB, SpecConfig<K>::MINB>(
                 st, kin, kout, base, lookback, n, shift, tf);
-        }
     }
     return launch_pass<K, VB, PassConfig<K, VB>::THREADS, PassConfig<K, VB>::ITEMS>(st, kin, kout, vin, vout, base, lookback, n,
-                                                                                     shift, tf, rank);
+                                                                                     shift, tf, gate);
 }
 
 // ---- multi-GPU partition pass: bucket histogram by splitters ---------------------------------------------
@@ -940,7 +914,7 @@ static int partition_scatter_shape(StreamState *st, const void *kin, const void 
     const size_t tile = (size_t)THREADS * ITEMS;
     const size_t tiles = (n + tile - 1) / tile;
     void *lb;
-    BCB_TRY(lookback_reserve(st, tiles * kRadixSize * sizeof(unsigned long long), &lb));
+    BCB_TRY(lookback_reserve(st, kArenaPacked, tiles * kRadixSize * sizeof(unsigned long long), &lb));
     return launch_pass_impl<K, VB, THREADS, ITEMS, 4, kRankBallot, kDigitSplit, MINB>(st, kin, nullptr, vin, nullptr, base,
                                                                                                   (unsigned long long *)lb, n, 0, tf);
 }
@@ -948,17 +922,6 @@ static int partition_scatter_shape(StreamState *st, const void *kin, const void 
 template <typename K, int VB>
 static int partition_scatter_typed(StreamState *st, const void *kin, const void *vin, size_t n, const Transform &tf, const unsigned *base)
 {
-    if constexpr (sizeof(K) == 4 && VB == 0) {  // BCB_SPLIT_VARIANT: tile shapes of the exchange pass (experiments)
-        static int variant = -1;
-        if (variant < 0) { const char *e = std::getenv("BCB_SPLIT_VARIANT"); variant = e ? std::atoi(e) : 0; }
-        switch (variant) {
-        case 1: return partition_scatter_shape<K, VB, 256, 20, 3>(st, kin, vin, n, tf, base);
-        case 2: return partition_scatter_shape<K, VB, 256, 16, 4>(st, kin, vin, n, tf, base);
-        case 3: return partition_scatter_shape<K, VB, 384, 28, 2>(st, kin, vin, n, tf, base);
-        case 4: return partition_scatter_shape<K, VB, 512, 16, 2>(st, kin, vin, n, tf, base);
-        default: break;
-        }
-    }
     return partition_scatter_shape<K, VB, PassConfig<K, VB>::THREADS, PassConfig<K, VB>::ITEMS, default_min_blocks(PassConfig<K, VB>::THREADS)>(
         st, kin, vin, n, tf, base);
 }
@@ -977,45 +940,32 @@ static int partition_scatter_by_value_size(StreamState *st, const void *kin, con
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// sets *flag to 1 if the range is not sorted by the transformed key (or if `force`); the caller clears it first
 template <typename K>
-static int run_verify(StreamState *st, const void *keys, size_t n, const Transform &tf, int *flag)
+static int run_verify(StreamState *st, const void *keys, size_t n, const Transform &tf, int *flag, int force = 0)
 {
     size_t blocks = (n + 256 * 16 - 1) / (256 * 16);
     const size_t cap = (size_t)st->sm_count * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     if ((tf.nm | tf.xc | tf.fa) == 0)
-        verify_sorted_kernel<K, true><<<(unsigned)blocks, 256, 0, st->stream>>>((const K *)keys, n, tf, flag);
+        verify_sorted_kernel<K, true><<<(unsigned)blocks, 256, 0, st->stream>>>((const K *)keys, n, tf, flag, force);
     else
-        verify_sorted_kernel<K, false><<<(unsigned)blocks, 256, 0, st->stream>>>((const K *)keys, n, tf, flag);
+        verify_sorted_kernel<K, false><<<(unsigned)blocks, 256, 0, st->stream>>>((const K *)keys, n, tf, flag, force);
     BCB_CUDA_TRY(cudaGetLastError());
     return BCB_SUCCESS;
 }
 
+// device words of the per-stream control block used by the speculative sort
+static int *spec_flag(StreamState *st) { return reinterpret_cast<int *>(st->control + kControlSpecFlag); }
+static unsigned long long *spec_fallback_counter(StreamState *st) { return st->control + kControlSpecFallbacks; }
+
+// histogram of every digit position + per-digit exclusive scan, then one pass per digit
 template <typename K, int VB>
-static int sort_typed(StreamState *st, void *keys, void *values, size_t n, const Transform &tf, const void *src_keys = nullptr,
-                      const void *src_vals = nullptr, int rank = -1)
+static int sort_passes(StreamState *st, void *keys, void *values, size_t n, const Transform &tf, const void *src_keys,
+                       const void *src_vals, int pass_kind, const int *gate)
 {
-    // src_keys / src_vals: read the input from there instead (sorted copy; the source is left untouched)
-    if (!src_keys) { src_keys = keys; src_vals = values; }
     constexpr int NPASS = sizeof(K);
-    if (rank < 0) {
-        rank = kRankAtomicOr;
-        if constexpr (VB == 0 && (sizeof(K) == 4 || sizeof(K) == 8)) {
-            // The verification argument needs an INJECTIVE key transform (sorted permutation => unique bytes).  The
-            // reference's descending float transform is not (radix_sort.hpp:100-127: -0.0 / +denorm_min and
-            // +0.0 / -denorm_min collide, and their relative order is then decided by stability alone), so
-            // descending float / double sorts always take the deterministic kernel.
-            const bool injective = !(tf.fa != 0 && tf.nm != 0);
-            if (injective) {
-                if (speculative_enabled() && n >= kSpeculativeMinKeys && !want_ns_kernel()) rank = kRankTwoSweep;
-                const char *e = std::getenv("BCB_SORT_RANK");  // explicit override for experiments
-                if (e && std::strcmp(e, "ordered") == 0) rank = kRankOrderedAtoms;
-                if (e && std::strcmp(e, "twosweep") == 0) rank = kRankTwoSweep;
-                if (e && std::strcmp(e, "atomic_or") == 0) rank = kRankAtomicOr;
-            }
-        }
-    }
     const size_t kbytes = align_up(n * sizeof(K), 256);
     const size_t vbytes = align_up(n * (size_t)VB, 256);
     void *scratch;
@@ -1023,74 +973,93 @@ static int sort_typed(StreamState *st, void *keys, void *values, size_t n, const
     void *tmp_keys = scratch;
     void *tmp_vals = VB ? (void *)((char *)scratch + kbytes) : nullptr;
 
-    const size_t tile = (size_t)tile_size_for<K, VB>(rank);
+    const size_t tile = tile_size_for<K, VB>(pass_kind);
     const size_t tiles = (n + tile - 1) / tile;
     void *lb;
-    BCB_TRY(lookback_reserve(st, tiles * kRadixSize * sizeof(unsigned long long), &lb));
+    BCB_TRY(lookback_reserve(st, kArenaPacked, tiles * kRadixSize * sizeof(unsigned long long), &lb));
 
     unsigned *hist = st->hist;
     unsigned *base = st->hist + 8 * kRadixSize;
     BCB_CUDA_TRY(cudaMemsetAsync(hist, 0, NPASS * kRadixSize * sizeof(unsigned), st->stream));
     {
-        size_t blocks = (n * sizeof(K) + (size_t)kHistThreads * 32 - 1) / ((size_t)kHistThreads * 32);
-        const size_t cap = (size_t)st->sm_count * (2048 / kHistThreads);
-        if (blocks > cap) blocks = cap;
-        if (blocks < 1) blocks = 1;
-        static int hist_variant = -1;  // BCB_HIST_VARIANT=0: plain layout; 1 (default for large inputs): one column per lane
-        if (hist_variant < 0) { const char *e = std::getenv("BCB_HIST_VARIANT"); hist_variant = e ? std::atoi(e) : 1; }
-        if (hist_variant == 1 && n >= ((size_t)1 << 22)) {
+        const bool ident = (tf.nm | tf.xc | tf.fa) == 0;
+        if (n >= ((size_t)1 << 22)) {  // one counter column per lane (conflict-free), one CTA per SM
             constexpr int COLS = sizeof(K) == 8 ? 16 : 32;
             constexpr size_t kSmem = sizeof(K) * kRadixSize * COLS * sizeof(unsigned);
-            const bool ident = (tf.nm | tf.xc | tf.fa) == 0;
             auto kernel = ident ? radix_histogram_columns<K, COLS, true> : radix_histogram_columns<K, COLS, false>;
-            static bool configured[2][64] = {};
-            if (st->device >= 64 || !configured[ident][st->device]) {
+            static std::atomic<unsigned long long> configured[2];  // bit per device
+            const unsigned long long bit = st->device < 64 ? (1ull << st->device) : 0ull;
+            if (!(configured[ident].load(std::memory_order_acquire) & bit) || !bit) {
                 BCB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
-                if (st->device < 64) configured[ident][st->device] = true;
+                configured[ident].fetch_or(bit, std::memory_order_release);
             }
             LaunchTimer timer(st, BCB_K_RADIX_HISTOGRAM);
-            kernel<<<(unsigned)st->sm_count, 1024, kSmem, st->stream>>>((const K *)src_keys, n, hist, tf);
+            kernel<<<(unsigned)st->sm_count, 1024, kSmem, st->stream>>>((const K *)src_keys, n, hist, tf, gate);
         } else {
+            size_t blocks = (n * sizeof(K) + (size_t)kHistThreads * 32 - 1) / ((size_t)kHistThreads * 32);
+            const size_t cap = (size_t)st->sm_count * (2048 / kHistThreads);
+            if (blocks > cap) blocks = cap;
+            if (blocks < 1) blocks = 1;
             LaunchTimer timer(st, BCB_K_RADIX_HISTOGRAM);
-            radix_histogram<K><<<(unsigned)blocks, kHistThreads, 0, st->stream>>>((const K *)src_keys, n, hist, tf);
+            radix_histogram<K><<<(unsigned)blocks, kHistThreads, 0, st->stream>>>((const K *)src_keys, n, hist, tf, gate);
         }
         BCB_CUDA_TRY(cudaGetLastError());
         {
             LaunchTimer timer(st, BCB_K_DIGIT_SCAN);
-            digit_scan<<<NPASS, kRadixSize, 0, st->stream>>>(hist, base);
+            digit_scan<<<NPASS, kRadixSize, 0, st->stream>>>(hist, base, gate, gate ? spec_fallback_counter(st) : nullptr);
         }
         BCB_CUDA_TRY(cudaGetLastError());
     }
     void *kin = keys, *kout = tmp_keys, *vin = values, *vout = tmp_vals;
     for (int p = 0; p < NPASS; p++) {
         BCB_TRY((run_pass<K, VB>(st, p == 0 ? src_keys : kin, kout, p == 0 ? src_vals : vin, vout, base + p * kRadixSize,
-                                 (unsigned long long *)lb, n, p * kRadixBits, tf, rank)));
+                                 (unsigned long long *)lb, n, p * kRadixBits, tf, pass_kind, gate)));
         void *t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;
     }
-    if (kin != keys) {  // odd pass count (8-bit keys): result is in the temporary
+    if (kin != keys) {  // odd pass count (8-bit keys): result is in the temporary (never gated: those sorts do not speculate)
         BCB_CUDA_TRY(cudaMemcpyAsync(keys, kin, n * sizeof(K), cudaMemcpyDeviceToDevice, st->stream));
         if (VB) BCB_CUDA_TRY(cudaMemcpyAsync(values, vin, n * (size_t)VB, cudaMemcpyDeviceToDevice, st->stream));
     }
+    return BCB_SUCCESS;
+}
+
+template <typename K, int VB>
+static int sort_typed(StreamState *st, void *keys, void *values, size_t n, const Transform &tf, const void *src_keys = nullptr,
+                      const void *src_vals = nullptr)
+{
+    // src_keys / src_vals: read the input from there instead (sorted copy; the source is left untouched)
+    if (!src_keys) { src_keys = keys; src_vals = values; }
+    int pass_kind = kPassDeterministic;
     if constexpr (VB == 0 && (sizeof(K) == 4 || sizeof(K) == 8)) {
-        if (rank_is_speculative(rank)) {
-            // verify the speculation (see above); on failure sort again with the deterministic kernel
-            int *flag = (int *)st->pinned_slot_dev;
-            *(volatile int *)st->pinned_slot = 0;
-            {
-                LaunchTimer timer(st, BCB_K_OTHER);
-                BCB_TRY(run_verify<K>(st, keys, n, tf, flag));
-            }
-            BCB_CUDA_TRY(cudaGetLastError());
-            BCB_CUDA_TRY(cudaStreamSynchronize(st->stream));
-            st->spec_runs++;
-            if (*(volatile int *)st->pinned_slot != 0 || g_force_fallback == 1) {
-                st->spec_fallbacks++;
-                return sort_typed<K, VB>(st, keys, values, n, tf, src_keys, src_vals, kRankAtomicOr);
-            }
+        // The verification argument needs an INJECTIVE key transform (sorted permutation => unique bytes).  The
+        // reference's descending float transform is not (radix_sort.hpp:100-127: -0.0 / +denorm_min and
+        // +0.0 / -denorm_min collide, and their relative order is then decided by stability alone), so
+        // descending float / double sorts always take the deterministic kernel.
+        const bool injective = !(tf.fa != 0 && tf.nm != 0);
+        const SortEnv &env = sort_env();
+        if (injective && env.speculative && n >= kSpeculativeMinKeys) {
+            pass_kind = kPassTwoSweep;
+            // bulk copies need 16-byte aligned arrays (the scratch buffer always is)
+            const bool aligned = ((((uintptr_t)keys) | ((uintptr_t)src_keys)) & 15) == 0;
+            if (env.ws && aligned && n >= kWsMinKeys) pass_kind = kPassWs;
         }
     }
-    return BCB_SUCCESS;
+    if (pass_kind == kPassDeterministic) return sort_passes<K, VB>(st, keys, values, n, tf, src_keys, src_vals, pass_kind, nullptr);
+
+    if constexpr (VB == 0 && (sizeof(K) == 4 || sizeof(K) == 8)) {
+        BCB_TRY((sort_passes<K, VB>(st, keys, values, n, tf, src_keys, src_vals, pass_kind, nullptr)));
+        // verify the speculation on the device; the deterministic sort of the (permuted) buffer follows, gated on the flag
+        int *flag = spec_flag(st);
+        BCB_CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st->stream));
+        {
+            LaunchTimer timer(st, BCB_K_OTHER);
+            BCB_TRY(run_verify<K>(st, keys, n, tf, flag, sort_env().force_fallback ? 1 : 0));
+        }
+        st->spec_runs++;
+        return sort_passes<K, VB>(st, keys, values, n, tf, keys, values, kPassDeterministic, flag);
+    }
+    return BCB_EINVAL;
 }
 
 template <typename K>
@@ -1273,7 +1242,10 @@ int bcb_sort_speculation_stats(bcb_stream stream, unsigned long long *runs, unsi
     StreamState *st;
     BCB_TRY(stream_state((cudaStream_t)stream, &st));
     if (runs) *runs = st->spec_runs;
-    if (fallbacks) *fallbacks = st->spec_fallbacks;
+    if (fallbacks) {  // counted on the device by the gated fallback launches
+        BCB_CUDA_TRY(cudaMemcpyAsync(fallbacks, spec_fallback_counter(st), sizeof(unsigned long long), cudaMemcpyDeviceToHost, st->stream));
+        BCB_CUDA_TRY(cudaStreamSynchronize(st->stream));
+    }
     return BCB_SUCCESS;
 }
 

@@ -85,30 +85,39 @@ int scratch_reserve(StreamState *st, size_t bytes, void **out)
     return BCB_SUCCESS;
 }
 
-int lookback_reserve(StreamState *st, size_t bytes, void **out)
+int lookback_reserve(StreamState *st, int arena, size_t bytes, void **out)
 {
-    if (bytes > st->lookback_bytes) {
-        if (st->lookback) BCB_CUDA_TRY(cudaFreeAsync(st->lookback, st->stream));
-        st->lookback = nullptr;
-        st->lookback_bytes = 0;
+    StreamState::LookbackArena &a = st->arena[arena];
+    if (bytes > a.bytes) {
+        if (a.mem) BCB_CUDA_TRY(cudaFreeAsync(a.mem, st->stream));
+        a.mem = nullptr;
+        a.bytes = 0;
         size_t want = (bytes + (bytes >> 2) + 255) & ~(size_t)255;
-        BCB_CUDA_TRY(cudaMallocAsync(&st->lookback, want, st->stream));
-        st->lookback_bytes = want;
-        BCB_CUDA_TRY(cudaMemsetAsync(st->lookback, 0, want, st->stream));
-        st->epoch = 0;
+        BCB_CUDA_TRY(cudaMallocAsync(&a.mem, want, st->stream));
+        a.bytes = want;
+        BCB_CUDA_TRY(cudaMemsetAsync(a.mem, 0, want, st->stream));
+        a.epoch = 0;
     }
-    *out = st->lookback;
+    *out = a.mem;
     return BCB_SUCCESS;
 }
 
-int next_epoch(StreamState *st, uint32_t *epoch)
+int next_epoch(StreamState *st, int arena, uint32_t *epoch)
 {
-    if (st->epoch >= (1u << 30) - 2) {
-        if (st->lookback) BCB_CUDA_TRY(cudaMemsetAsync(st->lookback, 0, st->lookback_bytes, st->stream));
-        st->epoch = 0;
+    StreamState::LookbackArena &a = st->arena[arena];
+    if (a.epoch >= (1u << 30) - 2) {
+        if (a.mem) BCB_CUDA_TRY(cudaMemsetAsync(a.mem, 0, a.bytes, st->stream));
+        a.epoch = 0;
     }
-    *epoch = ++st->epoch;
+    *epoch = ++a.epoch;
     return BCB_SUCCESS;
+}
+
+unsigned long long ticket_reserve(StreamState *st, unsigned long long draws)
+{
+    const unsigned long long base = st->ticket_base;
+    st->ticket_base += draws;
+    return base;
 }
 
 LaunchTimer::LaunchTimer(StreamState *s, int kind) : st(s)
@@ -124,7 +133,8 @@ LaunchTimer::LaunchTimer(StreamState *s, int kind) : st(s)
     }
     StreamState::TimedLaunch &t = st->timed[st->timed_count];
     t.kind = kind;
-    if (cudaEventCreate(&t.start) != cudaSuccess || cudaEventCreate(&t.stop) != cudaSuccess) { (void)cudaGetLastError(); return; }
+    if (cudaEventCreate(&t.start) != cudaSuccess) { (void)cudaGetLastError(); return; }
+    if (cudaEventCreate(&t.stop) != cudaSuccess) { (void)cudaGetLastError(); (void)cudaEventDestroy(t.start); return; }
     slot = st->timed_count++;
     (void)cudaEventRecord(t.start, st->stream);
 }
@@ -184,14 +194,6 @@ static int grid_for(size_t n, int sm_count)
 }  // namespace bcb
 
 using namespace bcb;
-
-// SM-issued copy: what a kernel's own stores to (peer) memory can sustain, next to the copy engines of bcb_memcpy_d2d
-template <typename V>
-__global__ void __launch_bounds__(256) sm_copy_kernel(V *__restrict__ dst, const V *__restrict__ src, size_t n)
-{
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
-}
 
 extern "C" {
 
@@ -292,8 +294,14 @@ int bcb_workspace_release(bcb_stream stream)
         g_states.erase(it);
     }
     (void)cudaStreamSynchronize(st->stream);
+    for (int i = 0; i < st->timed_count; i++) {  // timing records nobody read
+        (void)cudaEventDestroy(st->timed[i].start);
+        (void)cudaEventDestroy(st->timed[i].stop);
+    }
+    delete[] st->timed;
     if (st->scratch) (void)cudaFreeAsync(st->scratch, st->stream);
-    if (st->lookback) (void)cudaFreeAsync(st->lookback, st->stream);
+    for (int a = 0; a < kArenaCount; a++)
+        if (st->arena[a].mem) (void)cudaFreeAsync(st->arena[a].mem, st->stream);
     (void)cudaStreamSynchronize(st->stream);
     if (st->control) (void)cudaFree(st->control);
     if (st->hist) (void)cudaFree(st->hist);
@@ -310,7 +318,7 @@ int bcb_workspace_bytes(bcb_stream stream, size_t *bytes)
     BCB_CUDA_TRY(cudaGetDevice(&device));
     std::lock_guard<std::mutex> lock(g_mutex);
     auto it = g_states.find(Key{device, (cudaStream_t)stream});
-    *bytes = (it == g_states.end()) ? 0 : it->second->scratch_bytes + it->second->lookback_bytes;
+    *bytes = (it == g_states.end()) ? 0 : it->second->scratch_bytes + it->second->arena[0].bytes + it->second->arena[1].bytes;
     return BCB_SUCCESS;
 }
 
@@ -430,24 +438,6 @@ int bcb_memcpy_d2d(bcb_stream stream, void *dst, const void *src, size_t bytes)
     if (bytes == 0) return BCB_SUCCESS;
     if (!dst || !src) return BCB_EINVAL;
     BCB_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-    return BCB_SUCCESS;
-}
-
-int bcb_copy_kernel(bcb_stream stream, void *dst, const void *src, size_t bytes, int vector_bytes)
-{
-    if (bytes == 0) return BCB_SUCCESS;
-    if (!dst || !src) return BCB_EINVAL;
-    if ((vector_bytes != 4 && vector_bytes != 8 && vector_bytes != 16) || bytes % vector_bytes || ((uintptr_t)dst | (uintptr_t)src) % vector_bytes)
-        return BCB_EINVAL;
-    StreamState *st;
-    BCB_TRY(stream_state((cudaStream_t)stream, &st));
-    const size_t n = bytes / vector_bytes;
-    size_t blocks = (n + 255) / 256;
-    if (blocks > (size_t)st->sm_count * 8) blocks = (size_t)st->sm_count * 8;
-    if (vector_bytes == 4) sm_copy_kernel<unsigned><<<(unsigned)blocks, 256, 0, st->stream>>>((unsigned *)dst, (const unsigned *)src, n);
-    else if (vector_bytes == 8) sm_copy_kernel<uint2><<<(unsigned)blocks, 256, 0, st->stream>>>((uint2 *)dst, (const uint2 *)src, n);
-    else sm_copy_kernel<uint4><<<(unsigned)blocks, 256, 0, st->stream>>>((uint4 *)dst, (const uint4 *)src, n);
-    BCB_CUDA_TRY(cudaGetLastError());
     return BCB_SUCCESS;
 }
 

@@ -15,7 +15,9 @@
 // of its input before it writes, and tiles are disjoint.
 // Floating-point prefixes are folded strictly in tile order, so results are run-to-run deterministic.
 #include "ops.cuh"
+#include "tma.cuh"
 
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 
@@ -77,29 +79,26 @@ template <typename T> struct TileState<T, true> {
 };
 
 template <typename T> struct TileState<T, false> {
-    unsigned *status;
-    T *partial;
-    T *inclusive;
-    static size_t bytes(size_t tiles) { return ((tiles * 4 + 15) & ~(size_t)15) + 2 * tiles * sizeof(T); }
-    __host__ __device__ void bind(void *mem, size_t tiles)
-    {
-        status = (unsigned *)mem;
-        partial = (T *)((char *)mem + ((tiles * 4 + 15) & ~(size_t)15));
-        inclusive = partial + tiles;
-    }
+    // one 32-byte record per tile, the same for every 8-byte type and every tile count: a slot is only ever read
+    // as what it was written as (its own arena, see StreamState::arena), so stale bytes can never pose as a tag
+    struct Record { unsigned status; unsigned pad; T partial; T inclusive; unsigned long long pad2; };
+    static_assert(sizeof(Record) == 32, "record layout is part of the arena contract");
+    Record *rec;
+    static size_t bytes(size_t tiles) { return tiles * sizeof(Record); }
+    __host__ __device__ void bind(void *mem, size_t) { rec = (Record *)mem; }
     __device__ __forceinline__ void post(size_t tile, unsigned epoch, unsigned st, T v) const
     {
-        T *dst = (st == kPartial) ? partial : inclusive;
-        *((volatile T *)(dst + tile)) = v;
-        st_release_u32(status + tile, (epoch << 2) | st);
+        T *dst = (st == kPartial) ? &rec[tile].partial : &rec[tile].inclusive;
+        *((volatile T *)dst) = v;
+        st_release_u32(&rec[tile].status, (epoch << 2) | st);
     }
     __device__ __forceinline__ unsigned peek(size_t tile, unsigned epoch, T &v) const
     {
-        const unsigned tag = ld_acquire_u32(status + tile);
+        const unsigned tag = ld_acquire_u32(&rec[tile].status);
         if ((tag >> 2) != epoch) return kInvalid;
         const unsigned st = tag & 3u;
-        const T *src = (st == kPartial) ? partial : inclusive;
-        v = *((volatile const T *)(src + tile));
+        const T *src = (st == kPartial) ? &rec[tile].partial : &rec[tile].inclusive;
+        v = *((volatile const T *)src);
         return st;
     }
 };
@@ -289,46 +288,6 @@ scan_kernel(const T *in, T *out, size_t n, int exclusive, T init, TileState<T> t
 // tiles in flight at any moment form one contiguous window of the input and a prefetched tile is never one that
 // another CTA is waiting for.  (Drawing tickets ahead of time was measured to be 2x slower: a CTA then HOLDS
 // tiles it is not working on yet while their successors spin in the look-back.)
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(void *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(void *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, unsigned bytes, void *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
-                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tma_store_1d(void *gmem_dst, const void *smem_src, unsigned bytes)
-{
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
-                 : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-template <int N> __device__ __forceinline__ void tma_store_wait_read()
-{
-    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 constexpr int kRoundThreads = 512;                 // threads per CTA of the round-synchronous kernel
 constexpr int kRoundWarps = kRoundThreads / 32;
 
@@ -390,7 +349,7 @@ scan_tma_kernel(const T *in, T *out, size_t n, int exclusive, T init, TileState<
 
     if (tid == 0) {
         for (int s = 0; s < S; s++) mbar_init(&full_bar[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_init_fence();
         for (int s = 0; s < S; s++) issue_load(s, tile_of((unsigned)s));
     }
     __syncthreads();
@@ -585,39 +544,44 @@ static int launch_scan(StreamState *st, const void *in, void *out, size_t n, int
     if (init_host) std::memcpy(&init, init_host, sizeof(T));
     const size_t tiles = (n + kScanTile - 1) / kScanTile;
     if (tiles > 0x7fffffffull) return BCB_ETOOLARGE;
-    void *mem;
-    BCB_TRY(lookback_reserve(st, TileState<T>::bytes(tiles), &mem));
-    unsigned epoch;
-    BCB_TRY(next_epoch(st, &epoch));
-    TileState<T> ts;
-    ts.bind(mem, tiles);
-    static int use_tma = -1;  // BCB_SCAN_TMA=0 forces the one-tile-per-CTA kernel
-    if (use_tma < 0) { const char *e = std::getenv("BCB_SCAN_TMA"); use_tma = (e && e[0] == '0') ? 0 : 1; }
+    constexpr int kArena = sizeof(T) <= 4 ? kArenaPacked : kArenaWide;
+    static const bool use_tma = [] { const char *e = std::getenv("BCB_SCAN_TMA"); return !(e && e[0] == '0'); }();  // 0: one tile per CTA
     const bool aligned = (((uintptr_t)in | (uintptr_t)out) & 15) == 0;
+    void *mem;
+    unsigned epoch;
+    TileState<T> ts;
     if (use_tma && aligned && n >= (size_t)4 * ScanRing<T>::kTile) {
         typedef ScanRing<T> R;
         const size_t rtiles = (n + R::kTile - 1) / R::kTile;
-        BCB_TRY(lookback_reserve(st, TileState<T>::bytes(rtiles), &mem));
+        // reserve first, then draw the epoch (a reallocation restarts the arena's epoch counter)
+        BCB_TRY(lookback_reserve(st, kArena, TileState<T>::bytes(rtiles), &mem));
+        BCB_TRY(next_epoch(st, kArena, &epoch));
         ts.bind(mem, rtiles);
         auto kernel = scan_tma_kernel<T, OP>;
-        static int resident[64] = {};
-        int per_sm = (st->device < 64) ? resident[st->device] : 0;
+        static std::atomic<int> resident[64];
+        int per_sm = (st->device < 64) ? resident[st->device].load(std::memory_order_acquire) : 0;
         if (per_sm == 0) {
             BCB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R::kBytes));
             BCB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kRoundThreads, R::kBytes));
             if (per_sm < 1) per_sm = 1;
-            if (st->device < 64) resident[st->device] = per_sm;
+            if (st->device < 64) resident[st->device].store(per_sm, std::memory_order_release);
         }
         size_t grid = (size_t)st->sm_count * (size_t)per_sm;
         if (grid > (size_t)kRoundThreads) grid = kRoundThreads;  // one look-back thread per earlier tile of the round
         if (grid > rtiles) grid = rtiles;
         LaunchTimer timer(st, BCB_K_SCAN);
-        kernel<<<(unsigned)grid, kRoundThreads, R::kBytes, st->stream>>>((const T *)in, (T *)out, n, exclusive, init, ts, epoch, rtiles);
-        BCB_CUDA_TRY(cudaGetLastError());
+        // The round-synchronous look-back needs the whole grid resident: a cooperative launch guarantees that (or
+        // fails loudly) whatever else runs on the device.
+        const T *in_t = (const T *)in;
+        T *out_t = (T *)out;
+        void *args[] = {(void *)&in_t, (void *)&out_t, (void *)&n, (void *)&exclusive, (void *)&init, (void *)&ts, (void *)&epoch, (void *)&rtiles};
+        BCB_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)kernel, dim3((unsigned)grid), dim3(kRoundThreads), args, R::kBytes, st->stream));
         return BCB_SUCCESS;
     }
-    const unsigned long long base = st->ticket_base;
-    st->ticket_base += tiles;
+    BCB_TRY(lookback_reserve(st, kArena, TileState<T>::bytes(tiles), &mem));
+    BCB_TRY(next_epoch(st, kArena, &epoch));
+    ts.bind(mem, tiles);
+    const unsigned long long base = ticket_reserve(st, tiles);
     LaunchTimer timer(st, BCB_K_SCAN);
     scan_kernel<T, OP><<<(unsigned)tiles, kScanThreads, 0, st->stream>>>(
         (const T *)in, (T *)out, n, exclusive, init, ts, epoch, st->control + kControlTicket, base);

@@ -90,9 +90,6 @@ BCB_API int bcb_memcpy_h2d(bcb_stream stream, void *device_dst, const void *host
 BCB_API int bcb_memcpy_d2h(bcb_stream stream, void *host_dst, const void *device_src, size_t bytes);
 BCB_API int bcb_memcpy_d2d(bcb_stream stream, void *device_dst, const void *device_src, size_t bytes);
 /* fill / iota / is_sorted (algorithm/fill.hpp, iota.hpp, is_sorted.hpp:39-68) -- the helpers either side of the path */
-/* copy by a kernel's own loads and stores (vector_bytes 4, 8 or 16 per thread) instead of the copy engines: the
- * diagnostic for what SM-issued stores into peer memory sustain over NVLink (scripts/peer_bandwidth.py) */
-BCB_API int bcb_copy_kernel(bcb_stream stream, void *dst, const void *src, size_t bytes, int vector_bytes);
 BCB_API int bcb_fill(bcb_stream stream, void *device_ptr, size_t n, const void *value_host, size_t value_bytes);
 BCB_API int bcb_iota(bcb_stream stream, int dtype, void *device_ptr, size_t n, const void *start_host);
 BCB_API int bcb_is_sorted(bcb_stream stream, int dtype, int descending, const void *keys, size_t n, int *result_host);
@@ -101,7 +98,7 @@ BCB_API int bcb_is_sorted(bcb_stream stream, int dtype, int descending, const vo
  * since the last read of that kind, and forgets them. */
 typedef enum bcb_kernel_kind {
     BCB_K_RADIX_HISTOGRAM = 0, BCB_K_DIGIT_SCAN = 1, BCB_K_ONESWEEP_PASS = 2, BCB_K_SCAN = 3, BCB_K_REDUCE = 4,
-    BCB_K_OTHER = 5, BCB_K_COUNT = 6
+    BCB_K_OTHER = 5, BCB_K_EXCHANGE_PASS = 6, BCB_K_COUNT = 7
 } bcb_kernel_kind;
 BCB_API int bcb_timing_enable(bcb_stream stream, int enable);
 BCB_API int bcb_timing_read(bcb_stream stream, int kind, double *total_ms, unsigned long long *launches);

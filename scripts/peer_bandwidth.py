@@ -29,10 +29,9 @@ def main():
     results = {}
     for target, tname in (((rank + 1) % world, "peer"), (rank, "local")):
         dst = ctx.peer.peers[target]
-        for name, fn in (("copy-engine", lambda: check(L.bcb_memcpy_d2d(q.handle, dst, src.data_ptr(), nbytes))),
-                         ("sm-4B", lambda: check(L.bcb_copy_kernel(q.handle, dst, src.data_ptr(), nbytes, 4))),
-                         ("sm-8B", lambda: check(L.bcb_copy_kernel(q.handle, dst, src.data_ptr(), nbytes, 8))),
-                         ("sm-16B", lambda: check(L.bcb_copy_kernel(q.handle, dst, src.data_ptr(), nbytes, 16)))):
+        # (the SM-issued 4/8/16-byte store rows of round 1 -- 696-706 GB/s -- came from a diagnostic copy kernel that no
+        # longer ships in the product library)
+        for name, fn in (("copy-engine", lambda: check(L.bcb_memcpy_d2d(q.handle, dst, src.data_ptr(), nbytes))),):
             for _ in range(2):
                 fn()
             torch.cuda.synchronize(); dist.barrier()

@@ -453,3 +453,108 @@ def test_large_narrow_key_sorts_use_the_column_histogram(dtype, gpu):
     k = random_keys(dtype, n, seed=23, mode="bits")
     for desc in (False, True):
         assert gpu.radix_sort(k, desc).tobytes() == oracle.radix_sort(k, desc).tobytes(), (dtype, desc)
+
+
+# ------------------------------------------------------------------ round 2: warp-specialised pass, async contract, arenas
+@pytest.mark.parametrize("dtype", ["uint", "int", "float", "ulong", "double"])
+def test_warp_specialised_pass_bit_exact(dtype, gpu):
+    """n >= 2^23 keys-only sorts of 32/64-bit keys take onesweep_ws (bulk-copy stores, ticketed tiles, look-back in helper
+    warps): several tiles per CTA, a partial last tile, heavy duplicates (runs shorter than a 16-byte chunk / empty runs)."""
+    n = (1 << 23) + 4321
+    for desc, mode in ((False, "bits"), (True, "few"), (False, "sorted")):
+        if desc and dtype in ("float", "double"):
+            continue  # descending float keys never speculate (covered by the colliding-keys test)
+        k = random_keys(dtype, n, seed=23, mode=mode)
+        assert gpu.radix_sort(k, desc).tobytes() == oracle.radix_sort(k, desc).tobytes(), (dtype, desc, mode)
+
+
+def test_multi_round_persistent_sort_2_26_keys_and_pairs(gpu):
+    """2^26 elements: ~10 tiles per CTA in the warp-specialised kernel (keys only) and ~37 rounds of the persistent
+    deterministic kernel (pairs): ticket wrap-around inside a launch, long look-back chains, epoch reuse across passes."""
+    n = (1 << 26) + 7
+    rng = np.random.default_rng(26)
+    k = rng.integers(0, 2**32, size=n, dtype=np.uint32)
+    assert gpu.radix_sort(k).tobytes() == oracle.radix_sort(k).tobytes()
+    v = np.arange(n, dtype=np.uint32)
+    k &= np.uint32(0x000fffff)  # many equal keys: the payload order is decided by stability alone
+    gk, gv = gpu.radix_sort(k, False, v)
+    ok, ov = oracle.radix_sort(k, False, v)
+    assert gk.tobytes() == ok.tobytes() and gv.tobytes() == ov.tobytes()
+
+
+def test_sort_is_enqueue_and_return(gpu):
+    """perf_sort.cpp:38-39 enqueues the sort and calls queue.finish(): bcb_radix_sort must not wait for the device, even
+    on the speculative path (the verification and the gated fallback stay on the device)."""
+    import torch
+    import compute_b200 as cb
+    n = 1 << 27
+    k = torch.randint(0, 2**31 - 1, (n,), dtype=torch.int32, device="cuda").view(torch.uint32)
+    cb.radix_sort(k)  # warm-up: scratch allocation, function attributes
+    torch.cuda.synchronize()
+    k2 = torch.randint(0, 2**31 - 1, (n,), dtype=torch.int32, device="cuda").view(torch.uint32)
+    torch.cuda.synchronize()
+    cb.radix_sort(k2)
+    still_running = not torch.cuda.current_stream().query()
+    torch.cuda.synchronize()
+    assert still_running, "bcb_radix_sort blocked until the sort was finished"
+    assert cb.is_sorted(k2.view(torch.int32))  # values < 2^31: same order as unsigned
+
+
+def test_two_queues_sort_concurrently_from_two_threads(gpu):
+    """Forward progress must not depend on the whole grid of one sort being resident: two command queues of one device,
+    driven from two host threads, each sorting 2^26 keys (warp-specialised kernel) and 2^22 pairs (persistent
+    deterministic kernel) at the same time."""
+    import threading
+    import torch
+    import compute_b200 as cb
+    results = {}
+
+    def work(idx):
+        stream = torch.cuda.Stream()
+        q = cb.command_queue(stream)
+        with torch.cuda.stream(stream):
+            g = torch.Generator(device="cuda").manual_seed(100 + idx)
+            k = torch.randint(0, 2**31 - 1, (1 << 26,), dtype=torch.int32, device="cuda", generator=g)
+            pk = torch.randint(0, 1000, (1 << 22,), dtype=torch.int32, device="cuda", generator=g)
+            pv = torch.arange(1 << 22, dtype=torch.int32, device="cuda")
+            ref = torch.sort(k).values
+            pref = torch.sort(pk, stable=True)
+            for _ in range(3):
+                kk, pkk, pvv = k.clone(), pk.clone(), pv.clone()
+                cb.radix_sort(kk, True, q)
+                cb.radix_sort_by_key(pkk, pvv, True, q)
+            stream.synchronize()
+            results[idx] = bool(torch.equal(kk, ref)) and bool(torch.equal(pkk, pref.values)) and bool(torch.equal(pvv.long(), pref.indices))
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not any(t.is_alive() for t in threads), "concurrent sorts did not finish (look-back waiting for a CTA that is not resident?)"
+    assert results == {0: True, 1: True}
+
+
+def test_scan_descriptor_arenas_do_not_alias(gpu):
+    """Round-1 advisor findings: (a) two 8-byte scans of different data on a FRESH queue (the second launch used to draw
+    the first one's epoch again after a look-back reallocation), (b) an 8-byte scan right after a u32 sort on the same
+    stream (its status words used to overlay the sort's digit counts)."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r})\n"
+        "import gpu_api, oracle\n"
+        "rng = np.random.default_rng(5)\n"
+        "for i in range(3):\n"
+        "    x = rng.integers(-1000, 1000, size=(1 << 20) + 5 * i).astype(np.float64)\n"
+        "    assert np.array_equal(gpu_api.scan(x, 'plus', False), np.cumsum(x)), ('double scan', i)\n"
+        "for i in range(4):\n"
+        "    k = rng.integers(0, 64, size=1 << 21, dtype=np.uint32)\n"
+        "    assert np.array_equal(gpu_api.radix_sort(k), np.sort(k))\n"
+        "    y = rng.integers(-2**40, 2**40, size=(1 << 21) + 3, dtype=np.int64)\n"
+        "    assert np.array_equal(gpu_api.scan(y, 'plus', False), np.cumsum(y)), ('long scan after sort', i)\n"
+        "print('ARENAS_OK')\n"
+    )
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ARENAS_OK" in out.stdout, out.stdout + out.stderr
