@@ -645,7 +645,8 @@ static int launch_pass_impl(StreamState *st, const void *kin, void *kout, const 
     unsigned epoch;
     BCB_TRY(next_epoch(st, kArenaPacked, &epoch));
     const unsigned long long ticket_base = ticket_reserve(st, tiles + grid);  // every CTA draws one void ticket
-    LaunchTimer timer(st, IDENT == kDigitSplit ? BCB_K_EXCHANGE_PASS : BCB_K_ONESWEEP_PASS);
+    // (gated fallback launches of a speculative sort return at once: timed as "other", not as pass kernels)
+    LaunchTimer timer(st, gate ? BCB_K_OTHER : (IDENT == kDigitSplit ? BCB_K_EXCHANGE_PASS : BCB_K_ONESWEEP_PASS));
     kernel<<<(unsigned)grid, THREADS, kSmemBytes, st->stream>>>((const K *)kin, (K *)kout, vin, vout, base, lookback, epoch, n, tiles,
                                                                shift, st->control + kControlTicket, ticket_base, gate, tf);
     BCB_CUDA_TRY(cudaGetLastError());
@@ -993,19 +994,19 @@ static int sort_passes(StreamState *st, void *keys, void *values, size_t n, cons
                 BCB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
                 configured[ident].fetch_or(bit, std::memory_order_release);
             }
-            LaunchTimer timer(st, BCB_K_RADIX_HISTOGRAM);
+            LaunchTimer timer(st, gate ? BCB_K_OTHER : BCB_K_RADIX_HISTOGRAM);
             kernel<<<(unsigned)st->sm_count, 1024, kSmem, st->stream>>>((const K *)src_keys, n, hist, tf, gate);
         } else {
             size_t blocks = (n * sizeof(K) + (size_t)kHistThreads * 32 - 1) / ((size_t)kHistThreads * 32);
             const size_t cap = (size_t)st->sm_count * (2048 / kHistThreads);
             if (blocks > cap) blocks = cap;
             if (blocks < 1) blocks = 1;
-            LaunchTimer timer(st, BCB_K_RADIX_HISTOGRAM);
+            LaunchTimer timer(st, gate ? BCB_K_OTHER : BCB_K_RADIX_HISTOGRAM);
             radix_histogram<K><<<(unsigned)blocks, kHistThreads, 0, st->stream>>>((const K *)src_keys, n, hist, tf, gate);
         }
         BCB_CUDA_TRY(cudaGetLastError());
         {
-            LaunchTimer timer(st, BCB_K_DIGIT_SCAN);
+            LaunchTimer timer(st, gate ? BCB_K_OTHER : BCB_K_DIGIT_SCAN);
             digit_scan<<<NPASS, kRadixSize, 0, st->stream>>>(hist, base, gate, gate ? spec_fallback_counter(st) : nullptr);
         }
         BCB_CUDA_TRY(cudaGetLastError());
@@ -1042,7 +1043,9 @@ static int sort_typed(StreamState *st, void *keys, void *values, size_t n, const
             pass_kind = kPassTwoSweep;
             // bulk copies need 16-byte aligned arrays (the scratch buffer always is)
             const bool aligned = ((((uintptr_t)keys) | ((uintptr_t)src_keys)) & 15) == 0;
-            if (env.ws && aligned && n >= kWsMinKeys) pass_kind = kPassWs;
+            // (64-bit keys: measured 23.7 Gkeys/s with onesweep_ws against 29.2 with the two-sweep kernel -- 21504-key
+            // tiles give each CTA too few keys per digit run to pay for the helper-warp pipeline)
+            if (env.ws && aligned && n >= kWsMinKeys && sizeof(K) == 4) pass_kind = kPassWs;
         }
     }
     if (pass_kind == kPassDeterministic) return sort_passes<K, VB>(st, keys, values, n, tf, src_keys, src_vals, pass_kind, nullptr);

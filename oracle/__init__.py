@@ -42,11 +42,55 @@ def op_code(name: str) -> int:
     return OPS.index(name)
 
 
+_STL_LIB_PATH = os.path.join(_HERE, "liboracle_stl.so")
+
+
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    stale = False
+    for lib_path, src_name in ((_LIB_PATH, "oracle.c"), (_STL_LIB_PATH, "stl_baseline.cpp")):
+        src = os.path.join(_HERE, src_name)
+        stale |= not os.path.exists(lib_path) or os.path.getmtime(lib_path) < os.path.getmtime(src)
+    if force or stale:
         subprocess.check_call(["make", "-s", "-C", _HERE] + (["-B"] if force else []))
     return _LIB_PATH
+
+
+_stl = None
+
+
+def stl_lib():
+    """Single-threaded STL baselines (perf/perf_stl_sort.cpp, perf_stl_partial_sum.cpp, perf_stl_accumulate.cpp)."""
+    global _stl
+    if _stl is None:
+        build()
+        L = ctypes.CDLL(_STL_LIB_PATH)
+        vp, sz = ctypes.c_void_p, ctypes.c_size_t
+        L.orc_stl_sort_u32.restype = ctypes.c_double
+        L.orc_stl_sort_u32.argtypes = [vp, sz]
+        L.orc_stl_partial_sum_i32.restype = ctypes.c_double
+        L.orc_stl_partial_sum_i32.argtypes = [vp, vp, sz]
+        L.orc_stl_accumulate_i32.restype = ctypes.c_double
+        L.orc_stl_accumulate_i32.argtypes = [vp, sz, vp]
+        _stl = L
+    return _stl
+
+
+def stl_sort_u32(keys: np.ndarray) -> float:
+    """std::sort in place; returns seconds."""
+    assert keys.dtype == np.uint32 and keys.flags.c_contiguous
+    return float(stl_lib().orc_stl_sort_u32(_ptr(keys), keys.size))
+
+
+def stl_partial_sum_i32(x: np.ndarray, out: np.ndarray) -> float:
+    assert x.dtype == np.int32 and out.dtype == np.int32
+    return float(stl_lib().orc_stl_partial_sum_i32(_ptr(x), _ptr(out), x.size))
+
+
+def stl_accumulate_i32(x: np.ndarray):
+    assert x.dtype == np.int32
+    r = ctypes.c_int32()
+    t = float(stl_lib().orc_stl_accumulate_i32(_ptr(x), x.size, ctypes.byref(r)))
+    return t, int(r.value)
 
 
 _lib = None
