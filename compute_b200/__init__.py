@@ -8,6 +8,14 @@ lands in hand-written sm_100a CUDA kernels (compute_b200/csrc).  No CPU fallback
 from ._capi import ComputeError, LIB_PATH, lib  # noqa: F401
 from .algorithm import (  # noqa: F401
     accumulate,
+    copy_if,
+    count,
+    count_if,
+    inner_product,
+    predicate,
+    reduce_by_key,
+    transform_if,
+    transform_reduce,
     exclusive_scan,
     inclusive_scan,
     insertion_sort,

@@ -53,6 +53,10 @@ SIGNATURES = {
     "bcb_scan": ([_vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp], _i),
     "bcb_reduce": ([_vp, _i, _i, _i, _vp, _sz, _vp, _i], _i),
     "bcb_accumulate": ([_vp, _i, _i, _i, _i, _vp, _sz, _vp, _vp], _i),
+    "bcb_transform_if": ([_vp, _i, _vp, _sz, _i, _vp, _vp, ctypes.POINTER(_sz)], _i),
+    "bcb_count_if": ([_vp, _i, _vp, _sz, _vp, ctypes.POINTER(ctypes.c_ulonglong)], _i),
+    "bcb_transform_reduce": ([_vp, _i, _vp, _vp, _sz, _i, _i, _vp, _i], _i),
+    "bcb_reduce_by_key": ([_vp, _i, _i, _vp, _vp, _sz, _vp, _vp, _i, ctypes.POINTER(_sz)], _i),
 }
 
 _lib = None

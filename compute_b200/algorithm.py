@@ -207,8 +207,127 @@ def accumulate(first: torch.Tensor, init, op="plus", op_dtype=None, acc_dtype=No
     return out[0]
 
 
+# ---------------------------------------------------------------------------------------------------------
+# callers of scan / reduce: closed functor set, see include/compute_b200.h
+# ---------------------------------------------------------------------------------------------------------
+ARITH_NAMES = ["none", "mul", "mod", "add", "sub", "and"]
+CMP_NAMES = ["eq", "ne", "lt", "le", "gt", "ge", "true"]
+UNARY_NAMES = ["identity", "negate", "abs", "square"]
+
+
+class _BcbPred(ctypes.Structure):
+    _fields_ = [("arith", ctypes.c_int), ("cmp", ctypes.c_int), ("a_bits", ctypes.c_ulonglong), ("b_bits", ctypes.c_ulonglong)]
+
+
+def predicate(cmp: str, b=0, arith: str = "none", a=0):
+    """((x ARITH a) CMP b): what the reference's lambda placeholders `_1 < 5`, `_1 * 2 >= 10`, `_1 % 2 == 1` denote."""
+    return (ARITH_NAMES.index(arith), a, CMP_NAMES.index(cmp), b)
+
+
+def _pred_struct(pred, code: int) -> _BcbPred:
+    arith, a, cmp_, b = pred
+    bits = []
+    for v in (a, b):
+        raw = np.zeros(8, dtype=np.uint8)
+        arr = _host_scalar(v, code)
+        raw[: arr.itemsize] = arr.view(np.uint8)
+        bits.append(int(raw.view(np.uint64)[0]))
+    return _BcbPred(arith, cmp_, bits[0], bits[1])
+
+
+def transform_if(first: torch.Tensor, result: torch.Tensor, function, pred, queue: command_queue | None = None) -> int:
+    """transform_if(first, last, result, function, predicate, queue) -- algorithm/transform_if.hpp:42-117.
+    Returns the number of elements written (the reference returns result + count)."""
+    _range(first)
+    _range(result, "result")
+    code = dtype_code(first.dtype)
+    if dtype_code(result.dtype) != code:
+        raise TypeError("transform_if: result and input value types differ")
+    ps = _pred_struct(pred, code)
+    count = ctypes.c_size_t()
+    check(lib().bcb_transform_if(_q(queue).handle, code, first.data_ptr(), first.numel(), UNARY_NAMES.index(function),
+                                 ctypes.byref(ps), result.data_ptr(), ctypes.byref(count)))
+    return int(count.value)
+
+
+def copy_if(first: torch.Tensor, result: torch.Tensor, pred, queue: command_queue | None = None) -> int:
+    """copy_if(first, last, result, predicate, queue) -- algorithm/copy_if.hpp:28-52 (transform_if with identity)."""
+    return transform_if(first, result, "identity", pred, queue)
+
+
+def count_if(first: torch.Tensor, pred, queue: command_queue | None = None) -> int:
+    """count_if(first, last, predicate, queue) -- algorithm/count_if.hpp:31-58, detail/count_if_with_reduce.hpp:27-80."""
+    _range(first)
+    code = dtype_code(first.dtype)
+    ps = _pred_struct(pred, code)
+    count = ctypes.c_ulonglong()
+    check(lib().bcb_count_if(_q(queue).handle, code, first.data_ptr(), first.numel(), ctypes.byref(ps), ctypes.byref(count)))
+    return int(count.value)
+
+
+def count(first: torch.Tensor, value, queue: command_queue | None = None) -> int:
+    """count(first, last, value, queue) -- algorithm/count.hpp:32-59: count_if(_1 == value)."""
+    return count_if(first, predicate("eq", value), queue)
+
+
+def transform_reduce(first: torch.Tensor, transform, reduce_op="plus", first2: torch.Tensor | None = None, result=None,
+                     queue: command_queue | None = None):
+    """transform_reduce(first, last, result, transform, reduce, queue) -- algorithm/transform_reduce.hpp:40-90; with
+    ``first2`` the binary form (first1, last1, first2, result, transform, reduce).  ``transform`` is a unary name
+    (identity / negate / abs / square) or, for the binary form, an operator name.  ``result``: CUDA tensor (device
+    iterator) or None (host value returned; None for an empty range)."""
+    _range(first)
+    code = dtype_code(first.dtype)
+    n = first.numel()
+    p2 = None
+    if first2 is not None:
+        _range(first2)
+        if dtype_code(first2.dtype) != code or first2.numel() < n:
+            raise ValueError("transform_reduce: second range must have the same value type and at least n elements")
+        p2 = first2.data_ptr()
+        t = op_code(transform)
+    else:
+        t = UNARY_NAMES.index(transform)
+    if isinstance(result, torch.Tensor):
+        check(lib().bcb_transform_reduce(_q(queue).handle, code, first.data_ptr(), p2, n, t, op_code(reduce_op), result.data_ptr(), 1))
+        return None
+    host = np.zeros(1, dtype=NP_OF_CODE[code])
+    check(lib().bcb_transform_reduce(_q(queue).handle, code, first.data_ptr(), p2, n, t, op_code(reduce_op), host.ctypes.data, 0))
+    return None if n == 0 else host[0]
+
+
+def inner_product(first1: torch.Tensor, first2: torch.Tensor, init, queue: command_queue | None = None):
+    """inner_product(first1, last1, first2, init, queue) -- algorithm/inner_product.hpp:40-64:
+    accumulate(transform(multiplies)(zip(first1, first2)), init, plus).  Returns init's type = the value type."""
+    code = dtype_code(first1.dtype)
+    r = transform_reduce(first1, "multiplies", "plus", first2, None, queue)
+    init_v = _host_scalar(init, code)[0]
+    if r is None:
+        return init_v
+    with np.errstate(over="ignore"):
+        return NP_OF_CODE[code].type(init_v + r)
+
+
+def reduce_by_key(keys: torch.Tensor, values: torch.Tensor, keys_result: torch.Tensor, values_result: torch.Tensor,
+                  op="plus", queue: command_queue | None = None) -> int:
+    """reduce_by_key(keys_first, keys_last, values_first, keys_result, values_result[, function], queue) --
+    algorithm/reduce_by_key.hpp:60-118.  Returns the number of (key, reduced value) pairs written."""
+    _range(keys)
+    _range(values, "values")
+    _range(keys_result, "keys_result")
+    _range(values_result, "values_result")
+    n = keys.numel()
+    if values.numel() < n:
+        raise ValueError("values range is shorter than the key range")
+    count = ctypes.c_size_t()
+    check(lib().bcb_reduce_by_key(_q(queue).handle, dtype_code(keys.dtype), dtype_code(values.dtype), keys.data_ptr(), values.data_ptr(), n,
+                                  keys_result.data_ptr(), values_result.data_ptr(), op_code(op), ctypes.byref(count)))
+    return int(count.value)
+
+
 __all__ = [
     "radix_sort", "radix_sort_by_key", "insertion_sort", "sort", "sort_host", "sort_by_key", "stable_sort",
     "stable_sort_by_key", "is_sorted", "exclusive_scan", "inclusive_scan", "partial_sum", "reduce", "accumulate",
+    "predicate", "transform_if", "copy_if", "count_if", "count", "transform_reduce", "inner_product", "reduce_by_key",
 ]
 _ = TORCH_OF_CODE

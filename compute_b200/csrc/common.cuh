@@ -47,6 +47,8 @@ struct StreamState {
     //   [0]   u64 ticket counter (monotonic across calls; launchers pass the base)
     //   [1]   int flag of the speculative sort: set by the verification kernel when the result is not sorted
     //   [2]   u64 number of speculative sorts that fell back to the deterministic kernel
+    //   [3]   u32 blocks-done counter of the one-launch reductions (reset by the last block)
+    //   [4]   u64 element counter of count_if
     unsigned long long *control = nullptr;
     unsigned long long ticket_base = 0;
     // decoupled look-back descriptors (scan + sort); zeroed at (re)allocation, validated by epoch tags.  One arena per
@@ -58,7 +60,7 @@ struct StreamState {
         size_t bytes = 0;
         uint32_t epoch = 0;  // 30-bit generation tag, bumped once per launch that uses the arena
     };
-    LookbackArena arena[2];
+    LookbackArena arena[3];
     // radix digit histograms / bases
     uint32_t *hist = nullptr;  // [8 passes][256]
     // pinned, device-mapped result slot for host-returning calls
@@ -83,7 +85,7 @@ struct LaunchTimer {
 
 int stream_state(cudaStream_t stream, StreamState **out);
 int scratch_reserve(StreamState *st, size_t bytes, void **out);
-enum { kArenaPacked = 0, kArenaWide = 1, kArenaCount = 2 };
+enum { kArenaPacked = 0, kArenaWide = 1, kArenaSegmented = 2, kArenaCount = 3 };
 // Reserve FIRST, then draw the epoch: a (re)allocation zeroes the arena and restarts its epoch counter, so an epoch
 // drawn before the last reserve of a launch could be handed out again later.
 int lookback_reserve(StreamState *st, int arena, size_t bytes, void **out);
@@ -92,7 +94,7 @@ int next_epoch(StreamState *st, int arena, uint32_t *epoch);
 // persistent kernels draw tile ids from the per-stream ticket counter: returns the base of `draws` fresh tickets
 unsigned long long ticket_reserve(StreamState *st, unsigned long long draws);
 
-constexpr int kControlTicket = 0, kControlSpecFlag = 1, kControlSpecFallbacks = 2;
+constexpr int kControlTicket = 0, kControlSpecFlag = 1, kControlSpecFallbacks = 2, kControlReduceDone = 3, kControlCount = 4;
 
 // ---- device helpers ------------------------------------------------------------------------
 #ifdef __CUDACC__

@@ -115,4 +115,40 @@ __host__ __device__ __forceinline__ A load_as(const void *p, size_t i, int dtype
 #define BCB_FOR_EACH_FP_TYPE(X) X(BCB_FLOAT, float) X(BCB_DOUBLE, double)
 #define BCB_FOR_EACH_TYPE(X) BCB_FOR_EACH_INT_TYPE(X) BCB_FOR_EACH_FP_TYPE(X)
 
+#ifdef __CUDACC__
+// fixed-shape (hence run-to-run deterministic) warp / block folds shared by reduce.cu and stream_ops.cu
+template <typename A, int OP>
+__device__ __forceinline__ A warp_reduce(A v)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        A o;
+        if constexpr (sizeof(A) < 4) o = (A)__shfl_down_sync(0xffffffffu, (int)v, off);
+        else o = __shfl_down_sync(0xffffffffu, v, off);
+        v = Op<OP, A>::apply(v, o);
+    }
+    return v;
+}
+
+template <typename A, int OP>
+__device__ __forceinline__ A block_reduce(A v, A *smem /* [32] */)
+{
+    v = warp_reduce<A, OP>(v);
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    if (lane == 0) smem[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned nwarps = blockDim.x >> 5;
+        A w = lane < nwarps ? smem[lane] : Op<OP, A>::identity();
+        w = warp_reduce<A, OP>(w);
+        if (lane == 0) smem[0] = w;
+    }
+    __syncthreads();
+    A r = smem[0];
+    __syncthreads();
+    return r;
+}
+
+#endif  // __CUDACC__
+
 }  // namespace bcb

@@ -18,38 +18,6 @@ constexpr int kReduceThreads = 256;
 constexpr int kReduceUnroll = 4;
 constexpr int kMaxReduceBlocks = 148 * 8 * 2;
 
-template <typename A, int OP>
-__device__ __forceinline__ A warp_reduce(A v)
-{
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        A o;
-        if constexpr (sizeof(A) < 4) o = (A)__shfl_down_sync(0xffffffffu, (int)v, off);
-        else o = __shfl_down_sync(0xffffffffu, v, off);
-        v = Op<OP, A>::apply(v, o);
-    }
-    return v;
-}
-
-template <typename A, int OP>
-__device__ __forceinline__ A block_reduce(A v, A *smem /* [32] */)
-{
-    v = warp_reduce<A, OP>(v);
-    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    if (lane == 0) smem[warp] = v;
-    __syncthreads();
-    if (warp == 0) {
-        const unsigned nwarps = blockDim.x >> 5;
-        A w = lane < nwarps ? smem[lane] : Op<OP, A>::identity();
-        w = warp_reduce<A, OP>(w);
-        if (lane == 0) smem[0] = w;
-    }
-    __syncthreads();
-    A r = smem[0];
-    __syncthreads();
-    return r;
-}
-
 template <typename T, int OP, int VEC>
 __device__ __forceinline__ T fold_vec(T acc, const uint4 &v)
 {
@@ -222,25 +190,8 @@ static int launch_reduce_same(StreamState *st, const void *in, size_t n, void *r
 {
     void *partials;
     BCB_TRY(scratch_reserve(st, (size_t)kMaxReduceBlocks * sizeof(T), &partials));
-    unsigned *counter = reinterpret_cast<unsigned *>(st->control + 1);
-    static int variant = -1;  // BCB_REDUCE_VARIANT: tuning knob (grid multiplier / unroll / access pattern)
-    if (variant < 0) { const char *e = std::getenv("BCB_REDUCE_VARIANT"); variant = e ? std::atoi(e) : 0; }
-    int grid = reduce_grid(n, sizeof(T), st->sm_count);
+    unsigned *counter = reinterpret_cast<unsigned *>(st->control + kControlReduceDone);
     LaunchTimer timer(st, BCB_K_REDUCE);
-    if constexpr (sizeof(T) == 4 && OP == BCB_PLUS) {
-        const int cap4 = st->sm_count * 4, cap16 = st->sm_count * 16 < kMaxReduceBlocks ? st->sm_count * 16 : kMaxReduceBlocks;
-        switch (variant) {
-        case 1: reduce_kernel<T, OP, 4, true><<<grid, kReduceThreads, 0, st->stream>>>((const T *)in, n, (T *)partials, counter, (T *)result_dev); break;
-        case 2: reduce_kernel<T, OP, 8, true><<<grid, kReduceThreads, 0, st->stream>>>((const T *)in, n, (T *)partials, counter, (T *)result_dev); break;
-        case 3: reduce_kernel<T, OP, 8, true><<<grid < cap4 ? grid : cap4, kReduceThreads, 0, st->stream>>>((const T *)in, n, (T *)partials, counter, (T *)result_dev); break;
-        case 4: reduce_kernel<T, OP, 4, false><<<cap16, kReduceThreads, 0, st->stream>>>((const T *)in, n, (T *)partials, counter, (T *)result_dev); break;
-        case 5: reduce_kernel<T, OP, 8, false><<<grid, kReduceThreads, 0, st->stream>>>((const T *)in, n, (T *)partials, counter, (T *)result_dev); break;
-        case 6: reduce_kernel<T, OP, 2, true><<<cap16, kReduceThreads, 0, st->stream>>>((const T *)in, n, (T *)partials, counter, (T *)result_dev); break;
-        case 7: reduce_kernel<T, OP, 4, false><<<grid, kReduceThreads, 0, st->stream>>>((const T *)in, n, (T *)partials, counter, (T *)result_dev); break;
-        default: break;
-        }
-        if (variant >= 1 && variant <= 7) { BCB_CUDA_TRY(cudaGetLastError()); return BCB_SUCCESS; }
-    }
     {
         // default (measured best of the variants on B200): contiguous 8 KiB chunks per CTA, 2 vectors in flight per
         // thread, 16 CTAs per SM
@@ -258,7 +209,7 @@ static int launch_reduce_cast(StreamState *st, const void *in, int in_dtype, siz
 {
     void *partials;
     BCB_TRY(scratch_reserve(st, (size_t)kMaxReduceBlocks * sizeof(A), &partials));
-    unsigned *counter = reinterpret_cast<unsigned *>(st->control + 1);
+    unsigned *counter = reinterpret_cast<unsigned *>(st->control + kControlReduceDone);
     int grid = reduce_grid(n, dtype_size(in_dtype), st->sm_count);
     LaunchTimer timer(st, BCB_K_REDUCE);
     reduce_cast_kernel<A, OP><<<grid, kReduceThreads, 0, st->stream>>>(in, in_dtype, n, (A *)partials, counter, (A *)result_dev);

@@ -318,7 +318,7 @@ int bcb_workspace_bytes(bcb_stream stream, size_t *bytes)
     BCB_CUDA_TRY(cudaGetDevice(&device));
     std::lock_guard<std::mutex> lock(g_mutex);
     auto it = g_states.find(Key{device, (cudaStream_t)stream});
-    *bytes = (it == g_states.end()) ? 0 : it->second->scratch_bytes + it->second->arena[0].bytes + it->second->arena[1].bytes;
+    *bytes = (it == g_states.end()) ? 0 : it->second->scratch_bytes + it->second->arena[0].bytes + it->second->arena[1].bytes + it->second->arena[2].bytes;
     return BCB_SUCCESS;
 }
 

@@ -196,6 +196,35 @@ BCB_API int bcb_reduce(bcb_stream stream, int in_dtype, int result_dtype, int op
 BCB_API int bcb_accumulate(bcb_stream stream, int in_dtype, int op_dtype, int acc_dtype, int op, const void *in,
                    size_t n, const void *init_host, void *result_host);
 
+
+/* ---- callers of scan and reduce with a closed, ahead-of-time compiled functor set ---- */
+/* predicate ((x ARITH a) CMP b): what `_1 < 5`, `_1 * 2 >= 10`, `_1 % 2 == 1` of the reference's lambda placeholders
+ * (lambda/placeholders.hpp) expand to; a_bits / b_bits hold a and b in the ELEMENT type's bit pattern (low bytes) */
+typedef enum bcb_arith { BCB_AR_NONE = 0, BCB_AR_MUL = 1, BCB_AR_MOD = 2, BCB_AR_ADD = 3, BCB_AR_SUB = 4, BCB_AR_AND = 5 } bcb_arith;
+typedef enum bcb_cmp { BCB_CMP_EQ = 0, BCB_CMP_NE = 1, BCB_CMP_LT = 2, BCB_CMP_LE = 3, BCB_CMP_GT = 4, BCB_CMP_GE = 5, BCB_CMP_TRUE = 6 } bcb_cmp;
+typedef struct bcb_pred { int arith; int cmp; unsigned long long a_bits; unsigned long long b_bits; } bcb_pred;
+/* unary functions (functional/: identity, negate; abs<T> = math builtin; square = _1 * _1) */
+typedef enum bcb_unary { BCB_UN_IDENTITY = 0, BCB_UN_NEGATE = 1, BCB_UN_ABS = 2, BCB_UN_SQUARE = 3 } bcb_unary;
+
+/* transform_if (algorithm/transform_if.hpp:42-85) / copy_if (copy_if.hpp: unary = identity): stable compaction of the
+ * elements satisfying pred, transformed by `unary`, in ONE pass.  *count_host = number written (the reference returns
+ * result + count, a host value: blocks).  in and out must not overlap. */
+BCB_API int bcb_transform_if(bcb_stream stream, int dtype, const void *in, size_t n, int unary, const bcb_pred *pred,
+                             void *out, size_t *count_host);
+/* count_if / count (algorithm/detail/count_if_with_reduce.hpp:27-80; count(v) = pred {NONE, EQ, v}); blocks */
+BCB_API int bcb_count_if(bcb_stream stream, int dtype, const void *in, size_t n, const bcb_pred *pred,
+                         unsigned long long *count_host);
+/* transform_reduce (algorithm/transform_reduce.hpp:40-90) and inner_product (inner_product.hpp:40-97): in2 == NULL ->
+ * reduce_op over unary(transform, in1[i]); else reduce_op over binary(transform = a bcb_op code, in1[i], in2[i]).
+ * Arithmetic in `dtype`; n == 0 leaves the result untouched; result on the host (blocks) or on the device. */
+BCB_API int bcb_transform_reduce(bcb_stream stream, int dtype, const void *in1, const void *in2, size_t n, int transform,
+                                 int reduce_op, void *result, int result_is_device);
+/* reduce_by_key (algorithm/reduce_by_key.hpp:60-118, detail/reduce_by_key_with_scan.hpp:48-97): every run of consecutive
+ * equal keys -> one (key, op-fold of its values) pair, in input order, in ONE pass.  Values: 4- and 8-byte types.
+ * *count_host = number of runs (the reference returns the pair of end iterators: blocks). */
+BCB_API int bcb_reduce_by_key(bcb_stream stream, int key_dtype, int val_dtype, const void *keys_in, const void *vals_in,
+                              size_t n, void *keys_out, void *vals_out, int op, size_t *count_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -245,3 +245,131 @@ def reduce_on_cpu_i32(x: np.ndarray, threads: int) -> int:
     out = np.zeros(1, dtype=np.int32)
     _check(lib().orc_reduce_on_cpu_i32(_ptr(x), x.size, _ptr(out), threads), "reduce_on_cpu")
     return int(out[0])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# callers of scan / reduce: numpy restatements of the SERIAL definitions the
+# reference's algorithms implement (test infrastructure, like everything in this package)
+# ---------------------------------------------------------------------------------------------------------------
+ARITH_NAMES = ["none", "mul", "mod", "add", "sub", "and"]
+CMP_NAMES = ["eq", "ne", "lt", "le", "gt", "ge", "true"]
+
+
+def _promote(x: np.ndarray) -> np.ndarray:
+    """OpenCL C integer promotion: operands narrower than int are computed in int."""
+    if x.dtype.kind in "iu" and x.dtype.itemsize < 4:
+        return x.astype(np.int32)
+    return x
+
+
+def eval_predicate(x: np.ndarray, pred) -> np.ndarray:
+    """((x ARITH a) CMP b) -- the expressions the reference's tests build from lambda placeholders
+    (test_copy_if.cpp:35-66, test_transform_if.cpp:34, test_count.cpp:69)."""
+    arith, a, cmp_, b = pred
+    arith = ARITH_NAMES[arith] if isinstance(arith, int) else arith
+    cmp_ = CMP_NAMES[cmp_] if isinstance(cmp_, int) else cmp_
+    xv = _promote(x)
+    av = _promote(np.array([a]).astype(x.dtype))[0]
+    bv = _promote(np.array([b]).astype(x.dtype))[0]
+    with np.errstate(over="ignore", divide="ignore", invalid="ignore"):
+        if arith == "mul":
+            y = xv * av
+        elif arith == "add":
+            y = xv + av
+        elif arith == "sub":
+            y = xv - av
+        elif arith == "mod":  # C remainder: sign of the dividend
+            y = np.where(av == 0, 0, np.fmod(xv, av if av != 0 else 1)).astype(xv.dtype)
+        elif arith == "and":
+            y = xv & av
+        else:
+            y = xv
+    y = y.astype(xv.dtype)
+    return {"eq": y == bv, "ne": y != bv, "lt": y < bv, "le": y <= bv, "gt": y > bv, "ge": y >= bv,
+            "true": np.ones(x.shape, bool)}[cmp_]
+
+
+def apply_unary(x: np.ndarray, name: str) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        if name == "negate":
+            return (-x).astype(x.dtype) if x.dtype.kind != "u" else (np.zeros_like(x) - x)
+        if name == "abs":
+            return np.abs(x).astype(x.dtype)
+        if name == "square":
+            return (x * x).astype(x.dtype)
+    return x.copy()
+
+
+def transform_if(x: np.ndarray, function: str, pred) -> np.ndarray:
+    """transform_if.hpp:42-117 semantics: function(x_i) for every i with predicate(x_i), in input order."""
+    x = np.ascontiguousarray(x)
+    return apply_unary(x[eval_predicate(x, pred)], function)
+
+
+def copy_if(x: np.ndarray, pred) -> np.ndarray:
+    return transform_if(x, "identity", pred)
+
+
+def count_if(x: np.ndarray, pred) -> int:
+    """count_if_with_reduce.hpp:27-80: sum of predicate(x_i) in ulong."""
+    return int(np.count_nonzero(eval_predicate(np.ascontiguousarray(x), pred)))
+
+
+def _fold(values: np.ndarray, op: str):
+    """Left fold in the array's own type (wrap-around for integers), serial_reduce.hpp:45-50."""
+    if values.size == 0:
+        return None
+    if values.dtype.kind in "iu" and op in ("plus", "multiplies"):
+        w = values.astype({1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[values.dtype.itemsize])
+        with np.errstate(over="ignore"):
+            r = np.add.reduce(w, dtype=w.dtype) if op == "plus" else np.multiply.reduce(w, dtype=w.dtype)
+        return np.array([r], dtype=w.dtype).view(values.dtype)[0]
+    if op == "plus":
+        return values.dtype.type(np.add.reduce(values.astype(np.float64))) if values.dtype.kind == "f" else None
+    if op == "multiplies":
+        return values.dtype.type(np.multiply.reduce(values.astype(np.float64)))
+    if op == "min":
+        return values.min()
+    if op == "max":
+        return values.max()
+    raise ValueError(op)
+
+
+def transform_reduce(x: np.ndarray, transform: str, reduce_op: str = "plus", y: np.ndarray | None = None):
+    """transform_reduce.hpp:40-90: reduce(transform_iterator(first, transform) ...).  Floating-point sums are returned
+    from a float64 fold (compare with a tolerance)."""
+    x = np.ascontiguousarray(x)
+    if y is None:
+        t = apply_unary(x, transform)
+    else:
+        y = np.ascontiguousarray(y)[: x.size]
+        with np.errstate(over="ignore"):
+            t = {"plus": x + y, "minus": x - y, "multiplies": x * y, "min": np.minimum(x, y), "max": np.maximum(x, y)}[transform].astype(x.dtype)
+    return _fold(t, reduce_op)
+
+
+def inner_product(x: np.ndarray, y: np.ndarray, init):
+    """inner_product.hpp:40-64: init + sum of x_i * y_i, in the value type."""
+    r = transform_reduce(x, "multiplies", "plus", y)
+    init_v = np.array([init]).astype(x.dtype)[0]
+    if r is None:
+        return init_v
+    with np.errstate(over="ignore"):
+        return x.dtype.type(init_v + r)
+
+
+def reduce_by_key(keys: np.ndarray, values: np.ndarray, op: str = "plus"):
+    """reduce_by_key.hpp:60-118 (serial definition, detail/serial_reduce_by_key.hpp): every run of consecutive equal
+    keys -> (key, left fold of its values).  Float sums fold in float64 and are rounded once (compare with tolerance)."""
+    keys = np.ascontiguousarray(keys)
+    values = np.ascontiguousarray(values)[: keys.size]
+    if keys.size == 0:
+        return keys[:0].copy(), values[:0].copy()
+    heads = np.ones(keys.size, bool)
+    heads[1:] = ~(keys[1:] == keys[:-1])
+    starts = np.flatnonzero(heads)
+    ends = np.append(starts[1:], keys.size)
+    out_v = np.empty(starts.size, dtype=values.dtype)
+    for j, (s0, e0) in enumerate(zip(starts, ends)):
+        out_v[j] = _fold(values[s0:e0], op)
+    return keys[starts].copy(), out_v

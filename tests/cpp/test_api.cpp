@@ -411,6 +411,84 @@ static void test_array_and_mapped_view(compute::command_queue &queue)
     CHECK(sums[0] == 1 && sums[999] == 1000);
 }
 
+// callers of scan / reduce: the reference's own test literals
+static void test_scan_and_reduce_callers(compute::command_queue &queue)
+{
+    using compute::_1;
+    compute::context context = queue.get_context();
+    {   // test_copy_if.cpp:24-46
+        int data[] = { 1, 6, 3, 5, 8, 2, 4 };
+        compute::vector<int> input(data, data + 7, queue);
+        compute::vector<int> output(input.size(), context);
+        compute::fill(output.begin(), output.end(), -1, queue);
+        compute::vector<int>::iterator iter = compute::copy_if(input.begin(), input.end(), output.begin(), _1 < 5, queue);
+        CHECK(iter == output.begin() + 4);
+        CHECK(to_host(output, queue) == (std::vector<int>{1, 3, 2, 4, -1, -1, -1}));
+        compute::fill(output.begin(), output.end(), 42, queue);
+        iter = compute::copy_if(input.begin(), input.end(), output.begin(), _1 * 2 >= 10, queue);
+        CHECK(iter == output.begin() + 3);
+        CHECK(to_host(output, queue) == (std::vector<int>{6, 5, 8, 42, 42, 42, 42}));
+    }
+    {   // test_copy_if.cpp:48-68
+        int data[] = { 1, 2, 3, 4, 5, 1, 2, 3, 4, 5 };
+        compute::vector<int> input(data, data + 10, queue);
+        compute::vector<int> odds(input.size(), context);
+        CHECK(compute::copy_if(input.begin(), input.end(), odds.begin(), _1 % 2 == 1, queue) == odds.begin() + 6);
+        std::vector<int> h = to_host(odds, queue);
+        CHECK((std::vector<int>(h.begin(), h.begin() + 6) == std::vector<int>{1, 3, 5, 1, 3, 5}));
+    }
+    {   // test_transform_if.cpp:23-39
+        int data[] = { -2, -3, -4, -5, -6, -7, -8, -9 };
+        compute::vector<int> input(data, data + 8, queue);
+        compute::vector<int> output(input.size(), context);
+        compute::vector<int>::iterator end = compute::transform_if(input.begin(), input.end(), output.begin(), compute::abs<int>(), _1 % 2 != 0, queue);
+        CHECK(end - output.begin() == 4);
+        std::vector<int> h = to_host(output, queue);
+        CHECK((std::vector<int>(h.begin(), h.begin() + 4) == std::vector<int>{3, 5, 7, 9}));
+    }
+    {   // test_count.cpp:32-42, :63-72
+        int data[] = { 1, 2, 1, 2, 3 };
+        compute::vector<int> v(data, data + 5, queue);
+        CHECK(compute::count(v.begin(), v.end(), 1, queue) == 2u);
+        CHECK(compute::count(v.begin(), v.end(), 3, queue) == 1u);
+        CHECK(compute::count(v.begin() + 1, v.end(), 1, queue) == 1u);
+        CHECK(compute::count(v.begin() + 1, v.end() - 1, 2, queue) == 2u);
+        float fdata[] = { 1.0f, 2.5f, -1.0f, 3.0f, 5.0f };
+        compute::vector<float> f(fdata, fdata + 5, queue);
+        CHECK(compute::count_if(f.begin(), f.end(), _1 > 2.0f, queue) == 3u);
+    }
+    {   // test_inner_product.cpp:23-37, test_transform_reduce.cpp:24-40
+        int d1[] = { 1, 2, 3, 4 }, d2[] = { 10, 20, 30, 40 };
+        compute::vector<int> a(d1, d1 + 4, queue), b(d2, d2 + 4, queue);
+        CHECK(compute::inner_product(a.begin(), a.end(), b.begin(), 0, queue) == 300);
+        int d3[] = { 1, -2, -3, -4, 5 };
+        compute::vector<int> c(d3, d3 + 5, queue);
+        int sum = 0;
+        compute::transform_reduce(c.begin(), c.end(), &sum, compute::abs<int>(), compute::plus<int>(), queue);
+        CHECK(sum == 15);
+        compute::vector<int> dev_result(1, context);
+        compute::transform_reduce(c.begin(), c.end(), dev_result.begin(), compute::square<int>(), compute::plus<int>(), queue);
+        CHECK(to_host(dev_result, queue)[0] == 55);
+    }
+    {   // test_reduce_by_key.cpp:26-46, :108-132
+        int keys[] = { 0, 2, -3, -3, -3, -3, -3, 4 };
+        int data[] = { 1, 1, 1, 1, 1, 2, 5, 1 };
+        compute::vector<int> k(keys, keys + 8, queue), v(data, data + 8, queue), ko(8, context), vo(8, context);
+        std::pair<compute::vector<int>::iterator, compute::vector<int>::iterator> r =
+            compute::reduce_by_key(k.begin(), k.end(), v.begin(), ko.begin(), vo.begin(), queue);
+        CHECK(r.first == ko.begin() + 4 && r.second == vo.begin() + 4);
+        std::vector<int> hk = to_host(ko, queue), hv = to_host(vo, queue);
+        CHECK((std::vector<int>(hk.begin(), hk.begin() + 4) == std::vector<int>{0, 2, -3, 4}));
+        CHECK((std::vector<int>(hv.begin(), hv.begin() + 4) == std::vector<int>{1, 1, 10, 1}));
+        int keys2[] = { 0, 2, 2, 3, 3, 3, 3, 3, 4 };
+        int data2[] = { 1, 2, 1, -3, 1, 4, 2, 5, 77 };
+        compute::vector<int> k2(keys2, keys2 + 9, queue), v2(data2, data2 + 9, queue), ko2(9, context), vo2(9, context);
+        compute::reduce_by_key(k2.begin(), k2.end(), v2.begin(), ko2.begin(), vo2.begin(), compute::min<int>(), compute::equal_to<int>(), queue);
+        hv = to_host(vo2, queue);
+        CHECK((std::vector<int>(hv.begin(), hv.begin() + 4) == std::vector<int>{1, 1, -3, 77}));
+    }
+}
+
 int main()
 {
     try {
@@ -423,6 +501,7 @@ int main()
         test_scan(queue);
         test_reduce_accumulate(queue);
         test_array_and_mapped_view(queue);
+        test_scan_and_reduce_callers(queue);
         queue.finish();
     } catch(std::exception &e) {
         std::printf("EXCEPTION: %s\n", e.what());

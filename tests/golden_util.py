@@ -147,7 +147,61 @@ def check_case(c, api):
             exp = adt(c["expected"])
         assert adt(got) == exp, (c["ref"], got, exp)
         return
+    if fn in ("copy_if", "transform_if"):
+        x = _expand_input(c)
+        pred = tuple(c["pred"])
+        if _accepts(api.transform_if, "fill"):  # GPU adapter: output buffer pre-filled, tail must stay untouched
+            out, count = api.transform_if(x, c.get("function", "identity"), pred, fill=c["fill"])
+        else:
+            sel = api.transform_if(x, c.get("function", "identity"), pred)
+            count = len(sel)
+            out = np.full(x.size, c["fill"], dtype=x.dtype)
+            out[:count] = sel
+        assert count == c["count"], (c["ref"], count)
+        np.testing.assert_array_equal(out, np.array(c["expected"], dtype=x.dtype), err_msg=c["ref"])  # untouched tail included
+        return
+    if fn in ("count", "count_if"):
+        x = _expand_input(c)
+        if "sub_range" in c:
+            lo, hi = c["sub_range"]
+            x = x[lo:hi]
+        pred = ("none", 0, "eq", c["value"]) if fn == "count" else tuple(c["pred"])
+        assert api.count_if(x, pred) == c["expected"], c["ref"]
+        return
+    if fn == "inner_product":
+        x = _expand_input(c)
+        y = _expand_input({"dtype": c["dtype"], "gen": c["input2_gen"]}) if "input2_gen" in c else np.array(c["input2"], dtype=x.dtype)
+        assert api.inner_product(x, y, c["init"]) == x.dtype.type(c["expected"]), c["ref"]
+        return
+    if fn == "transform_reduce":
+        x = _expand_input(c)
+        assert api.transform_reduce(x, c["transform"], c["op"]) == x.dtype.type(c["expected"]), c["ref"]
+        return
+    if fn == "reduce_by_key":
+        kd, vd = NP[c["dtype"]], NP[c["value_dtype"]]
+        keys = _expand_gen(c["keys_gen"], kd) if "keys_gen" in c else np.array(c["keys"], dtype=kd)
+        vals = _expand_gen(c["values_gen"], vd) if "values_gen" in c else np.array(c["values"], dtype=vd)
+        gk, gv = api.reduce_by_key(keys, vals, c["op"])
+        np.testing.assert_array_equal(gk, np.array(c["expected_keys"], dtype=kd), err_msg=c["ref"])
+        if np.dtype(vd).kind == "f":
+            np.testing.assert_allclose(gv, np.array(c["expected_values"], dtype=vd), rtol=1e-6, err_msg=c["ref"])  # BOOST_CHECK_CLOSE 1e-4 %
+        else:
+            np.testing.assert_array_equal(gv, np.array(c["expected_values"], dtype=vd), err_msg=c["ref"])
+        return
     raise ValueError(fn)
+
+
+def _expand_gen(g, dtype):
+    n = g["n"]
+    if g["kind"] == "fill":
+        return np.full(n, g["value"], dtype=dtype)
+    if g["kind"] == "iota":
+        return (np.arange(n) + g.get("start", 0)).astype(dtype)
+    if g["kind"] == "steps":  # zeros with ones at the given positions, then an inclusive scan (test_reduce_by_key.cpp:63-66)
+        k = np.zeros(n, dtype=dtype)
+        k[g["at"]] = 1
+        return np.cumsum(k).astype(dtype)
+    raise ValueError(g["kind"])
 
 
 def _accepts(f, name):

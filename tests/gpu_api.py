@@ -143,3 +143,47 @@ def is_sorted(keys, descending=False):
 
 
 _ = (NP_OF_CODE, dtype_code)
+
+
+# ---- callers of scan / reduce ----
+def _pred(pred):
+    arith, a, cmp_, b = pred
+    return cb.predicate(cmp_ if isinstance(cmp_, str) else cb.algorithm.CMP_NAMES[cmp_], b,
+                        arith if isinstance(arith, str) else cb.algorithm.ARITH_NAMES[arith], a)
+
+
+def transform_if(x, function, pred, fill=0):
+    """Returns (whole output buffer -- pre-filled with `fill`, so an overrun past the count shows --, count)."""
+    x = np.ascontiguousarray(x)
+    d_in = to_dev(x)
+    d_out = to_dev(np.full(x.size, fill, dtype=x.dtype))
+    count = cb.transform_if(d_in, d_out, function, _pred(pred))
+    torch.cuda.synchronize()
+    return to_host(d_out, x.dtype), count
+
+
+def copy_if(x, pred, fill=0):
+    return transform_if(x, "identity", pred, fill)
+
+
+def count_if(x, pred):
+    return cb.count_if(to_dev(np.ascontiguousarray(x)), _pred(pred))
+
+
+def transform_reduce(x, transform, reduce_op="plus", y=None):
+    x = np.ascontiguousarray(x)
+    return cb.transform_reduce(to_dev(x), transform, reduce_op, None if y is None else to_dev(np.ascontiguousarray(y)))
+
+
+def inner_product(x, y, init):
+    return cb.inner_product(to_dev(np.ascontiguousarray(x)), to_dev(np.ascontiguousarray(y)), init)
+
+
+def reduce_by_key(keys, values, op="plus"):
+    keys, values = np.ascontiguousarray(keys), np.ascontiguousarray(values)
+    dk, dv = to_dev(keys), to_dev(values)
+    ok = to_dev(np.zeros(keys.size, dtype=keys.dtype))
+    ov = to_dev(np.zeros(keys.size, dtype=values.dtype))
+    m = cb.reduce_by_key(dk, dv, ok, ov, op)
+    torch.cuda.synchronize()
+    return to_host(ok, keys.dtype)[:m], to_host(ov, values.dtype)[:m]

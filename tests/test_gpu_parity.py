@@ -558,3 +558,93 @@ def test_scan_descriptor_arenas_do_not_alias(gpu):
     )
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ARENAS_OK" in out.stdout, out.stdout + out.stderr
+
+
+# ------------------------------------------------------------------ round 2: callers of scan / reduce
+PREDS = [("none", 0, "lt", 5), ("mul", 2, "ge", 10), ("mod", 2, "eq", 1), ("mod", 3, "ne", 0), ("and", 5, "eq", 4), ("add", 3, "gt", 0),
+         ("sub", 7, "le", -2), ("none", 0, "true", 0)]
+
+
+@pytest.mark.parametrize("dtype", ["char", "uchar", "short", "int", "uint", "long", "ulong", "float", "double"])
+def test_transform_if_copy_if_count_if_bit_exact(dtype, gpu):
+    """One-pass stable compaction vs the serial definition (transform_if.hpp:42-117): empty, one tile, many tiles
+    (look-back), nothing / everything selected, the output tail past the count stays untouched."""
+    npdt = np.dtype(NPD[dtype])
+    rng = np.random.default_rng(31)
+    for n in (0, 1, 31, 4096, 4097, 100_003, 1_500_001):
+        if npdt.kind == "f":
+            x = (rng.integers(-40, 40, size=n) / 2.0).astype(npdt)
+        else:
+            lo = -20 if npdt.kind == "i" else 0
+            x = rng.integers(lo, 20, size=n).astype(npdt)
+        for pred in PREDS:
+            if npdt.kind == "f" and pred[0] in ("mod", "and"):
+                continue
+            if npdt.kind == "u" and pred[3] < 0:
+                continue
+            fn = ["identity", "negate", "abs", "square"][(n + len(pred[0])) % 4]
+            exp = oracle.transform_if(x, fn, pred)
+            out, count = gpu.transform_if(x, fn, pred, fill=77)
+            assert count == exp.size == gpu.count_if(x, pred) == oracle.count_if(x, pred), (dtype, n, pred)
+            assert out[:count].tobytes() == exp.tobytes(), (dtype, n, pred, fn)
+            assert np.all(out[count:] == npdt.type(77)), "wrote past the selected count"
+
+
+@pytest.mark.parametrize("dtype", ["char", "ushort", "int", "uint", "long", "ulong"])
+def test_transform_reduce_inner_product_integer_bit_exact(dtype, gpu):
+    npdt = np.dtype(NPD[dtype])
+    rng = np.random.default_rng(32)
+    for n in (1, 255, 100_003, 3_000_001):
+        x = rng.integers(0, 2**(8 * npdt.itemsize), size=n, dtype=np.uint64).astype({1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[npdt.itemsize]).view(npdt)
+        y = rng.integers(0, 2**(8 * npdt.itemsize), size=n, dtype=np.uint64).astype({1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[npdt.itemsize]).view(npdt)
+        for t in ("identity", "negate", "abs", "square"):
+            for op in ("plus", "min", "max"):
+                assert gpu.transform_reduce(x, t, op) == oracle.transform_reduce(x, t, op), (dtype, n, t, op)
+        for t in ("multiplies", "plus", "minus"):
+            assert gpu.transform_reduce(x, t, "plus", y) == oracle.transform_reduce(x, t, "plus", y), (dtype, n, t)
+        assert gpu.inner_product(x, y, 5) == oracle.inner_product(x, y, 5)
+    assert gpu.transform_reduce(np.empty(0, npdt), "abs", "plus") is None
+    assert gpu.inner_product(np.empty(0, npdt), np.empty(0, npdt), 9) == npdt.type(9)
+
+
+@pytest.mark.parametrize("dtype", ["float", "double"])
+def test_transform_reduce_inner_product_float_tolerance(dtype, gpu):
+    npdt = np.dtype(NPD[dtype])
+    eps = 2.0**-24 if dtype == "float" else 2.0**-53
+    rng = np.random.default_rng(33)
+    n = 2_000_003
+    x = rng.uniform(-1, 1, size=n).astype(npdt)
+    y = rng.uniform(-1, 1, size=n).astype(npdt)
+    tol = 4 * math.ceil(math.log2(n)) * eps
+    exact = float(np.sum(np.abs(x.astype(np.float64))))
+    assert abs(float(gpu.transform_reduce(x, "abs", "plus")) - exact) <= tol * exact
+    prod = x.astype(np.float64) * y.astype(np.float64)
+    got = float(gpu.inner_product(x, y, 0.5))
+    assert abs(got - (0.5 + float(prod.sum()))) <= tol * float(np.abs(prod).sum()) + eps
+    assert float(gpu.transform_reduce(x, "square", "max")) == float(np.max(x * x))
+    assert gpu.transform_reduce(x, "identity", "plus", None) == gpu.transform_reduce(x, "identity", "plus", None)  # deterministic
+
+
+@pytest.mark.parametrize("key_dtype", ["uchar", "int", "ulong", "float"])
+@pytest.mark.parametrize("val_dtype", ["int", "uint", "long", "float", "double"])
+def test_reduce_by_key_matches_serial_definition(key_dtype, val_dtype, gpu):
+    """Segmented one-pass reduction vs the serial definition: runs inside a thread, across threads / warps / tiles
+    (carry through the look-back, including tiles without any segment head), single run, all runs of length 1."""
+    kd, vd = np.dtype(NPD[key_dtype]), np.dtype(NPD[val_dtype])
+    rng = np.random.default_rng(34)
+    for n, mean_run in ((1, 1), (2047, 3), (2048, 1), (2049, 5000), (300_001, 40), (1_000_003, 30_000), (500_000, 1)):
+        runs = np.maximum(1, rng.geometric(1.0 / mean_run, size=n // mean_run + 2))
+        ids = np.repeat(np.arange(runs.size), runs)[:n]
+        palette = rng.permutation(251)  # key values repeat along the range (non-adjacent equal keys stay separate runs)
+        keys = palette[ids % 251].astype(kd)
+        if vd.kind == "f":
+            vals = (rng.integers(-8, 9, size=n) / 4.0).astype(vd)  # exactly representable: sums are order independent
+        else:
+            vals = rng.integers(-9 if vd.kind == "i" else 0, 10, size=n).astype(vd)
+        for op in ("plus", "min", "max"):
+            ek, ev = oracle.reduce_by_key(keys, vals, op)
+            gk, gv = gpu.reduce_by_key(keys, vals, op)
+            assert gk.tobytes() == ek.tobytes(), (key_dtype, val_dtype, n, mean_run, op)
+            assert gv.tobytes() == ev.tobytes(), (key_dtype, val_dtype, n, mean_run, op)
+    gk, gv = gpu.reduce_by_key(np.empty(0, kd), np.empty(0, vd))
+    assert gk.size == 0 and gv.size == 0
