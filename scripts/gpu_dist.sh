@@ -4,9 +4,9 @@ N=${1:-2}
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 echo "== dist_check N=$N (peer-memory plan)"
-timeout 600 $TR --master-port 29511 scripts/dist_check.py > gpurun_out/dist_check_$N.log 2>&1; echo "rc=$?"; grep -E "OK|MISMATCH|DIST_CHECK|Error|error" gpurun_out/dist_check_$N.log | cut -c1-260 | tail -20
+timeout 600 $TR --master-port 29511 tests/dist_check_worker.py > gpurun_out/dist_check_$N.log 2>&1; echo "rc=$?"; grep -E "OK|MISMATCH|DIST_CHECK|Error|error" gpurun_out/dist_check_$N.log | cut -c1-260 | tail -20
 echo "== dist_check N=$N (NCCL all-to-all plan)"
-BCB_DIST_PEER=0 timeout 600 $TR --master-port 29512 scripts/dist_check.py > gpurun_out/dist_check_nccl_$N.log 2>&1; echo "rc=$?"; grep -E "DIST_CHECK|Error|error" gpurun_out/dist_check_nccl_$N.log | cut -c1-200 | tail -5
+BCB_DIST_PEER=0 timeout 600 $TR --master-port 29512 tests/dist_check_worker.py > gpurun_out/dist_check_nccl_$N.log 2>&1; echo "rc=$?"; grep -E "DIST_CHECK|Error|error" gpurun_out/dist_check_nccl_$N.log | cut -c1-200 | tail -5
 for mode in peer nccl; do
   if [ $mode = nccl ]; then export BCB_DIST_PEER=0; else export BCB_DIST_PEER=1; fi
   echo "== bench sort_u32 N=$N plan=$mode"

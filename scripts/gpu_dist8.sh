@@ -5,7 +5,7 @@ for N in 8 4; do
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 if [ $N = 8 ]; then
 echo "== dist_check N=$N"
-timeout 600 $TR --master-port 29511 scripts/dist_check.py > gpurun_out/dist_check_$N.log 2>&1; echo "rc=$?"; grep -E "OK|MISMATCH|DIST_CHECK|rror" gpurun_out/dist_check_$N.log | cut -c1-230 | tail -20
+timeout 600 $TR --master-port 29511 tests/dist_check_worker.py > gpurun_out/dist_check_$N.log 2>&1; echo "rc=$?"; grep -E "OK|MISMATCH|DIST_CHECK|rror" gpurun_out/dist_check_$N.log | cut -c1-230 | tail -20
 fi
 echo "== bench sort_u32 N=$N"
 timeout 600 $TR --master-port 29513 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_sort_u32_N${N}_peer.json 2> gpurun_out/bench_N${N}_peer.err

@@ -18,4 +18,4 @@ python - <<PY
 import json
 d=json.loads(open('gpurun_out/bench_prof_N8_peer.json').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d.get('distributed'))
 PY
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29515 scripts/dist_check.py 2>&1 | grep -E "MISMATCH|DIST_CHECK|rror" | head -5
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29515 tests/dist_check_worker.py 2>&1 | grep -E "MISMATCH|DIST_CHECK|rror" | head -5

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Multi-GPU parity check, run under torchrun (one rank per GPU):
-   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P scripts/dist_check.py
+"""Multi-GPU parity check (worker of tests/test_gpu_distributed.py), run under torchrun (one rank per GPU):
+   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tests/dist_check_worker.py
 Every distributed result must equal the single-GPU result bit for bit (rank 0 recomputes on one GPU and, for small
 sizes, against the CPU oracle)."""
 import os
@@ -40,7 +40,8 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
     ctx = cbd.Context()
     ok = True
-    for n_total, dt, vb, desc in ((1 << 22, torch.uint32, 0, False), (1 << 21, torch.float32, 0, True), (1 << 21, torch.int32, 8, False),
+    # (the first case gives every rank >= 2^23 keys: the local sorts take the warp-specialised pass kernel)
+    for n_total, dt, vb, desc in (((1 << 23) * world + 12345, torch.uint32, 0, False), (1 << 22, torch.uint32, 0, False), (1 << 21, torch.float32, 0, True), (1 << 21, torch.int32, 8, False),
                                   (100_003, torch.uint64, 4, True), (1 << 20, torch.int16, 0, False)):
         g = torch.Generator(device="cuda"); g.manual_seed(7)
         if dt == torch.float32:
