@@ -94,6 +94,34 @@ __global__ void partition_points_kernel(const K *__restrict__ keys, size_t n, co
     points[j] = lo;
 }
 
+// transformed key in the key's own compute width, and its inverse (all transforms except descending float / double,
+// which is not injective -- radix_sort.hpp:100-127 -- and never takes this path)
+template <typename K>
+__device__ __forceinline__ typename key_traits<K>::U transform_fwd(K raw, const Transform &tf)
+{
+    typedef typename key_traits<K>::U U;
+    typedef typename key_traits<K>::S S;
+    const U x = (U)raw;
+    const U nm = (U)tf.nm;
+    const U neg = (U)((S)x >> (sizeof(U) * 8 - 1));
+    return ((x ^ nm) - nm) ^ (U)tf.xc ^ (neg & (U)tf.fa);
+}
+template <typename K>
+__device__ __forceinline__ K transform_inv(typename key_traits<K>::U t, const Transform &tf)
+{
+    typedef typename key_traits<K>::U U;
+    if (tf.fa) {  // ascending float: originally non-negative keys carry the sign bit now
+        const U sign = (U)tf.xc;
+        return (K)((t & sign) ? (t ^ sign) : ~t);
+    }
+    const U nm = (U)tf.nm;
+    return (K)(((t ^ (U)tf.xc) + nm) ^ nm);
+}
+// what a pass does with the key transform: kXfNone -- the keys in memory are already in sortable (transformed or
+// unsigned-ascending) form; kXfIn -- first pass: transform on load, store transformed; kXfOut -- last pass: store the
+// original bit pattern again; kXfBoth -- transform only to extract the digit (keys stay raw in memory)
+enum { kXfNone = 0, kXfIn = 1, kXfOut = 2, kXfBoth = 3 };
+
 // digit modes of the pass kernel: plain bit field (unsigned ascending), transformed bit field, splitter bucket
 enum { kDigitIdent = 1, kDigitTransform = 0, kDigitSplit = 2 };
 
@@ -124,10 +152,12 @@ __device__ __forceinline__ unsigned pass_digit(K raw, int shift, const Transform
 }
 
 
-// warp-specialised bulk-copy pass kernel (radix_pass_ws.cu): large keys-only sorts of 32- / 64-bit keys, speculative
-// two-sweep ranking.  Returns BCB_EUNSUPPORTED for shapes it does not cover (arrays not 16-byte aligned).
-int ws_launch_pass(StreamState *st, int key_bytes, const void *kin, void *kout, const unsigned *base, unsigned long long *lookback,
-                   size_t n, int shift, const Transform &tf);
-size_t ws_tile_size(int key_bytes);
+// warp-specialised bulk-copy pass kernel (radix_pass_ws.cu): large sorts.  Keys only (32- / 64-bit) with the speculative
+// two-sweep ranking; 32-bit keys + 4- / 8-byte payload, or keys only with a non-injective transform, with the
+// deterministic atomic-OR ranking.  Returns BCB_EUNSUPPORTED for shapes it does not cover (arrays not 16-byte aligned).
+int ws_launch_pass(StreamState *st, int key_bytes, const void *kin, void *kout, const void *vin, void *vout, int value_bytes,
+                   const unsigned *base, unsigned long long *lookback, size_t n, int shift, const Transform &tf, int xf, bool deterministic);
+size_t ws_tile_size(int key_bytes, int value_bytes, bool deterministic);
+bool ws_supports(int key_bytes, int value_bytes, bool deterministic);
 
 }  // namespace bcb

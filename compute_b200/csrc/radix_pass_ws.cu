@@ -57,47 +57,68 @@ constexpr unsigned kWsNoTile = 0xffffffffu;
 // named barriers (0 is __syncthreads); p = parity of the tile's sequence number inside the CTA
 enum { kBarCounted = 1 /* +p */, kBarOffsets = 3 /* +p */, kBarScattered = 5, kBarDrained = 6, kBarHelpers = 7, kBarWorkers = 8 };
 
-template <typename K> struct WsShape {
-    static constexpr int A = 16 / (int)sizeof(K);          // keys per 16-byte chunk
-    static constexpr int ITEMS = 224 / (int)sizeof(K);     // keys per worker thread: 168 KB tiles
-    static constexpr int CHUNK = 56 / (int)sizeof(K);      // keys a worker holds in registers at a time (+ as many in flight)
-    static constexpr int SEG = ITEMS * 32;                 // keys per worker warp (one contiguous segment)
-    static constexpr int TILE = kWsWorkers * ITEMS;        // 43008 (u32) / 21504 (u64)
+template <int VB> struct ws_value { typedef unsigned type; };
+template <> struct ws_value<8> { typedef unsigned long long type; };
+
+// K: key type, VB: payload bytes (0, 4, 8), DET: deterministic ranking (peer masks by atomicOr; needs a mask table)
+template <typename K, int VB, bool DET> struct WsShape {
+    static constexpr int KB = (int)sizeof(K);
+    static constexpr int MINB = VB ? (VB < KB ? VB : KB) : KB;
+    static constexpr int A = 16 / MINB;  // elements per 16-byte chunk of the NARROWER array: run starts aligned to A elements are 16-byte aligned in both
+    // elements per worker thread: what fits next to the tables
+    static constexpr int ITEMS = VB == 0 ? (DET ? 192 / KB : 224 / KB) : (KB + VB == 8 ? 24 : 16);
+    static constexpr int CHUNK = VB == 0 ? (DET ? 48 : 56) / KB : (VB == 4 ? 8 : 4);  // elements a worker holds in registers at a time (+ as many in flight)
+    static constexpr int SEG = ITEMS * 32;                 // elements per worker warp (one contiguous segment)
+    static constexpr int TILE = kWsWorkers * ITEMS;        // 43008 u32 keys / 21504 u64 keys / 18432 u32+u32 pairs / 12288 u32+u64 pairs
     static constexpr int PAD = (A - 1) * kRadixSize;       // alignment shifts: run d starts (A-1)*d + [0, A) later
-    static constexpr size_t BUF_BYTES = (size_t)(TILE + PAD) * sizeof(K);
+    static constexpr size_t KBUF_BYTES = (size_t)(TILE + PAD) * KB;
+    static constexpr size_t VBUF_BYTES = (size_t)(TILE + PAD) * VB;
     static constexpr size_t TAB_BYTES = 2 * (size_t)kWsWorkerWarps * kRadixSize * sizeof(unsigned);  // [2][24][256]
+    static constexpr size_t MASK_BYTES = DET ? (size_t)kWsWorkerWarps * kRadixSize * sizeof(unsigned) : 0;  // [24][256]
     static constexpr size_t MISC_BYTES = 128;
-    static constexpr size_t SMEM_BYTES = BUF_BYTES + TAB_BYTES + MISC_BYTES;
-    static_assert(BUF_BYTES % 128 == 0, "the tables stay aligned");
+    static constexpr size_t SMEM_BYTES = KBUF_BYTES + VBUF_BYTES + TAB_BYTES + MASK_BYTES + MISC_BYTES;
+    static_assert(KBUF_BYTES % 128 == 0 && VBUF_BYTES % 128 == 0, "the buffers and tables stay aligned");
     static_assert(ITEMS % CHUNK == 0, "whole chunks");
     static_assert(SMEM_BYTES <= 232448, "one CTA per SM: 227 KB of shared memory");
 };
 
-template <typename K, int IDENT, int LB>
+template <typename K, int VB, bool DET, int XF, int LB>
 __global__ void __launch_bounds__(kWsThreads, 1)
-onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const unsigned *__restrict__ digit_base,
-            unsigned long long *lookback, unsigned epoch, size_t n, unsigned num_tiles, int shift,
+onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *__restrict__ vals_in_v, void *__restrict__ vals_out_v,
+            const unsigned *__restrict__ digit_base, unsigned long long *lookback, unsigned epoch, size_t n, unsigned num_tiles, int shift,
             const __grid_constant__ Transform tf, unsigned long long *ticket, unsigned long long ticket_base, int flags)
 {
-    typedef WsShape<K> C;
+    typedef WsShape<K, VB, DET> C;
+    typedef typename ws_value<VB>::type V;
+    static_assert(VB == 0 || DET, "a payload needs the deterministic ranking (its stability cannot be verified afterwards)");
+    const V *vals_in = reinterpret_cast<const V *>(vals_in_v);
+    V *vals_out = reinterpret_cast<V *>(vals_out_v);
     constexpr int ITEMS = C::ITEMS, TILE = C::TILE, A = C::A, SEG = C::SEG, CHUNK = C::CHUNK;
     constexpr int ROW = kRadixSize;  // words per (warp, tile) table row.  (16-bit counters packed two per word would let
                                      // the tile grow to 49152 keys, but measured 4.0 instead of 3.35 wavefronts per atomic:
                                      // twice as many lanes share a word -- and five more ALU instructions per key)
     extern __shared__ __align__(128) unsigned char smem[];
     K *buf = reinterpret_cast<K *>(smem);
-    unsigned *tab = reinterpret_cast<unsigned *>(smem + C::BUF_BYTES);                          // [2][24][ROW]
-    volatile unsigned *ring = reinterpret_cast<volatile unsigned *>(smem + C::BUF_BYTES + C::TAB_BYTES);  // [4] tile ids
+    V *vbuf = reinterpret_cast<V *>(smem + C::KBUF_BYTES);                                      // payload, same positions as the keys
+    unsigned *tab = reinterpret_cast<unsigned *>(smem + C::KBUF_BYTES + C::VBUF_BYTES);         // [2][24][ROW]
+    unsigned *masks = tab + 2 * kWsWorkerWarps * ROW;                                           // [24][ROW] (DET only)
+    volatile unsigned *ring = reinterpret_cast<volatile unsigned *>(smem + C::KBUF_BYTES + C::VBUF_BYTES + C::TAB_BYTES + C::MASK_BYTES);  // [4] tile ids
     unsigned *hscan = const_cast<unsigned *>(ring) + 4;                                        // [2][8] helper warp sums
     const unsigned tid = threadIdx.x;
 
-    for (unsigned i = tid; i < 2 * kWsWorkerWarps * ROW; i += kWsThreads) tab[i] = 0;
+    for (unsigned i = tid; i < (DET ? 3 : 2) * kWsWorkerWarps * ROW; i += kWsThreads) tab[i] = 0;  // (the mask table follows the count tables)
     __syncthreads();
 
     if (tid < kWsWorkers) {
         // ======================= workers: counting sweep, scatter sweep =======================
         const unsigned w = tid >> 5, lane = tid & 31u;
         const unsigned long long keep = l2_policy_evict_last(), drop = l2_policy_evict_first();
+        typedef typename key_traits<K>::U U;
+        // keys travel between the passes in sortable form: transformed once by the first pass (kXfIn), turned back into
+        // the original bit pattern by the last one (kXfOut); in between the digit is a plain bit field
+        auto sortable = [&](K raw) -> U { return (XF == kXfIn || XF == kXfBoth) ? transform_fwd<K>(raw, tf) : (U)raw; };
+        auto digit = [&](U t) -> unsigned { return (unsigned)(t >> shift) & (kRadixSize - 1); };
+        auto stored = [&](K raw, U t) -> K { return XF == kXfOut ? transform_inv<K>(t, tf) : (XF == kXfIn ? (K)t : raw); };
         WS_PROF_DECL;
         auto draw = [&](unsigned i) {  // tile id of the CTA's i-th tile -> ring[i & 3], visible after the workers' barrier
             if (tid == 0) {
@@ -120,8 +141,9 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const unsig
                 // any order inside the warp's segment: 128-bit loads, a window of WIN per lane in flight.  The lines are
                 // asked to STAY in L2 (evict_last): the scatter sweep reads them again one tile later.
                 const uint4 *src = reinterpret_cast<const uint4 *>(keys_in + base) + lane;
-                constexpr int NV = SEG / A / 32, WIN = 7;  // vectors per lane
-                static_assert(NV % WIN == 0, "whole windows");
+                constexpr int VECK = 16 / (int)sizeof(K);                                     // keys per 128-bit vector
+                constexpr int NV = SEG / VECK / 32;                                           // vectors per lane
+                constexpr int WIN = NV % 7 == 0 ? 7 : (NV % 6 == 0 ? 6 : (NV % 4 == 0 ? 4 : 1));  // vectors in flight per lane
                 uint4 v[WIN];
 #pragma unroll
                 for (int u = 0; u < WIN; u++) v[u] = ld_hint_v4(src + u * 32, keep);
@@ -129,7 +151,7 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const unsig
                 for (int j = 0; j < NV; j++) {
                     const K *e = reinterpret_cast<const K *>(&v[j % WIN]);
 #pragma unroll
-                    for (int c = 0; c < A; c++) atomicAdd(&row[pass_digit<K, IDENT>(e[c], shift, tf)], 1u);
+                    for (int c = 0; c < VECK; c++) atomicAdd(&row[digit(sortable(e[c]))], 1u);
                     if (j + WIN < NV) v[j % WIN] = ld_hint_v4(src + (j + WIN) * 32, keep);
                 }
             } else {
@@ -137,7 +159,7 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const unsig
                 for (int i = 0; i < ITEMS; i++) {
                     const size_t idx = base + (size_t)i * 32 + lane;
                     // padding counts as digit 255: sorts last
-                    atomicAdd(&row[idx < n ? pass_digit<K, IDENT>(__ldg(keys_in + idx), shift, tf) : (unsigned)(kRadixSize - 1)], 1u);
+                    atomicAdd(&row[idx < n ? digit(sortable(__ldg(keys_in + idx))) : (unsigned)(kRadixSize - 1)], 1u);
                 }
             }
             named_bar_arrive(kBarCounted + p, kWsThreads);
@@ -147,32 +169,58 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const unsig
             const size_t base = (size_t)t * TILE + (size_t)w * SEG + lane;
             unsigned *row = tab + (p * kWsWorkerWarps + w) * ROW;
             K cur[CHUNK], nxt[CHUNK];
-            auto load = [&](K (&dst)[CHUNK], int c) {
+            V vcur[VB ? CHUNK : 1], vnxt[VB ? CHUNK : 1];
+            auto load = [&](K (&dst)[CHUNK], V (&vdst)[VB ? CHUNK : 1], int c) {
 #pragma unroll
                 for (int i = 0; i < CHUNK; i++) {
                     const size_t idx = base + (size_t)(c * CHUNK + i) * 32;
                     dst[i] = (FULL || idx < n) ? ld_hint(keys_in + idx, drop) : (K)0;  // last use: first in line for eviction
+                    if constexpr (VB > 0) vdst[i] = (FULL || idx < n) ? __ldg(vals_in + idx) : V();
                 }
             };
-            load(cur, 0);  // second read of the tile (the counting sweep was the first): flies during the waits below
+            load(cur, vcur, 0);  // second read of the tile (the counting sweep was the first): flies during the waits below
             WS_PROF_BEGIN();
             named_bar_sync(kBarOffsets + p, kWsThreads);          // the tables hold the start of every (warp, digit) run
             WS_PROF_END(2);
             if (!first) named_bar_sync(kBarDrained, kWsThreads);  // the previous tile's bulk copies have read the buffer
             WS_PROF_END(3);
+            unsigned *mrow = masks + w * ROW;
 #pragma unroll 1
             for (int c = 0; c < ITEMS / CHUNK; c++) {
-                if (c + 1 < ITEMS / CHUNK) load(nxt, c + 1);
+                if (c + 1 < ITEMS / CHUNK) load(nxt, vnxt, c + 1);
 #pragma unroll
                 for (int i = 0; i < CHUNK; i++) {
-                    unsigned d = pass_digit<K, IDENT>(cur[i], shift, tf);
+                    const U t = sortable(cur[i]);
+                    unsigned d = digit(t);
                     if (!FULL && base + (size_t)(c * CHUNK + i) * 32 >= n) d = kRadixSize - 1;
-                    // same atomics, same order as count(): start of the run + rank.  (Issuing all atomics of the chunk
-                    // before the first store was measured 3 % slower: the LSU queue, not the latency, is the limit.)
-                    buf[atomicAdd(&row[d], 1u)] = cur[i];
+                    unsigned pos;
+                    if constexpr (DET) {
+                        // deterministic by construction: the lanes OR their bit into the mask of their digit; after a warp
+                        // barrier the mask holds the complete peer set whatever order the atomics were applied in; the
+                        // highest peer clears it and advances the run's cursor
+                        atomicOr(&mrow[d], 1u << lane);
+                        __syncwarp();
+                        const unsigned m = mrow[d], o = row[d];
+                        __syncwarp();
+                        if ((m >> lane) == 1u) {
+                            mrow[d] = 0;
+                            row[d] = o + __popc(m);
+                        }
+                        __syncwarp();
+                        pos = o + __popc(m & lanemask_lt());
+                    } else {
+                        // same atomics, same order as count(): start of the run + rank.  (Issuing all atomics of the chunk
+                        // before the first store was measured 3 % slower: the LSU queue, not the latency, is the limit.)
+                        pos = atomicAdd(&row[d], 1u);
+                    }
+                    buf[pos] = stored(cur[i], t);
+                    if constexpr (VB > 0) vbuf[pos] = vcur[i];
                 }
 #pragma unroll
-                for (int i = 0; i < CHUNK; i++) cur[i] = nxt[i];
+                for (int i = 0; i < CHUNK; i++) {
+                    cur[i] = nxt[i];
+                    if constexpr (VB > 0) vcur[i] = vnxt[i];
+                }
             }
             __syncwarp();
             {  // the row is this warp's own: zero it for the warp's next tile
@@ -299,8 +347,11 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const unsig
             K *dst0 = keys_out + ((size_t)r.g - m);
             const unsigned first = (m + A - 1) / A, last = end / A;  // full chunks [first, last)
             if (r.c && last > first) {
-                if (flags & 2) tma_store_issue(dst0 + first * A, src0 + first * A, (last - first) * 16u);
-                else tma_store_issue_hint(dst0 + first * A, src0 + first * A, (last - first) * 16u, drop);
+                // (first * A keys / values are a whole number of 16-byte chunks in BOTH arrays: A counts elements of the narrower one)
+                if (flags & 2) tma_store_issue(dst0 + first * A, src0 + first * A, (last - first) * A * (unsigned)sizeof(K));
+                else tma_store_issue_hint(dst0 + first * A, src0 + first * A, (last - first) * A * (unsigned)sizeof(K), drop);
+                if constexpr (VB > 0)
+                    tma_store_issue_hint(vals_out + ((size_t)r.g - m) + first * A, vbuf + (r.s - m) + first * A, (last - first) * A * (unsigned)VB, drop);
             }
             WS_PROF_END(4);
             tma_commit();
@@ -327,7 +378,10 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const unsig
                             k = olast * A + (slot - (A - 1));
                             on = olast >= ofirst && k < oend;
                         }
-                        if (on) keys_out[(size_t)og - om + k] = buf[os - om + k];
+                        if (on) {
+                            keys_out[(size_t)og - om + k] = buf[os - om + k];
+                            if constexpr (VB > 0) vals_out[(size_t)og - om + k] = vbuf[os - om + k];
+                        }
                     }
                 }
             }
@@ -355,12 +409,12 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const unsig
     }
 }
 
-template <typename K, int IDENT>
-static int ws_launch_typed(StreamState *st, const void *kin, void *kout, const unsigned *base, unsigned long long *lookback, size_t n,
-                           int shift, const Transform &tf)
+template <typename K, int VB, bool DET, int XF>
+static int ws_launch_typed(StreamState *st, const void *kin, void *kout, const void *vin, void *vout, const unsigned *base,
+                           unsigned long long *lookback, size_t n, int shift, const Transform &tf)
 {
-    typedef WsShape<K> C;
-    auto kernel = onesweep_ws<K, IDENT, 8>;
+    typedef WsShape<K, VB, DET> C;
+    auto kernel = onesweep_ws<K, VB, DET, XF, 8>;
     static std::atomic<unsigned long long> configured{0};  // bit per device: > 48 KB dynamic shared memory opted in
     const unsigned long long bit = st->device < 64 ? (1ull << st->device) : 0ull;
     if (!(configured.load(std::memory_order_acquire) & bit) || !bit) {
@@ -375,40 +429,50 @@ static int ws_launch_typed(StreamState *st, const void *kin, void *kout, const u
     const unsigned long long ticket_base = ticket_reserve(st, tiles + grid);  // every CTA draws one void ticket
     static const int ws_flags = [] { const char *e = std::getenv("BCB_WS_FLAGS"); return e ? std::atoi(e) : 0; }();  // experiments
     LaunchTimer timer(st, BCB_K_ONESWEEP_PASS);
-    kernel<<<(unsigned)grid, kWsThreads, C::SMEM_BYTES, st->stream>>>((const K *)kin, (K *)kout, base, lookback, epoch, n, (unsigned)tiles,
-                                                                      shift, tf, st->control + kControlTicket, ticket_base, ws_flags);
+    kernel<<<(unsigned)grid, kWsThreads, C::SMEM_BYTES, st->stream>>>((const K *)kin, (K *)kout, vin, vout, base, lookback, epoch, n,
+                                                                      (unsigned)tiles, shift, tf, st->control + kControlTicket, ticket_base, ws_flags);
     BCB_CUDA_TRY(cudaGetLastError());
-#ifdef BCB_WS_PROFILE
-    {
-        static unsigned long long host[148 * 16 * 4];
-        cudaStreamSynchronize(st->stream);
-        cudaMemcpyFromSymbol(host, g_ws_prof, sizeof(unsigned long long) * grid * 16);
-        double avg[16] = {};
-        for (size_t b = 0; b < grid; b++) for (int q = 0; q < 16; q++) avg[q] += (double)host[b * 16 + q] / grid;
-        const double per = (double)grid / tiles;  // -> cycles per tile
-        fprintf(stderr, "[ws prof] cycles/tile  workers: draw %.0f count %.0f waitOffsets %.0f waitDrained %.0f scatter %.0f | "
-                        "helpers: waitCounted %.0f sums+scan %.0f lookback %.0f offsets %.0f waitScattered %.0f issue %.0f edges %.0f drain %.0f\n",
-                avg[0] * per, avg[1] * per, avg[2] * per, avg[3] * per, avg[4] * per,
-                avg[15] * per, avg[8] * per, avg[9] * per, avg[10] * per, avg[11] * per, avg[12] * per, avg[13] * per, avg[14] * per);
-    }
-#endif
     return BCB_SUCCESS;
 }
 
-size_t ws_tile_size(int key_bytes) { return key_bytes == 8 ? (size_t)WsShape<unsigned long long>::TILE : (size_t)WsShape<unsigned>::TILE; }
-
-int ws_launch_pass(StreamState *st, int key_bytes, const void *kin, void *kout, const unsigned *base, unsigned long long *lookback,
-                   size_t n, int shift, const Transform &tf)
+template <typename K, int VB, bool DET>
+static int ws_launch_xf(StreamState *st, const void *kin, void *kout, const void *vin, void *vout, const unsigned *base,
+                        unsigned long long *lookback, size_t n, int shift, const Transform &tf, int xf)
 {
-    if ((((uintptr_t)kin | (uintptr_t)kout) & 15) != 0) return BCB_EUNSUPPORTED;  // bulk copies need 16-byte aligned arrays
-    const bool ident = (tf.nm | tf.xc | tf.fa) == 0;
-    if (key_bytes == 4)
-        return ident ? ws_launch_typed<unsigned, kDigitIdent>(st, kin, kout, base, lookback, n, shift, tf)
-                     : ws_launch_typed<unsigned, kDigitTransform>(st, kin, kout, base, lookback, n, shift, tf);
-    if (key_bytes == 8)
-        return ident ? ws_launch_typed<unsigned long long, kDigitIdent>(st, kin, kout, base, lookback, n, shift, tf)
-                     : ws_launch_typed<unsigned long long, kDigitTransform>(st, kin, kout, base, lookback, n, shift, tf);
-    return BCB_EUNSUPPORTED;
+    switch (xf) {
+    case kXfNone: return ws_launch_typed<K, VB, DET, kXfNone>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
+    case kXfIn: return ws_launch_typed<K, VB, DET, kXfIn>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
+    case kXfOut: return ws_launch_typed<K, VB, DET, kXfOut>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
+    default: return ws_launch_typed<K, VB, DET, kXfBoth>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
+    }
+}
+
+size_t ws_tile_size(int key_bytes, int value_bytes, bool deterministic)
+{
+    if (value_bytes == 4) return (size_t)WsShape<unsigned, 4, true>::TILE;
+    if (value_bytes == 8) return (size_t)WsShape<unsigned, 8, true>::TILE;
+    if (key_bytes == 8) return (size_t)WsShape<unsigned long long, 0, false>::TILE;
+    return deterministic ? (size_t)WsShape<unsigned, 0, true>::TILE : (size_t)WsShape<unsigned, 0, false>::TILE;
+}
+
+bool ws_supports(int key_bytes, int value_bytes, bool deterministic)
+{
+    if (value_bytes) return key_bytes == 4 && (value_bytes == 4 || value_bytes == 8);
+    if (deterministic) return key_bytes == 4;
+    return key_bytes == 4 || key_bytes == 8;
+}
+
+int ws_launch_pass(StreamState *st, int key_bytes, const void *kin, void *kout, const void *vin, void *vout, int value_bytes,
+                   const unsigned *base, unsigned long long *lookback, size_t n, int shift, const Transform &tf, int xf, bool deterministic)
+{
+    // bulk copies need 16-byte aligned arrays
+    if ((((uintptr_t)kin | (uintptr_t)kout | (uintptr_t)vin | (uintptr_t)vout) & 15) != 0) return BCB_EUNSUPPORTED;
+    if (!ws_supports(key_bytes, value_bytes, deterministic)) return BCB_EUNSUPPORTED;
+    if (value_bytes == 4) return ws_launch_xf<unsigned, 4, true>(st, kin, kout, vin, vout, base, lookback, n, shift, tf, xf);
+    if (value_bytes == 8) return ws_launch_xf<unsigned, 8, true>(st, kin, kout, vin, vout, base, lookback, n, shift, tf, xf);
+    if (key_bytes == 8) return ws_launch_xf<unsigned long long, 0, false>(st, kin, kout, nullptr, nullptr, base, lookback, n, shift, tf, xf);
+    return deterministic ? ws_launch_xf<unsigned, 0, true>(st, kin, kout, nullptr, nullptr, base, lookback, n, shift, tf, xf)
+                         : ws_launch_xf<unsigned, 0, false>(st, kin, kout, nullptr, nullptr, base, lookback, n, shift, tf, xf);
 }
 
 }  // namespace bcb

@@ -791,13 +791,16 @@ template <typename K> struct SpecConfig { static constexpr int THREADS = 384, IT
 // (2^28 u64 keys, 8 passes: 384x12 10.9 ms, 384x16 9.2 ms, 384x20 8.7 ms, 384x24 8.7 ms)
 template <> struct SpecConfig<unsigned long long> { static constexpr int THREADS = 384, ITEMS = 20, LB = 4, MINB = 2; };
 
-enum { kPassDeterministic = 0, kPassTwoSweep = 1, kPassWs = 2 };  // which pass kernel a sort uses
+// which pass kernel a sort uses: the r01 deterministic atomic-OR kernel, the r01 speculative two-sweep kernel, the
+// warp-specialised kernel with the speculative ranking (keys only), or with the deterministic ranking (payloads, keys
+// with a non-injective transform)
+enum { kPassDeterministic = 0, kPassTwoSweep = 1, kPassWs = 2, kPassWsDet = 3 };
 
 template <typename K, int VB>
 static size_t tile_size_for(int pass_kind)
 {
+    if (pass_kind == kPassWs || pass_kind == kPassWsDet) return ws_tile_size((int)sizeof(K), VB, pass_kind == kPassWsDet);
     if constexpr (VB == 0 && (sizeof(K) == 4 || sizeof(K) == 8)) {
-        if (pass_kind == kPassWs) return ws_tile_size((int)sizeof(K));
         if (pass_kind == kPassTwoSweep) return (size_t)SpecConfig<K>::THREADS * SpecConfig<K>::ITEMS;
     }
     return (size_t)PassConfig<K, VB>::THREADS * PassConfig<K, VB>::ITEMS;
@@ -807,8 +810,15 @@ template <typename K, int VB>
 static int run_pass(StreamState *st, const void *kin, void *kout, const void *vin, void *vout, const unsigned *base,
                     unsigned long long *lookback, size_t n, int shift, const Transform &tf, int pass_kind, const int *gate)
 {
+    if (pass_kind == kPassWs || pass_kind == kPassWsDet) {
+        // keys travel between the passes in transformed form (one transform in the first pass, its inverse in the last)
+        // unless the transform cannot be inverted (descending float / double): then every pass transforms for the digit only
+        const bool ident = (tf.nm | tf.xc | tf.fa) == 0, injective = !(tf.fa != 0 && tf.nm != 0);
+        constexpr int kLastShift = ((int)sizeof(K) - 1) * kRadixBits;
+        const int xf = ident ? kXfNone : (!injective ? kXfBoth : (shift == 0 ? kXfIn : (shift == kLastShift ? kXfOut : kXfNone)));
+        return ws_launch_pass(st, (int)sizeof(K), kin, kout, vin, vout, VB, base, lookback, n, shift, tf, xf, pass_kind == kPassWsDet);
+    }
     if constexpr (VB == 0 && (sizeof(K) == 4 || sizeof(K) == 8)) {
-        if (pass_kind == kPassWs) return ws_launch_pass(st, (int)sizeof(K), kin, kout, base, lookback, n, shift, tf);
         if (pass_kind == kPassTwoSweep)
             return launch_two_sweep<K, SpecConfig<K>::THREADS, SpecConfig<K>::ITEMS, SpecConfig<K>::LB, SpecConfig<K>::MINB>(
                 st, kin, kout, base, lookback, n, shift, tf);
@@ -1032,6 +1042,11 @@ static int sort_typed(StreamState *st, void *keys, void *values, size_t n, const
     // src_keys / src_vals: read the input from there instead (sorted copy; the source is left untouched)
     if (!src_keys) { src_keys = keys; src_vals = values; }
     int pass_kind = kPassDeterministic;
+    {   // large sorts the warp-specialised kernel covers with its deterministic ranking: payloads, non-injective transforms
+        const SortEnv &env = sort_env();
+        const bool aligned = ((((uintptr_t)keys) | ((uintptr_t)src_keys) | ((uintptr_t)values) | ((uintptr_t)src_vals)) & 15) == 0;
+        if (env.ws && aligned && n >= kWsMinKeys && ws_supports((int)sizeof(K), VB, true)) pass_kind = kPassWsDet;
+    }
     if constexpr (VB == 0 && (sizeof(K) == 4 || sizeof(K) == 8)) {
         // The verification argument needs an INJECTIVE key transform (sorted permutation => unique bytes).  The
         // reference's descending float transform is not (radix_sort.hpp:100-127: -0.0 / +denorm_min and
@@ -1048,7 +1063,7 @@ static int sort_typed(StreamState *st, void *keys, void *values, size_t n, const
             if (env.ws && aligned && n >= kWsMinKeys && sizeof(K) == 4) pass_kind = kPassWs;
         }
     }
-    if (pass_kind == kPassDeterministic) return sort_passes<K, VB>(st, keys, values, n, tf, src_keys, src_vals, pass_kind, nullptr);
+    if (pass_kind == kPassDeterministic || pass_kind == kPassWsDet) return sort_passes<K, VB>(st, keys, values, n, tf, src_keys, src_vals, pass_kind, nullptr);
 
     if constexpr (VB == 0 && (sizeof(K) == 4 || sizeof(K) == 8)) {
         BCB_TRY((sort_passes<K, VB>(st, keys, values, n, tf, src_keys, src_vals, pass_kind, nullptr)));
