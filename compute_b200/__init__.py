@@ -10,6 +10,10 @@ from .algorithm import (  # noqa: F401
     accumulate,
     copy_if,
     count,
+    equal,
+    is_permutation,
+    sort_by_transform,
+    transform,
     count_if,
     inner_product,
     predicate,

@@ -325,9 +325,54 @@ def reduce_by_key(keys: torch.Tensor, values: torch.Tensor, keys_result: torch.T
     return int(count.value)
 
 
+def transform(first: torch.Tensor, result: torch.Tensor, function, queue: command_queue | None = None) -> int:
+    """transform(first, last, result, function, queue) -- algorithm/transform.hpp:30-75, unary form, closed function set."""
+    return transform_if(first, result, function, predicate("true"), queue)
+
+
+def equal(first1: torch.Tensor, first2: torch.Tensor, queue: command_queue | None = None) -> bool:
+    """equal(first1, last1, first2, queue) -- algorithm/equal.hpp:30-47, on the bit patterns of same-typed ranges."""
+    _range(first1)
+    _range(first2)
+    n = first1.numel()
+    if dtype_code(first1.dtype) != dtype_code(first2.dtype) or first2.numel() < n:
+        raise ValueError("equal: ranges must have the same value type and the second at least n elements")
+    if n == 0:
+        return True
+    code = {1: 1, 2: 3, 4: 5, 8: 7}[first1.element_size()]  # unsigned type of the same width
+    host = np.zeros(1, dtype=NP_OF_CODE[code])
+    check(lib().bcb_transform_reduce(_q(queue).handle, code, first1.data_ptr(), first2.data_ptr(), n, op_code("bit_xor"), op_code("bit_or"),
+                                     host.ctypes.data, 0))
+    return int(host[0]) == 0
+
+
+def is_permutation(first1: torch.Tensor, first2: torch.Tensor, queue: command_queue | None = None) -> bool:
+    """is_permutation(first1, last1, first2, last2, queue) -- algorithm/is_permutation.hpp:43-67: sort copies, compare."""
+    _range(first1)
+    _range(first2)
+    if first1.numel() != first2.numel():
+        return False
+    a, b = first1.clone(), first2.clone()
+    sort(a, False, queue)
+    sort(b, False, queue)
+    return equal(a, b, queue)
+
+
+def sort_by_transform(first: torch.Tensor, function, descending: bool = False, queue: command_queue | None = None) -> None:
+    """experimental::sort_by_transform(first, last, transform, compare, queue) -- experimental/sort_by_transform.hpp:26-63:
+    keys = transform(range); sort_by_key(keys, range, compare)."""
+    _range(first)
+    if first.numel() < 2:
+        return
+    keys = torch.empty_like(first)
+    transform(first, keys, function, queue)
+    sort_by_key(keys, first, descending, queue)
+
+
 __all__ = [
     "radix_sort", "radix_sort_by_key", "insertion_sort", "sort", "sort_host", "sort_by_key", "stable_sort",
     "stable_sort_by_key", "is_sorted", "exclusive_scan", "inclusive_scan", "partial_sum", "reduce", "accumulate",
     "predicate", "transform_if", "copy_if", "count_if", "count", "transform_reduce", "inner_product", "reduce_by_key",
+    "transform", "equal", "is_permutation", "sort_by_transform",
 ]
 _ = TORCH_OF_CODE

@@ -667,12 +667,25 @@ static int launch_pass_impl(StreamState *st, const void *kin, void *kout, const 
 //   BCB_SORT_SPECULATIVE=0       always use the deterministic atomic-OR kernel
 //   BCB_SORT_FORCE_FALLBACK=1    test hook: treat every verification as failed
 //   BCB_SORT_WS=0                keep the r01 two-sweep kernel for large sorts (A/B comparison)
-constexpr size_t kSpeculativeMinKeys = (size_t)1 << 20;
-constexpr size_t kWsMinKeys = (size_t)1 << 23;  // below this too few tiles per SM for the warp-specialised pipeline
+//   BCB_SORT_SPEC_MIN_LOG2=k, BCB_SORT_WS_MIN_LOG2=k   test hooks: move the size thresholds below
+// Size thresholds, measured on B200 (2^k uint32 keys, ms per sort: deterministic / two-sweep + verification / onesweep_ws +
+// verification): 2^23 0.26 / - / 0.33; 2^24 0.45 / 0.34 / -; 2^25 0.70 / 0.52 / 0.61; 2^26 1.19 / 0.90 / 0.95; 2^27 2.19 / - / 1.63;
+// 2^30 19 / 12.7 / 11.2.  Verification and the gated fallback launches cost ~70 us, the warp-specialised pipeline needs
+// >= ~20 tiles per SM to fill.
+constexpr int kSpeculativeMinLog2 = 24;
+constexpr int kWsMinLog2 = 27;
 struct SortEnv {
     bool speculative, force_fallback, ws;
+    size_t spec_min, ws_min;
     SortEnv()
     {
+        auto log2_of = [](const char *name, int dflt) {
+            const char *v = std::getenv(name);
+            const int k = v ? std::atoi(v) : dflt;
+            return (size_t)1 << (k < 10 ? 10 : (k > 40 ? 40 : k));
+        };
+        spec_min = log2_of("BCB_SORT_SPEC_MIN_LOG2", kSpeculativeMinLog2);
+        ws_min = log2_of("BCB_SORT_WS_MIN_LOG2", kWsMinLog2);
         const char *e = std::getenv("BCB_SORT_SPECULATIVE");
         speculative = !(e && e[0] == '0');
         e = std::getenv("BCB_SORT_FORCE_FALLBACK");
@@ -1045,7 +1058,7 @@ static int sort_typed(StreamState *st, void *keys, void *values, size_t n, const
     {   // large sorts the warp-specialised kernel covers with its deterministic ranking: payloads, non-injective transforms
         const SortEnv &env = sort_env();
         const bool aligned = ((((uintptr_t)keys) | ((uintptr_t)src_keys) | ((uintptr_t)values) | ((uintptr_t)src_vals)) & 15) == 0;
-        if (env.ws && aligned && n >= kWsMinKeys && ws_supports((int)sizeof(K), VB, true)) pass_kind = kPassWsDet;
+        if (env.ws && aligned && n >= env.ws_min && ws_supports((int)sizeof(K), VB, true)) pass_kind = kPassWsDet;
     }
     if constexpr (VB == 0 && (sizeof(K) == 4 || sizeof(K) == 8)) {
         // The verification argument needs an INJECTIVE key transform (sorted permutation => unique bytes).  The
@@ -1054,13 +1067,13 @@ static int sort_typed(StreamState *st, void *keys, void *values, size_t n, const
         // descending float / double sorts always take the deterministic kernel.
         const bool injective = !(tf.fa != 0 && tf.nm != 0);
         const SortEnv &env = sort_env();
-        if (injective && env.speculative && n >= kSpeculativeMinKeys) {
+        if (injective && env.speculative && n >= env.spec_min) {
             pass_kind = kPassTwoSweep;
             // bulk copies need 16-byte aligned arrays (the scratch buffer always is)
             const bool aligned = ((((uintptr_t)keys) | ((uintptr_t)src_keys)) & 15) == 0;
             // (64-bit keys: measured 23.7 Gkeys/s with onesweep_ws against 29.2 with the two-sweep kernel -- 21504-key
             // tiles give each CTA too few keys per digit run to pay for the helper-warp pipeline)
-            if (env.ws && aligned && n >= kWsMinKeys && sizeof(K) == 4) pass_kind = kPassWs;
+            if (env.ws && aligned && n >= env.ws_min && sizeof(K) == 4) pass_kind = kPassWs;
         }
     }
     if (pass_kind == kPassDeterministic || pass_kind == kPassWsDet) return sort_passes<K, VB>(st, keys, values, n, tf, src_keys, src_vals, pass_kind, nullptr);

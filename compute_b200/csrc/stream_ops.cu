@@ -484,8 +484,12 @@ static int dispatch_transform_reduce(StreamState *st, int reduce_op, const void 
     case BCB_MULTIPLIES: return launch_transform_reduce<T, BCB_MULTIPLIES>(st, in1, in2, n, tcode, result_dev);
     case BCB_MIN: return launch_transform_reduce<T, BCB_MIN>(st, in1, in2, n, tcode, result_dev);
     case BCB_MAX: return launch_transform_reduce<T, BCB_MAX>(st, in1, in2, n, tcode, result_dev);
-    default: return BCB_EUNSUPPORTED;
+    default: break;
     }
+    if constexpr (!is_fp<T>::value) {
+        if (reduce_op == BCB_BIT_OR) return launch_transform_reduce<T, BCB_BIT_OR>(st, in1, in2, n, tcode, result_dev);
+    }
+    return BCB_EUNSUPPORTED;
 }
 
 template <typename K, typename V>
@@ -587,7 +591,8 @@ int bcb_transform_reduce(bcb_stream stream, int dtype, const void *in1, const vo
     if (!w) return BCB_EINVAL;
     if (n == 0) return BCB_SUCCESS;  // like reduce: the result is left untouched
     if (!in1 || !result) return BCB_EINVAL;
-    if (in2 ? !(transform == BCB_PLUS || transform == BCB_MINUS || transform == BCB_MULTIPLIES || transform == BCB_MIN || transform == BCB_MAX)
+    if (in2 ? !(transform == BCB_PLUS || transform == BCB_MINUS || transform == BCB_MULTIPLIES || transform == BCB_MIN || transform == BCB_MAX ||
+                (op_is_bitwise(transform) && !dtype_is_float(dtype)))
             : (transform < BCB_UN_IDENTITY || transform > BCB_UN_SQUARE))
         return BCB_EUNSUPPORTED;
     StreamState *st;

@@ -373,3 +373,18 @@ def reduce_by_key(keys: np.ndarray, values: np.ndarray, op: str = "plus"):
     for j, (s0, e0) in enumerate(zip(starts, ends)):
         out_v[j] = _fold(values[s0:e0], op)
     return keys[starts].copy(), out_v
+
+
+def is_permutation(a: np.ndarray, b: np.ndarray) -> bool:
+    """is_permutation.hpp:43-67: equal after sorting both (compared on the bit patterns, as the GPU path does)."""
+    if a.size != b.size:
+        return False
+    return sort(np.ascontiguousarray(a), False).tobytes() == sort(np.ascontiguousarray(b), False).tobytes()
+
+
+def sort_by_transform(x: np.ndarray, function: str, descending: bool = False) -> np.ndarray:
+    """experimental/sort_by_transform.hpp:26-63: sort_by_key(transform(x), x, compare) -- stable by the transformed key."""
+    x = np.ascontiguousarray(x)
+    if x.size < 2:
+        return x.copy()
+    return sort_by_key(apply_unary(x, function), x.copy(), descending)[1]

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include <boost/compute.hpp>
+#include <boost/compute/experimental/sort_by_transform.hpp>
 
 namespace compute = boost::compute;
 
@@ -489,6 +490,42 @@ static void test_scan_and_reduce_callers(compute::command_queue &queue)
     }
 }
 
+// callers of sort
+static void test_sort_callers(compute::command_queue &queue)
+{
+    {   // test_is_permutation.cpp:25-46, :48-69
+        int d1[] = {1, 3, 1, 2, 5}, d2[] = {3, 1, 5, 1, 2};
+        compute::vector<int> v1(d1, d1 + 5, queue), v2(d2, d2 + 5, queue);
+        CHECK(compute::is_permutation(v1.begin(), v1.begin() + 5, v2.begin(), v2.begin() + 5, queue));
+        int one = 1;
+        compute::copy(&one, &one + 1, v2.begin(), queue);
+        CHECK(!compute::is_permutation(v1.begin(), v1.begin() + 5, v2.begin(), v2.begin() + 5, queue));
+        const char s1[] = "abade", s2[] = "aadeb";
+        compute::vector<char> c1(s1, s1 + 5, queue), c2(s2, s2 + 5, queue);
+        CHECK(compute::is_permutation(c1.begin(), c1.end(), c2.begin(), c2.end(), queue));
+        CHECK(!compute::is_permutation(c1.begin(), c1.end(), c2.begin(), c2.begin() + 4, queue));
+    }
+    {   // test_sort_by_transform.cpp:24-39
+        int data[] = { 1, -2, 4, -3, 0, 5, -8, -9 };
+        compute::vector<int> v(data, data + 8, queue);
+        compute::experimental::sort_by_transform(v.begin(), v.end(), compute::abs<int>(), compute::less<int>(), queue);
+        CHECK(to_host(v, queue) == (std::vector<int>{0, 1, -2, -3, 4, 5, -8, -9}));
+        // a range long enough for the radix path: stable order by |x|
+        std::vector<int> big(5000);
+        for (size_t i = 0; i < big.size(); i++) big[i] = (int)((i * 7919u) % 201u) - 100;
+        compute::vector<int> dv(big.begin(), big.end(), queue);
+        compute::experimental::sort_by_transform(dv.begin(), dv.end(), compute::abs<int>(), compute::less<int>(), queue);
+        std::stable_sort(big.begin(), big.end(), [](int a, int b) { return std::abs(a) < std::abs(b); });
+        CHECK(to_host(dv, queue) == big);
+    }
+    {   // transform(): unary closed set
+        int data[] = { 3, -4, 5 };
+        compute::vector<int> in(data, data + 3, queue), out(3, queue.get_context());
+        CHECK(compute::transform(in.begin(), in.end(), out.begin(), compute::square<int>(), queue) == out.end());
+        CHECK(to_host(out, queue) == (std::vector<int>{9, 16, 25}));
+    }
+}
+
 int main()
 {
     try {
@@ -502,6 +539,7 @@ int main()
         test_reduce_accumulate(queue);
         test_array_and_mapped_view(queue);
         test_scan_and_reduce_callers(queue);
+        test_sort_callers(queue);
         queue.finish();
     } catch(std::exception &e) {
         std::printf("EXCEPTION: %s\n", e.what());

@@ -188,6 +188,14 @@ def check_case(c, api):
         else:
             np.testing.assert_array_equal(gv, np.array(c["expected_values"], dtype=vd), err_msg=c["ref"])
         return
+    if fn == "is_permutation":
+        x = _expand_input(c)
+        assert bool(api.is_permutation(x, np.array(c["input2"], dtype=x.dtype))) == c["expected"], c["ref"]
+        return
+    if fn == "sort_by_transform":
+        x = _expand_input(c)
+        np.testing.assert_array_equal(api.sort_by_transform(x, c["function"], desc), np.array(c["expected"], dtype=x.dtype), err_msg=c["ref"])
+        return
     raise ValueError(fn)
 
 

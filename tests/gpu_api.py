@@ -187,3 +187,14 @@ def reduce_by_key(keys, values, op="plus"):
     m = cb.reduce_by_key(dk, dv, ok, ov, op)
     torch.cuda.synchronize()
     return to_host(ok, keys.dtype)[:m], to_host(ov, values.dtype)[:m]
+
+
+def is_permutation(a, b):
+    return cb.is_permutation(to_dev(np.ascontiguousarray(a)), to_dev(np.ascontiguousarray(b)))
+
+
+def sort_by_transform(x, function, descending=False):
+    d = to_dev(np.ascontiguousarray(x))
+    cb.sort_by_transform(d, function, descending)
+    torch.cuda.synchronize()
+    return to_host(d, x.dtype)

@@ -482,6 +482,33 @@ def test_multi_round_persistent_sort_2_26_keys_and_pairs(gpu):
     assert gk.tobytes() == ok.tobytes() and gv.tobytes() == ov.tobytes()
 
 
+def test_default_thresholds_pick_the_measured_kernels():
+    """Without the test hooks: 2^23 keys sort deterministically (no speculation), 2^24 keys speculate (two-sweep), and a
+    2^27-key sort goes through the warp-specialised kernel; all verified against torch.sort."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, ctypes, torch\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "import compute_b200 as cb\n"
+        "def runs():\n"
+        "    r, f = ctypes.c_ulonglong(), ctypes.c_ulonglong()\n"
+        "    cb.lib().bcb_sort_speculation_stats(cb.command_queue().handle, ctypes.byref(r), ctypes.byref(f))\n"
+        "    return r.value, f.value\n"
+        "for lg, want in ((23, 0), (24, 1), (27, 2)):\n"
+        "    k = torch.randint(0, 2**31 - 1, (1 << lg,), dtype=torch.int32, device='cuda')\n"
+        "    ref = torch.sort(k).values\n"
+        "    cb.radix_sort(k)\n"
+        "    torch.cuda.synchronize()\n"
+        "    assert torch.equal(k, ref), lg\n"
+        "    assert runs() == (want, 0), (lg, runs())\n"
+        "print('THRESHOLDS_OK')\n"
+    )
+    env = {k: v for k, v in os.environ.items() if k not in ("BCB_SORT_SPEC_MIN_LOG2", "BCB_SORT_WS_MIN_LOG2")}
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0 and "THRESHOLDS_OK" in out.stdout, out.stdout + out.stderr
+
+
 def test_sort_is_enqueue_and_return(gpu):
     """perf_sort.cpp:38-39 enqueues the sort and calls queue.finish(): bcb_radix_sort must not wait for the device, even
     on the speculative path (the verification and the gated fallback stay on the device)."""
@@ -648,3 +675,21 @@ def test_reduce_by_key_matches_serial_definition(key_dtype, val_dtype, gpu):
             assert gv.tobytes() == ev.tobytes(), (key_dtype, val_dtype, n, mean_run, op)
     gk, gv = gpu.reduce_by_key(np.empty(0, kd), np.empty(0, vd))
     assert gk.size == 0 and gv.size == 0
+
+
+@pytest.mark.parametrize("dtype", ["char", "ushort", "int", "ulong", "float"])
+def test_sort_callers_is_permutation_and_sort_by_transform(dtype, gpu):
+    """is_permutation.hpp:43-67 and experimental/sort_by_transform.hpp:26-63 on top of the sort path."""
+    npdt = np.dtype(NPD[dtype])
+    rng = np.random.default_rng(41)
+    for n in (1, 33, 5000, 300_001):
+        x = rng.integers(-100 if npdt.kind != "u" else 0, 100, size=n).astype(npdt)
+        y = rng.permutation(x)
+        assert gpu.is_permutation(x, y) is True
+        if n > 1:
+            z = y.copy()
+            z[n // 2] = z[n // 2] + npdt.type(1)
+            assert gpu.is_permutation(x, z) is oracle.is_permutation(x, z) is False
+        for fn in ("abs", "negate", "square"):
+            assert gpu.sort_by_transform(x, fn).tobytes() == oracle.sort_by_transform(x, fn).tobytes(), (dtype, n, fn)
+        assert gpu.sort_by_transform(x, "abs", True).tobytes() == oracle.sort_by_transform(x, "abs", True).tobytes()
