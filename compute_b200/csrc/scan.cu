@@ -16,6 +16,7 @@
 // Floating-point prefixes are folded strictly in tile order, so results are run-to-run deterministic.
 #include "ops.cuh"
 #include "tile_state.cuh"
+#include "scan_ws.cuh"
 #include "tma.cuh"
 
 #include <atomic>
@@ -162,6 +163,7 @@ scan_kernel(const T *in, T *out, size_t n, int exclusive, T init, TileState<T> t
 // tiles in flight at any moment form one contiguous window of the input and a prefetched tile is never one that
 // another CTA is waiting for.  (Drawing tickets ahead of time was measured to be 2x slower: a CTA then HOLDS
 // tiles it is not working on yet while their successors spin in the look-back.)
+constexpr int kScanWsMinLog2Bytes = 20;               // smallest range (bytes) the warp-specialised kernel takes
 constexpr int kRoundThreads = 512;                 // threads per CTA of the round-synchronous kernel
 constexpr int kRoundWarps = kRoundThreads / 32;
 
@@ -424,6 +426,45 @@ static int launch_scan(StreamState *st, const void *in, void *out, size_t n, int
     void *mem;
     unsigned epoch;
     TileState<T> ts;
+    // Large ranges: the warp-specialised kernel (scan_ws.cuh).  Measured on B200, 2^28 int32: 6.0 TB/s against 4.8 for
+    // scan_tma_kernel; faster from 1 MB on (16 us against 25 us for 1-8 MB).
+    //   BCB_SCAN_WS=0            keep scan_tma_kernel for large ranges (A/B comparison)
+    //   BCB_SCAN_WS_MIN_LOG2=k   test hook: use it from 2^k BYTES on
+    static const size_t ws_min_bytes = [] {
+        const char *e = std::getenv("BCB_SCAN_WS");
+        if (e && e[0] == '0') return (size_t)-1;
+        const char *v = std::getenv("BCB_SCAN_WS_MIN_LOG2");
+        const int k = v ? std::atoi(v) : kScanWsMinLog2Bytes;
+        return (size_t)1 << (k < 10 ? 10 : (k > 40 ? 40 : k));
+    }();
+    if (aligned && n * sizeof(T) >= ws_min_bytes) {
+        constexpr int NV = 3, S = 9, D = 5;
+        typedef ScanWsShape<T, NV, S> C;
+        const size_t wtiles = (n + C::TILE - 1) / C::TILE;
+        // (tagged 64-bit words for every element width: the packed arena, whatever T is)
+        BCB_TRY(lookback_reserve(st, kArenaPacked, WsTileState<T>::bytes(wtiles), &mem));
+        BCB_TRY(next_epoch(st, kArenaPacked, &epoch));
+        WsTileState<T> wts;
+        wts.bind(mem);
+        auto kernel = scan_ws_kernel<T, OP, NV, S, D>;
+        static std::atomic<unsigned long long> configured{0};  // bit per device: > 48 KB dynamic shared memory opted in
+        const unsigned long long bit = st->device < 64 ? (1ull << st->device) : 0ull;
+        if (!(configured.load(std::memory_order_acquire) & bit) || !bit) {
+            BCB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+            configured.fetch_or(bit, std::memory_order_release);
+        }
+        size_t grid = (size_t)st->sm_count;  // one CTA per SM
+        if (grid > (size_t)kSwMaxGrid) grid = kSwMaxGrid;
+        if (grid > wtiles) grid = wtiles;
+        LaunchTimer timer(st, BCB_K_SCAN);
+        // every CTA waits for every tile of a round: the whole grid must be resident, which a cooperative launch
+        // guarantees (or it fails loudly) whatever else runs on the device
+        const T *in_t = (const T *)in;
+        T *out_t = (T *)out;
+        void *args[] = {(void *)&in_t, (void *)&out_t, (void *)&n, (void *)&exclusive, (void *)&init, (void *)&wts, (void *)&epoch, (void *)&wtiles};
+        BCB_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)kernel, dim3((unsigned)grid), dim3(kSwThreads), args, C::SMEM_BYTES, st->stream));
+        return BCB_SUCCESS;
+    }
     if (use_tma && aligned && n >= (size_t)4 * ScanRing<T>::kTile) {
         typedef ScanRing<T> R;
         const size_t rtiles = (n + R::kTile - 1) / R::kTile;

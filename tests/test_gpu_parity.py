@@ -205,6 +205,46 @@ def test_scan_mixed_types(gpu):
         assert got.tobytes() == exp.tobytes(), out  # uchar sums < 2^24: exact in float too
 
 
+# ranges of >= 1 MB take the warp-specialised kernel (scan_ws.cuh); here many rounds of it: ragged and exact tile
+# multiples, every element width
+@pytest.mark.parametrize("dtype,op", [("int", "plus"), ("uint", "max"), ("uchar", "plus"), ("short", "bit_xor"), ("long", "plus"),
+                                     ("ulong", "min"), ("int", "multiplies")])
+def test_scan_large_warp_specialised_integer_bit_exact(dtype, op, gpu):
+    w = np.dtype(NPD[dtype]).itemsize
+    for nbytes in ((1 << 24) + (1 << 22) + 13 * w, 9 * 24576 * 148 * 2):
+        n = nbytes // w
+        x = scan_input(dtype, n, seed=n % 1000)
+        if op == "multiplies":
+            x = (x | 1).astype(x.dtype)
+        for excl, init, in_place in ((False, 0, False), (True, 7, False), (True, 3, True)):
+            got = gpu.scan(x, op, excl, init, in_place=in_place)
+            assert got.tobytes() == oracle.scan(x, op, excl, init).tobytes(), (dtype, op, n, excl, init, in_place)
+
+
+@pytest.mark.parametrize("dtype", ["float", "double"])
+def test_scan_large_warp_specialised_float(dtype, gpu):
+    eps = 2.0 ** -24 if dtype == "float" else 2.0 ** -53
+    w = np.dtype(NPD[dtype]).itemsize
+    n = ((1 << 25) + 4444) // w
+    x = scan_input(dtype, n, seed=5)
+    for excl in (False, True):
+        got = gpu.scan(x, "plus", excl, 0.25 if excl else 0).astype(np.float64)
+        pref, apref = oracle.prefix_f64(x)
+        if dtype == "double":
+            pref = np.cumsum(x.astype(np.longdouble)).astype(np.float64)
+        if excl:
+            ref = np.concatenate([[0.25], 0.25 + pref[:-1]])
+            aref = np.concatenate([[0.25], 0.25 + apref[:-1]])
+        else:
+            ref, aref = pref, apref
+        tol = 4 * math.ceil(math.log2(n)) * eps * aref + 1e-300
+        assert np.all(np.abs(got - ref) <= tol), (dtype, excl, float(np.max(np.abs(got - ref) / tol)))
+        again = gpu.scan(x, "plus", excl, 0.25 if excl else 0)
+        assert again.astype(np.float64).tobytes() == got.tobytes(), "float scan must be run-to-run deterministic"
+    for op, init in (("min", 0.5), ("max", -0.5)):
+        assert gpu.scan(x, op, True, init).tobytes() == oracle.scan(x, op, True, init).tobytes()
+
+
 # ------------------------------------------------------------------------------------------ reduce / accumulate
 RED_SIZES = [1, 2, 3, 33, 1023, 1024, 1025, 4099, 65_537, 1_000_003, 5_000_011]
 
