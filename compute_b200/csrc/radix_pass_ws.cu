@@ -259,16 +259,14 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
         const unsigned long long tag_i = (unsigned long long)((epoch << 2) | kLbInclusive) << 32;
         struct Run { unsigned g, s, c; };  // first index in keys_out, first index in the tile buffer, length
         WS_PROF_DECL;
-        auto offsets = [&](unsigned p, unsigned t) -> Run {
+        struct Scan { unsigned pub, e; };
+        // part 1: digit counts of the tile, exclusive scan over the digit values, publish the tile's count of this digit
+        auto scan_publish = [&](unsigned p, unsigned t, Scan &sc) {
             WS_PROF_BEGIN();
             unsigned *col = tab + p * kWsWorkerWarps * ROW + d;
-            unsigned short cw[kWsWorkerWarps];  // (a warp's segment has < 65536 keys)
             unsigned count = 0;
 #pragma unroll
-            for (int w = 0; w < kWsWorkerWarps; w++) {
-                cw[w] = (unsigned short)col[w * ROW];
-                count += cw[w];
-            }
+            for (int w = 0; w < kWsWorkerWarps; w++) count += col[w * ROW];
             unsigned pub = count;  // without the padding of a partial tile (counted as digit 255)
             const size_t tile_end = (size_t)t * TILE + TILE;
             if (tile_end > n && d == kRadixSize - 1) pub -= (unsigned)(tile_end - n);
@@ -284,16 +282,19 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
             unsigned add = 0;
 #pragma unroll
             for (int j = 0; j < 7; j++) add += (j < (int)hw) ? hscan[p * 8 + j] : 0u;
-            const unsigned e = incl - count + add;
-
-            // publish the tile's digit count, then walk back over the earlier tiles (LB descriptors in flight per step)
+            sc.e = incl - count + add;
+            sc.pub = pub;
+            st_relaxed_u64(lookback + (size_t)t * kRadixSize + d, (t == 0 ? tag_i : tag_p) | pub);
+            WS_PROF_END(0);
+        };
+        // part 2: walk back over the earlier tiles (LB descriptors in flight per step), publish the inclusive count, turn
+        // the (warp, digit) counts into the start of every (warp, digit) run inside the tile buffer
+        auto resolve = [&](unsigned p, unsigned t, const Scan &sc) -> Run {
+            WS_PROF_BEGIN();
+            unsigned *col = tab + p * kWsWorkerWarps * ROW + d;
             unsigned long long *mine = lookback + (size_t)t * kRadixSize + d;
             unsigned excl = 0;
-            WS_PROF_END(0);
-            if (t == 0) {
-                st_relaxed_u64(mine, tag_i | pub);
-            } else {
-                st_relaxed_u64(mine, tag_p | pub);
+            if (t != 0) {
                 long long j = (long long)t - 1;
                 bool done = false;
                 while (!done) {
@@ -318,20 +319,21 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
                     j -= consumed;
                     if (consumed == 0) __nanosleep(40);
                 }
-                st_relaxed_u64(mine, tag_i | (unsigned)(excl + pub));
+                st_relaxed_u64(mine, tag_i | (unsigned)(excl + sc.pub));
             }
             WS_PROF_END(1);
             // shared-memory start of the run: after the runs before it, shifted to its destination's 16-byte phase
             Run r;
             r.g = gbase + excl;
-            const unsigned nat = e + (A - 1) * d;
+            const unsigned nat = sc.e + (A - 1) * d;
             r.s = nat + ((r.g - nat) & (A - 1));
-            r.c = pub;
+            r.c = sc.pub;
             unsigned run = r.s;
 #pragma unroll
-            for (int w = 0; w < kWsWorkerWarps; w++) {
+            for (int w = 0; w < kWsWorkerWarps; w++) {  // (the table still holds the counts scan_publish read)
+                const unsigned c = col[w * ROW];
                 col[w * ROW] = run;
-                run += cw[w];
+                run += c;
             }
             named_bar_arrive(kBarOffsets + p, kWsThreads);
             WS_PROF_END(2);
@@ -393,15 +395,28 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
         named_bar_sync(kBarCounted + 0, kWsThreads);
         unsigned t_cur = ring[0];
         Run r_cur{0, 0, 0};
-        if (t_cur != kWsNoTile) r_cur = offsets(0, t_cur);
+        Scan sc;
+        if (t_cur != kWsNoTile) {
+            scan_publish(0, t_cur, sc);
+            r_cur = resolve(0, t_cur, sc);
+        }
+        // Per iteration: offsets (scan, publish, look-back) of the next tile, then the stores of the current one.
+        // (BCB_WS_FLAGS=4, experiment: publish, store, and only then walk the look-back -- its predecessors have had the
+        // whole store phase to publish, so the walk spins half as long (cycle counters: 214K -> 107K per CTA), but the
+        // bulk copies are then issued while the workers are in their scatter sweep and take longer to get through the
+        // LSU queue (603K -> 771K): 2^30 keys 2.47 ms per pass against 2.41.)
         for (unsigned i = 0; t_cur != kWsNoTile; ++i) {
             WS_PROF_BEGIN();
             named_bar_sync(kBarCounted + ((i + 1) & 1u), kWsThreads);
             WS_PROF_END(7);
             const unsigned t_next = ring[(i + 1) & 3u];
             Run r_next{0, 0, 0};
-            if (t_next != kWsNoTile) r_next = offsets((i + 1) & 1u, t_next);
+            if (t_next != kWsNoTile) {
+                scan_publish((i + 1) & 1u, t_next, sc);
+                if (!(flags & 4)) r_next = resolve((i + 1) & 1u, t_next, sc);
+            }
             store(r_cur, t_next != kWsNoTile);
+            if (t_next != kWsNoTile && (flags & 4)) r_next = resolve((i + 1) & 1u, t_next, sc);
             t_cur = t_next;
             r_cur = r_next;
         }
@@ -432,6 +447,19 @@ static int ws_launch_typed(StreamState *st, const void *kin, void *kout, const v
     kernel<<<(unsigned)grid, kWsThreads, C::SMEM_BYTES, st->stream>>>((const K *)kin, (K *)kout, vin, vout, base, lookback, epoch, n,
                                                                       (unsigned)tiles, shift, tf, st->control + kControlTicket, ticket_base, ws_flags);
     BCB_CUDA_TRY(cudaGetLastError());
+#ifdef BCB_WS_PROFILE
+    {   // mean cycles per CTA and phase (workers 0-7, helpers 8-15); see the WS_PROF_END(k) sites for what k is
+        static unsigned long long host[148 * 16 * 4];
+        cudaStreamSynchronize(st->stream);
+        cudaMemcpyFromSymbol(host, g_ws_prof, sizeof(host));
+        double mean[16] = {};
+        for (size_t b = 0; b < grid; b++)
+            for (int q = 0; q < 16; q++) mean[q] += (double)host[b * 16 + q] / (double)grid;
+        fprintf(stderr, "ws_prof tiles/CTA %.1f | workers: draw %.0f count %.0f wait_offsets %.0f wait_drained %.0f scatter %.0f | helpers: scan %.0f lookback %.0f "
+                        "offsets_out %.0f wait_scattered %.0f issue %.0f edges %.0f drain %.0f wait_counted %.0f\n",
+                (double)tiles / (double)grid, mean[0], mean[1], mean[2], mean[3], mean[4], mean[8], mean[9], mean[10], mean[11], mean[12], mean[13], mean[14], mean[15]);
+    }
+#endif
     return BCB_SUCCESS;
 }
 
