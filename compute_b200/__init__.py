@@ -9,6 +9,13 @@ from ._capi import ComputeError, LIB_PATH, lib  # noqa: F401
 from .algorithm import (  # noqa: F401
     accumulate,
     copy_if,
+    max_element,
+    min_element,
+    minmax_element,
+    set_difference,
+    set_intersection,
+    set_symmetric_difference,
+    set_union,
     count,
     equal,
     is_permutation,

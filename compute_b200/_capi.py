@@ -57,6 +57,8 @@ SIGNATURES = {
     "bcb_count_if": ([_vp, _i, _vp, _sz, _vp, ctypes.POINTER(ctypes.c_ulonglong)], _i),
     "bcb_transform_reduce": ([_vp, _i, _vp, _vp, _sz, _i, _i, _vp, _i], _i),
     "bcb_reduce_by_key": ([_vp, _i, _i, _vp, _vp, _sz, _vp, _vp, _i, ctypes.POINTER(_sz)], _i),
+    "bcb_set_operation": ([_vp, _i, _i, _vp, _sz, _vp, _sz, _vp, ctypes.POINTER(_sz)], _i),
+    "bcb_find_extremum": ([_vp, _i, _vp, _sz, _i, ctypes.POINTER(_sz)], _i),
 }
 
 _lib = None

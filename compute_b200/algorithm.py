@@ -369,10 +369,88 @@ def sort_by_transform(first: torch.Tensor, function, descending: bool = False, q
     sort_by_key(keys, first, descending, queue)
 
 
+SET_OPS = ("union", "intersection", "difference", "symmetric_difference")
+
+
+def _set_operation(which: str, first1: torch.Tensor, first2: torch.Tensor, result: torch.Tensor, queue) -> int:
+    _range(first1)
+    _range(first2, "second range")
+    _range(result, "result")
+    code = dtype_code(first1.dtype)
+    if dtype_code(first2.dtype) != code:
+        raise ValueError("set operations need two ranges of the same value type")
+    # the result may be another integer type of the same width (test_set_union.cpp:24-42 writes int_ into uint_):
+    # same-width integer conversion keeps the bits
+    if result.element_size() != first1.element_size() or result.is_floating_point() != first1.is_floating_point():
+        raise ValueError("result must have the inputs' value type (or an integer type of the same width)")
+    worst = {"union": first1.numel() + first2.numel(), "intersection": min(first1.numel(), first2.numel()),
+             "difference": first1.numel(), "symmetric_difference": first1.numel() + first2.numel()}[which]
+    if result.numel() < worst:
+        # the C ABI writes at most `worst` elements; a shorter result is fine when the caller knows the count
+        # (the reference's tests size it exactly) -- checked after the fact
+        tmp = torch.empty(worst, dtype=first1.dtype, device=first1.device)
+    else:
+        tmp = None
+    count = ctypes.c_size_t()
+    dst = result if tmp is None else tmp
+    check(lib().bcb_set_operation(_q(queue).handle, code, SET_OPS.index(which), first1.data_ptr(), first1.numel(), first2.data_ptr(),
+                                  first2.numel(), dst.data_ptr(), ctypes.byref(count)))
+    n = int(count.value)
+    if tmp is not None:
+        if n > result.numel():
+            raise ValueError(f"result holds {result.numel()} elements, the set {which} has {n}")
+        result.view(torch.uint8)[: n * result.element_size()].copy_(tmp.view(torch.uint8)[: n * result.element_size()])
+    return n
+
+
+def set_union(first1: torch.Tensor, first2: torch.Tensor, result: torch.Tensor, queue: command_queue | None = None) -> int:
+    """set_union(first1, last1, first2, last2, result, queue) -- algorithm/set_union.hpp:120-199.  Returns the count."""
+    return _set_operation("union", first1, first2, result, queue)
+
+
+def set_intersection(first1: torch.Tensor, first2: torch.Tensor, result: torch.Tensor, queue: command_queue | None = None) -> int:
+    """set_intersection(...) -- algorithm/set_intersection.hpp:104-175."""
+    return _set_operation("intersection", first1, first2, result, queue)
+
+
+def set_difference(first1: torch.Tensor, first2: torch.Tensor, result: torch.Tensor, queue: command_queue | None = None) -> int:
+    """set_difference(...) -- algorithm/set_difference.hpp:112-186."""
+    return _set_operation("difference", first1, first2, result, queue)
+
+
+def set_symmetric_difference(first1: torch.Tensor, first2: torch.Tensor, result: torch.Tensor, queue: command_queue | None = None) -> int:
+    """set_symmetric_difference(...) -- algorithm/set_symmetric_difference.hpp:121-199."""
+    return _set_operation("symmetric_difference", first1, first2, result, queue)
+
+
+def _find_extremum(first: torch.Tensor, want_max: bool, queue) -> int:
+    _range(first)
+    idx = ctypes.c_size_t()
+    check(lib().bcb_find_extremum(_q(queue).handle, dtype_code(first.dtype), first.data_ptr(), first.numel(), int(want_max), ctypes.byref(idx)))
+    return int(idx.value)
+
+
+def min_element(first: torch.Tensor, queue: command_queue | None = None) -> int:
+    """min_element(first, last, queue) -- algorithm/min_element.hpp:36-80 (less<T>): index of the first smallest element
+    (0 for an empty range, like the reference's `first`)."""
+    return _find_extremum(first, False, queue)
+
+
+def max_element(first: torch.Tensor, queue: command_queue | None = None) -> int:
+    """max_element(first, last, queue) -- algorithm/max_element.hpp:36-79: index of the first largest element."""
+    return _find_extremum(first, True, queue)
+
+
+def minmax_element(first: torch.Tensor, queue: command_queue | None = None):
+    """minmax_element(first, last, queue) -- algorithm/minmax_element.hpp:33-66: (min_element, max_element)."""
+    return min_element(first, queue), max_element(first, queue)
+
+
 __all__ = [
     "radix_sort", "radix_sort_by_key", "insertion_sort", "sort", "sort_host", "sort_by_key", "stable_sort",
     "stable_sort_by_key", "is_sorted", "exclusive_scan", "inclusive_scan", "partial_sum", "reduce", "accumulate",
     "predicate", "transform_if", "copy_if", "count_if", "count", "transform_reduce", "inner_product", "reduce_by_key",
-    "transform", "equal", "is_permutation", "sort_by_transform",
+    "transform", "equal", "is_permutation", "sort_by_transform", "set_union", "set_intersection", "set_difference",
+    "set_symmetric_difference", "min_element", "max_element", "minmax_element",
 ]
 _ = TORCH_OF_CODE

@@ -225,6 +225,18 @@ BCB_API int bcb_transform_reduce(bcb_stream stream, int dtype, const void *in1, 
 BCB_API int bcb_reduce_by_key(bcb_stream stream, int key_dtype, int val_dtype, const void *keys_in, const void *vals_in,
                               size_t n, void *keys_out, void *vals_out, int op, size_t *count_host);
 
+/* set operations on two SORTED ranges (algorithm/set_union.hpp:120-199, set_intersection.hpp:104-175, set_difference.hpp:
+ * 112-186, set_symmetric_difference.hpp:121-199; std::set_* multiset semantics, equal elements: first range first):
+ * flags by binary search -> the library's scan -> scatter.  out must hold the result (na + nb elements always do) and
+ * must not overlap a or b.  *count_host = number written (the reference returns result + count: blocks). */
+typedef enum bcb_set_op { BCB_SET_UNION = 0, BCB_SET_INTERSECTION = 1, BCB_SET_DIFFERENCE = 2, BCB_SET_SYMMETRIC_DIFFERENCE = 3 } bcb_set_op;
+BCB_API int bcb_set_operation(bcb_stream stream, int dtype, int which, const void *a, size_t na, const void *b, size_t nb,
+                              void *out, size_t *count_host);
+/* min_element / max_element (algorithm/min_element.hpp, max_element.hpp with less<T>;
+ * detail/find_extrema_with_reduce.hpp:77-316): index of the FIRST smallest / largest element (ties: smaller index,
+ * :156-158); n < 2 -> 0.  The reference returns an iterator, a host value: blocks. */
+BCB_API int bcb_find_extremum(bcb_stream stream, int dtype, const void *in, size_t n, int want_max, size_t *index_host);
+
 #ifdef __cplusplus
 }
 #endif

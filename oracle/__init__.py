@@ -388,3 +388,63 @@ def sort_by_transform(x: np.ndarray, function: str, descending: bool = False) ->
     if x.size < 2:
         return x.copy()
     return sort_by_key(apply_unary(x, function), x.copy(), descending)[1]
+
+
+# ---- second batch of callers: set operations on sorted ranges, extrema ----
+def set_operation(which: str, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """std::set_union / set_intersection / set_difference / set_symmetric_difference restated as the two-pointer merge
+    the standard (and set_union.hpp:120-199 etc. of the reference, through its serial definitions) specifies: multiset
+    semantics, equal elements taken from the first range first.  Pure Python loop: small inputs only."""
+    a = np.ascontiguousarray(a)
+    b = np.ascontiguousarray(b)
+    out = []
+    i = j = 0
+    na, nb = a.size, b.size
+    while i < na and j < nb:
+        if a[i] < b[j]:
+            if which in ("union", "difference", "symmetric_difference"):
+                out.append(a[i])
+            i += 1
+        elif b[j] < a[i]:
+            if which in ("union", "symmetric_difference"):
+                out.append(b[j])
+            j += 1
+        else:
+            if which in ("union", "intersection"):
+                out.append(a[i])
+            i += 1
+            j += 1
+    if which in ("union", "difference", "symmetric_difference"):
+        out.extend(a[i:])
+    if which in ("union", "symmetric_difference"):
+        out.extend(b[j:])
+    return np.array(out, dtype=a.dtype)
+
+
+def set_operation_counting(which: str, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """The same results from the multiset-count definition (value v appears max / min / a-b / |a-b| times), vectorised
+    with numpy for large inputs; cross-checked against set_operation() by the CPU tests."""
+    a = np.ascontiguousarray(a)
+    b = np.ascontiguousarray(b)
+    vals = np.union1d(a, b)
+    ca = np.searchsorted(a, vals, "right") - np.searchsorted(a, vals, "left")
+    cb = np.searchsorted(b, vals, "right") - np.searchsorted(b, vals, "left")
+    if which == "union":
+        c = np.maximum(ca, cb)
+    elif which == "intersection":
+        c = np.minimum(ca, cb)
+    elif which == "difference":
+        c = np.maximum(ca - cb, 0)
+    else:
+        c = np.abs(ca - cb)
+    return np.repeat(vals, c).astype(a.dtype)
+
+
+def min_element(x: np.ndarray) -> int:
+    """min_element.hpp / detail/find_extrema_with_reduce.hpp:156-158: index of the FIRST smallest element (0 if empty)."""
+    return int(np.argmin(x)) if x.size else 0
+
+
+def max_element(x: np.ndarray) -> int:
+    """max_element.hpp: index of the FIRST largest element (ties: the smaller index, find_extrema_with_reduce.hpp:156-158)."""
+    return int(np.argmax(x)) if x.size else 0

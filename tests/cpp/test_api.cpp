@@ -526,6 +526,81 @@ static void test_sort_callers(compute::command_queue &queue)
     }
 }
 
+// second batch of callers: set operations on sorted ranges, extrema, valarray reductions
+static void test_set_operations_and_extrema(compute::command_queue &queue)
+{
+    compute::context context = queue.get_context();
+    {   // test_set_union.cpp:24-42, test_set_intersection.cpp:24-41, test_set_difference.cpp:24-41, test_set_symmetric_difference.cpp:24-42
+        int dataset1[] = {1, 1, 2, 2, 2, 2, 3, 3, 4, 5, 6, 10};
+        int dataset2[] = {0, 2, 2, 4, 5, 6, 8, 8, 9, 9, 9, 13};
+        compute::vector<int> set1(dataset1, dataset1 + 12, queue), set2(dataset2, dataset2 + 12, queue);
+        compute::vector<unsigned> result(19, context);  // (the reference's tests write int_ sets into a uint_ vector)
+        compute::vector<unsigned>::iterator iter =
+            compute::set_union(set1.begin(), set1.begin() + 12, set2.begin(), set2.begin() + 12, result.begin(), queue);
+        CHECK(iter == result.begin() + 19);
+        CHECK(to_host(result, queue) == (std::vector<unsigned>{0, 1, 1, 2, 2, 2, 2, 3, 3, 4, 5, 6, 8, 8, 9, 9, 9, 10, 13}));
+        compute::vector<int> r2(24, context);
+        compute::fill(r2.begin(), r2.end(), -1, queue);
+        CHECK(compute::set_intersection(set1.begin(), set1.end(), set2.begin(), set2.end(), r2.begin(), queue) == r2.begin() + 5);
+        std::vector<int> h = to_host(r2, queue);
+        CHECK((std::vector<int>(h.begin(), h.begin() + 6) == std::vector<int>{2, 2, 4, 5, 6, -1}));
+        CHECK(compute::set_difference(set1.begin(), set1.end(), set2.begin(), set2.end(), r2.begin(), queue) == r2.begin() + 7);
+        h = to_host(r2, queue);
+        CHECK((std::vector<int>(h.begin(), h.begin() + 7) == std::vector<int>{1, 1, 2, 2, 3, 3, 10}));
+        CHECK(compute::set_symmetric_difference(set1.begin(), set1.end(), set2.begin(), set2.end(), r2.begin(), queue) == r2.begin() + 14);
+        h = to_host(r2, queue);
+        CHECK((std::vector<int>(h.begin(), h.begin() + 14) == std::vector<int>{0, 1, 1, 2, 2, 3, 3, 8, 8, 9, 9, 9, 10, 13}));
+    }
+    {   // test_set_union.cpp:44-62 (strings), and against std::set_* on longer ranges with many duplicates
+        const char s1[] = "abcccdddeeff", s2[] = "bccdfgh";
+        compute::vector<char> c1(s1, s1 + 12, queue), c2(s2, s2 + 7, queue), out(19, context);
+        CHECK(compute::set_union(c1.begin(), c1.end(), c2.begin(), c2.end(), out.begin(), queue) == out.begin() + 14);
+        std::vector<char> h = to_host(out, queue);
+        CHECK(std::string(h.begin(), h.begin() + 14) == "abcccdddeeffgh");
+        std::vector<int> a(70001), b(50003);
+        for (size_t i = 0; i < a.size(); i++) a[i] = (int)((i * 2654435761u) % 30011u);
+        for (size_t i = 0; i < b.size(); i++) b[i] = (int)((i * 40503u + 17u) % 30011u);
+        std::sort(a.begin(), a.end());
+        std::sort(b.begin(), b.end());
+        compute::vector<int> da(a.begin(), a.end(), queue), db(b.begin(), b.end(), queue), dr(a.size() + b.size(), context);
+        std::vector<int> expect(a.size() + b.size());
+        expect.resize(std::set_union(a.begin(), a.end(), b.begin(), b.end(), expect.begin()) - expect.begin());
+        size_t n = compute::set_union(da.begin(), da.end(), db.begin(), db.end(), dr.begin(), queue) - dr.begin();
+        std::vector<int> got = to_host(dr, queue);
+        CHECK(n == expect.size() && std::equal(expect.begin(), expect.end(), got.begin()));
+        expect.assign(a.size() + b.size(), 0);
+        expect.resize(std::set_symmetric_difference(a.begin(), a.end(), b.begin(), b.end(), expect.begin()) - expect.begin());
+        n = compute::set_symmetric_difference(da.begin(), da.end(), db.begin(), db.end(), dr.begin(), queue) - dr.begin();
+        got = to_host(dr, queue);
+        CHECK(n == expect.size() && std::equal(expect.begin(), expect.end(), got.begin()));
+    }
+    {   // test_extrema.cpp:39-51, :53-75, :259-306
+        compute::vector<int> v(size_t(4096), 0, queue);
+        CHECK(compute::min_element(v.begin(), v.begin(), queue) == v.begin());
+        CHECK(compute::min_element(v.begin(), v.begin() + 1, queue) == v.begin());
+        compute::iota(v.begin(), v.begin() + 512, 1, queue);
+        compute::fill(v.end() - 512, v.end(), 513, queue);
+        CHECK(compute::min_element(v.begin(), v.end(), queue) == v.begin() + 512);
+        CHECK(compute::max_element(v.begin(), v.end(), queue) == v.end() - 512);
+        std::pair<compute::vector<int>::iterator, compute::vector<int>::iterator> mm = compute::minmax_element(v.begin(), v.end(), compute::less<int>(), queue);
+        CHECK(mm.first.read(queue) == 0 && mm.second.read(queue) == 513);
+        compute::vector<int> w(5000, context);
+        compute::iota(w.begin(), w.end(), 0, queue);
+        CHECK(compute::max_element(w.begin(), w.end(), queue) == w.end() - 1);
+        CHECK(compute::min_element(w.begin() + 1000, w.end() - 1000, queue) == w.begin() + 1000);
+        CHECK(compute::max_element(w.begin() + 1000, w.end() - 1000, queue) == w.begin() + 3999);
+    }
+    {   // test_valarray.cpp:44-62
+        int data[] = { 5, 2, 3, 7, 1, 9, 6, 5 };
+        compute::valarray<int> array(data, 8);
+        CHECK(array.size() == 8u);
+        CHECK((array.min)() == 1 && (array.max)() == 9);
+        int d2[] = { 1, 2, 3, 4 };
+        compute::valarray<int> a2(d2, 4);
+        CHECK(a2.sum() == 10);
+    }
+}
+
 int main()
 {
     try {
@@ -540,6 +615,7 @@ int main()
         test_array_and_mapped_view(queue);
         test_scan_and_reduce_callers(queue);
         test_sort_callers(queue);
+        test_set_operations_and_extrema(queue);
         queue.finish();
     } catch(std::exception &e) {
         std::printf("EXCEPTION: %s\n", e.what());

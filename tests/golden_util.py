@@ -39,7 +39,7 @@ def _expand_input(c):
             return np.arange(g["start"], g["start"] + g["n"]).astype(dt)
         if g["kind"] == "fill":
             return np.full(g["n"], g["value"]).astype(dt)
-        raise ValueError(g["kind"])
+        return _expand_gen(g, dt)
     return np.array(c.get("input", []), dtype=dt)
 
 
@@ -196,6 +196,19 @@ def check_case(c, api):
         x = _expand_input(c)
         np.testing.assert_array_equal(api.sort_by_transform(x, c["function"], desc), np.array(c["expected"], dtype=x.dtype), err_msg=c["ref"])
         return
+    if fn.startswith("set_"):
+        x = _expand_input(c)
+        got = api.set_operation(fn[4:], x, np.array(c["input2"], dtype=x.dtype))
+        np.testing.assert_array_equal(got, np.array(c["expected"], dtype=x.dtype), err_msg=c["ref"])
+        return
+    if fn == "extrema":
+        x = _expand_input(c)
+        if "sub_range" in c:
+            lo, hi = c["sub_range"]
+            x = x[lo:hi]
+        assert api.min_element(x) == c["expected_min"], c["ref"]
+        assert api.max_element(x) == c["expected_max"], c["ref"]
+        return
     raise ValueError(fn)
 
 
@@ -205,6 +218,11 @@ def _expand_gen(g, dtype):
         return np.full(n, g["value"], dtype=dtype)
     if g["kind"] == "iota":
         return (np.arange(n) + g.get("start", 0)).astype(dtype)
+    if g["kind"] == "ramp_plateau":  # zeros; 1..ramp at the front; the last `plateau` elements = value (test_extrema.cpp:58-60)
+        k = np.zeros(n, dtype=dtype)
+        k[: g["ramp"]] = np.arange(1, g["ramp"] + 1)
+        k[n - g["plateau"]:] = g["value"]
+        return k
     if g["kind"] == "steps":  # zeros with ones at the given positions, then an inclusive scan (test_reduce_by_key.cpp:63-66)
         k = np.zeros(n, dtype=dtype)
         k[g["at"]] = 1

@@ -198,3 +198,21 @@ def sort_by_transform(x, function, descending=False):
     cb.sort_by_transform(d, function, descending)
     torch.cuda.synchronize()
     return to_host(d, x.dtype)
+
+
+def set_operation(which, a, b):
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    d_out = to_dev(np.full((a.size + b.size + 3) * a.dtype.itemsize, 0x5A, dtype=np.uint8).view(a.dtype))
+    n = getattr(cb, "set_" + which)(to_dev(a), to_dev(b), d_out)
+    torch.cuda.synchronize()
+    out = to_host(d_out, a.dtype)
+    assert np.all(out[n:].view(np.uint8) == 0x5A), "set operation wrote past its count"
+    return out[:n]
+
+
+def min_element(x):
+    return cb.min_element(to_dev(np.ascontiguousarray(x)))
+
+
+def max_element(x):
+    return cb.max_element(to_dev(np.ascontiguousarray(x)))

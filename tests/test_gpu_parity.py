@@ -733,3 +733,50 @@ def test_sort_callers_is_permutation_and_sort_by_transform(dtype, gpu):
         for fn in ("abs", "negate", "square"):
             assert gpu.sort_by_transform(x, fn).tobytes() == oracle.sort_by_transform(x, fn).tobytes(), (dtype, n, fn)
         assert gpu.sort_by_transform(x, "abs", True).tobytes() == oracle.sort_by_transform(x, "abs", True).tobytes()
+
+
+# ------------------------------------------------------------------ round 2: set operations on sorted ranges, extrema
+@pytest.mark.parametrize("which", ["union", "intersection", "difference", "symmetric_difference"])
+@pytest.mark.parametrize("dtype", ["int", "uchar", "ulong", "float", "short"])
+def test_set_operations_match_oracle(which, dtype, gpu):
+    rng = np.random.default_rng(11)
+    npdt = NPD[dtype]
+    for na, nb, hi in ((0, 0, 5), (0, 9, 5), (7, 0, 5), (1, 1, 2), (100, 120, 10), (5_000, 3_000, 200), (70_001, 50_003, 30_011), (300_000, 1, 1000)):
+        if np.dtype(npdt).kind == "f":
+            a = np.sort((rng.integers(0, hi, size=na) * 0.5 - hi / 4).astype(npdt))
+            b = np.sort((rng.integers(0, hi, size=nb) * 0.5 - hi / 4).astype(npdt))
+        else:
+            top = min(hi, int(np.iinfo(npdt).max))
+            a = np.sort(rng.integers(0, top, size=na).astype(npdt))
+            b = np.sort(rng.integers(0, top, size=nb).astype(npdt))
+        got = gpu.set_operation(which, a, b)
+        exp = oracle.set_operation(which, a, b) if na + nb <= 10_000 else oracle.set_operation_counting(which, a, b)
+        assert got.tobytes() == exp.tobytes(), (which, dtype, na, nb)
+
+
+def test_set_union_large_disjoint_and_identical(gpu):
+    n = 3_000_000
+    a = np.arange(0, 2 * n, 2, dtype=np.int32)
+    b = np.arange(1, 2 * n, 2, dtype=np.int32)
+    assert np.array_equal(gpu.set_operation("union", a, b), np.arange(2 * n, dtype=np.int32))
+    assert gpu.set_operation("intersection", a, b).size == 0
+    assert np.array_equal(gpu.set_operation("symmetric_difference", a, a), a[:0])
+    assert np.array_equal(gpu.set_operation("difference", a, a[::2].copy()), a[1::2])
+
+
+@pytest.mark.parametrize("dtype", ["char", "uchar", "short", "int", "uint", "long", "ulong", "float", "double"])
+def test_extrema_first_occurrence(dtype, gpu):
+    rng = np.random.default_rng(5)
+    npdt = NPD[dtype]
+    for n in (1, 2, 33, 1000, 4097, 65_537, 1_000_003, 5_000_011):
+        if np.dtype(npdt).kind == "f":
+            x = rng.integers(-50, 50, size=n).astype(npdt) / 4
+        else:
+            info = np.iinfo(npdt)
+            x = rng.integers(max(info.min, -50), min(info.max, 50) + 1, size=n).astype(npdt)  # few distinct values: ties everywhere
+        assert gpu.min_element(x) == oracle.min_element(x), (dtype, n)
+        assert gpu.max_element(x) == oracle.max_element(x), (dtype, n)
+    x = np.zeros(100_000, dtype=npdt)
+    assert gpu.min_element(x) == 0 and gpu.max_element(x) == 0
+    x[77_777] = 1
+    assert gpu.max_element(x) == 77_777 and gpu.min_element(x) == 0

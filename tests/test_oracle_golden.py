@@ -98,3 +98,14 @@ def test_cpu_device_algorithms_match_serial_definitions():
         oracle.scan_on_cpu_i32(x, out, excl, 5 if excl else 0, 8)
         np.testing.assert_array_equal(out, oracle.scan(x, "plus", excl, 5 if excl else 0))
     assert oracle.reduce_on_cpu_i32(x, 8) == int(oracle.reduce(x, "plus"))
+
+
+def test_set_operations_two_pointer_equals_multiset_counts():
+    """the two restatements of std::set_* (merge loop / multiset counts) agree, duplicates and empty ranges included"""
+    rng = np.random.default_rng(3)
+    for na, nb, hi in ((0, 0, 5), (0, 7, 5), (9, 0, 5), (50, 60, 8), (300, 200, 40), (257, 1000, 1000)):
+        a = np.sort(rng.integers(0, hi, size=na).astype(np.int32))
+        b = np.sort(rng.integers(0, hi, size=nb).astype(np.int32))
+        for which in ("union", "intersection", "difference", "symmetric_difference"):
+            x, y = oracle.set_operation(which, a, b), oracle.set_operation_counting(which, a, b)
+            assert x.tobytes() == y.tobytes(), (which, na, nb)
