@@ -985,6 +985,35 @@ static int *spec_flag(StreamState *st) { return reinterpret_cast<int *>(st->cont
 static unsigned long long *spec_fallback_counter(StreamState *st) { return st->control + kControlSpecFallbacks; }
 
 // histogram of every digit position + per-digit exclusive scan, then one pass per digit
+// histogram of every digit position of the transformed keys, one read (hist: [sizeof(K)][256], zeroed by the caller)
+template <typename K>
+static int launch_histogram(StreamState *st, const void *src_keys, size_t n, unsigned *hist, const Transform &tf, const int *gate)
+{
+    const bool ident = (tf.nm | tf.xc | tf.fa) == 0;
+    if (n >= ((size_t)1 << 22)) {  // one counter column per lane (conflict-free), one CTA per SM
+        constexpr int COLS = sizeof(K) == 8 ? 16 : 32;
+        constexpr size_t kSmem = sizeof(K) * kRadixSize * COLS * sizeof(unsigned);
+        auto kernel = ident ? radix_histogram_columns<K, COLS, true> : radix_histogram_columns<K, COLS, false>;
+        static std::atomic<unsigned long long> configured[2];  // bit per device
+        const unsigned long long bit = st->device < 64 ? (1ull << st->device) : 0ull;
+        if (!(configured[ident].load(std::memory_order_acquire) & bit) || !bit) {
+            BCB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+            configured[ident].fetch_or(bit, std::memory_order_release);
+        }
+        LaunchTimer timer(st, gate ? BCB_K_OTHER : BCB_K_RADIX_HISTOGRAM);
+        kernel<<<(unsigned)st->sm_count, 1024, kSmem, st->stream>>>((const K *)src_keys, n, hist, tf, gate);
+    } else {
+        size_t blocks = (n * sizeof(K) + (size_t)kHistThreads * 32 - 1) / ((size_t)kHistThreads * 32);
+        const size_t cap = (size_t)st->sm_count * (2048 / kHistThreads);
+        if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
+        LaunchTimer timer(st, gate ? BCB_K_OTHER : BCB_K_RADIX_HISTOGRAM);
+        radix_histogram<K><<<(unsigned)blocks, kHistThreads, 0, st->stream>>>((const K *)src_keys, n, hist, tf, gate);
+    }
+    BCB_CUDA_TRY(cudaGetLastError());
+    return BCB_SUCCESS;
+}
+
 template <typename K, int VB>
 static int sort_passes(StreamState *st, void *keys, void *values, size_t n, const Transform &tf, const void *src_keys,
                        const void *src_vals, int pass_kind, const int *gate)
@@ -1006,28 +1035,7 @@ static int sort_passes(StreamState *st, void *keys, void *values, size_t n, cons
     unsigned *base = st->hist + 8 * kRadixSize;
     BCB_CUDA_TRY(cudaMemsetAsync(hist, 0, NPASS * kRadixSize * sizeof(unsigned), st->stream));
     {
-        const bool ident = (tf.nm | tf.xc | tf.fa) == 0;
-        if (n >= ((size_t)1 << 22)) {  // one counter column per lane (conflict-free), one CTA per SM
-            constexpr int COLS = sizeof(K) == 8 ? 16 : 32;
-            constexpr size_t kSmem = sizeof(K) * kRadixSize * COLS * sizeof(unsigned);
-            auto kernel = ident ? radix_histogram_columns<K, COLS, true> : radix_histogram_columns<K, COLS, false>;
-            static std::atomic<unsigned long long> configured[2];  // bit per device
-            const unsigned long long bit = st->device < 64 ? (1ull << st->device) : 0ull;
-            if (!(configured[ident].load(std::memory_order_acquire) & bit) || !bit) {
-                BCB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
-                configured[ident].fetch_or(bit, std::memory_order_release);
-            }
-            LaunchTimer timer(st, gate ? BCB_K_OTHER : BCB_K_RADIX_HISTOGRAM);
-            kernel<<<(unsigned)st->sm_count, 1024, kSmem, st->stream>>>((const K *)src_keys, n, hist, tf, gate);
-        } else {
-            size_t blocks = (n * sizeof(K) + (size_t)kHistThreads * 32 - 1) / ((size_t)kHistThreads * 32);
-            const size_t cap = (size_t)st->sm_count * (2048 / kHistThreads);
-            if (blocks > cap) blocks = cap;
-            if (blocks < 1) blocks = 1;
-            LaunchTimer timer(st, gate ? BCB_K_OTHER : BCB_K_RADIX_HISTOGRAM);
-            radix_histogram<K><<<(unsigned)blocks, kHistThreads, 0, st->stream>>>((const K *)src_keys, n, hist, tf, gate);
-        }
-        BCB_CUDA_TRY(cudaGetLastError());
+        BCB_TRY((launch_histogram<K>(st, src_keys, n, hist, tf, gate)));
         {
             LaunchTimer timer(st, gate ? BCB_K_OTHER : BCB_K_DIGIT_SCAN);
             digit_scan<<<NPASS, kRadixSize, 0, st->stream>>>(hist, base, gate, gate ? spec_fallback_counter(st) : nullptr);
@@ -1288,6 +1296,35 @@ static int split_transform(int key_dtype, int ascending, const unsigned long lon
     *tf = make_transform(key_dtype, ascending != 0);
     tf->nsplit = (int)num_splitters;
     for (size_t j = 0; j < (size_t)kMaxSplitters; j++) tf->split[j] = j < num_splitters ? splitters_host[j] : ~0ull;
+    return BCB_SUCCESS;
+}
+
+int bcb_radix_top_histogram(bcb_stream stream, int key_dtype, int ascending, const void *keys, size_t n, unsigned long long *counts_host)
+{
+    if (!counts_host) return BCB_EINVAL;
+    const size_t w = dtype_size(key_dtype);
+    if (!w) return BCB_EINVAL;
+    for (int d = 0; d < kRadixSize; d++) counts_host[d] = 0;
+    if (n == 0) return BCB_SUCCESS;
+    if (!keys) return BCB_EINVAL;
+    if (n >= 0xffff0000ull) return BCB_ETOOLARGE;
+    StreamState *st;
+    BCB_TRY(stream_state((cudaStream_t)stream, &st));
+    const Transform tf = make_transform(key_dtype, ascending != 0);
+    unsigned *hist = st->hist;
+    BCB_CUDA_TRY(cudaMemsetAsync(hist, 0, w * kRadixSize * sizeof(unsigned), st->stream));
+    int rc;
+    switch (w) {
+    case 1: rc = launch_histogram<unsigned char>(st, keys, n, hist, tf, nullptr); break;
+    case 2: rc = launch_histogram<unsigned short>(st, keys, n, hist, tf, nullptr); break;
+    case 4: rc = launch_histogram<unsigned>(st, keys, n, hist, tf, nullptr); break;
+    default: rc = launch_histogram<unsigned long long>(st, keys, n, hist, tf, nullptr); break;
+    }
+    BCB_TRY(rc);
+    unsigned host[kRadixSize];
+    BCB_CUDA_TRY(cudaMemcpyAsync(host, hist + (w - 1) * kRadixSize, sizeof(host), cudaMemcpyDeviceToHost, st->stream));
+    BCB_CUDA_TRY(cudaStreamSynchronize(st->stream));
+    for (int d = 0; d < kRadixSize; d++) counts_host[d] = host[d];
     return BCB_SUCCESS;
 }
 

@@ -76,6 +76,36 @@ def select_splitters(all_samples: np.ndarray, world: int) -> np.ndarray:
     return s[np.minimum(pos, s.size - 1)]
 
 
+def histogram_plan(all_hist: np.ndarray, world: int, key_bits: int, max_imbalance: float = 1.06):
+    """Splitters and the P x P count matrix from the all-gathered 256-bin histograms of the keys' most significant digit
+    (all_hist[src][digit]).  Rank d is dealt the digit values [b_d, b_(d+1)); the boundaries are the bin edges whose
+    cumulative global count is closest to d * N / P.  Returns (splitters uint64[P-1] in transformed-key space,
+    counts int64[P][P] = counts[src][dst], imbalance = largest receive count * P / N), or None when whole digit values
+    cannot be dealt evenly enough (skewed keys: the caller samples instead).  Deterministic: every rank computes the same."""
+    h = np.asarray(all_hist, dtype=np.int64).reshape(world, 256)
+    tot = h.sum(axis=0)
+    n = int(tot.sum())
+    if n == 0 or world <= 1:
+        return None
+    cum = np.cumsum(tot)                                        # cum[b - 1] = keys with digit < b
+    edges = np.zeros(world + 1, dtype=np.int64)
+    edges[world] = 256
+    for d in range(1, world):
+        target = (d * n) // world
+        b = int(np.searchsorted(cum, target, side="left")) + 1  # first edge with at least `target` keys below it
+        below = int(cum[b - 2]) if b >= 2 else 0                # the edge before it
+        if b >= 2 and target - below < int(cum[b - 1]) - target:
+            b -= 1
+        edges[d] = min(max(b, edges[d - 1]), 256)
+    recv = np.array([int(tot[edges[d]:edges[d + 1]].sum()) for d in range(world)], dtype=np.int64)
+    imbalance = float(recv.max() * world / n)
+    if imbalance > max_imbalance:
+        return None
+    counts = np.stack([[int(h[src, edges[d]:edges[d + 1]].sum()) for d in range(world)] for src in range(world)]).astype(np.int64)
+    splitters = (edges[1:world].astype(np.uint64) << np.uint64(key_bits - 8))
+    return splitters, counts, imbalance
+
+
 def exchange_plan(points: np.ndarray, n_local: int):
     """Send counts per destination from the partition points of the sorted shard (points[j] = first index whose
     transformed key is >= splitter j)."""
@@ -155,6 +185,13 @@ class CudaLocalOps:
     @staticmethod
     def _row_bytes(values) -> int:
         return 0 if values is None else values.element_size() * (values.numel() // max(1, values.shape[0]))
+
+    def top_histogram(self, keys, descending: bool) -> np.ndarray:
+        """256-bin histogram of the most significant digit of the transformed keys (int64[256]); blocks."""
+        counts = np.zeros(256, dtype=np.uint64)
+        self._check(self._lib.bcb_radix_top_histogram(self.queue.handle, dtype_code(keys.dtype), int(not descending), keys.data_ptr(),
+                                                      keys.shape[0], counts.ctypes.data))
+        return counts.astype(np.int64)
 
     def partition_counts(self, keys, splitters: np.ndarray, descending: bool) -> np.ndarray:
         counts = np.zeros(splitters.size + 1, dtype=np.uint64)
@@ -301,6 +338,7 @@ class Context:
         # BCB_DIST_PEER=0: always exchange through NCCL all-to-all; BCB_DIST_PROFILE=1: synchronise after every phase
         # and record last_stats["phases_ms"] (diagnostics only -- the synchronisation costs time)
         self.use_peer_memory = os.environ.get("BCB_DIST_PEER", "1") != "0"
+        self.use_histogram_plan = os.environ.get("BCB_DIST_HISTOGRAM", "1") != "0"  # 0: always sample (A/B comparison)
         self.profile = os.environ.get("BCB_DIST_PROFILE", "0") == "1"
         self._flag = None
 
@@ -378,14 +416,26 @@ class Context:
             return select_splitters(self._all_gather_np(tk), P)
 
         self._phase(None)
-        # Preferred plan: evenly spaced samples of the UNSORTED shard -> splitters -> ONE stable partition pass
-        # (bucket = number of splitters <= transformed key) whose stores go straight into the destination ranks'
-        # receive buffers over NVLink -> one local sort out of the receive buffer.
+        vb = 0 if values is None else values.element_size() * (values.numel() // max(1, values.shape[0]))
+        peer_ok = (self.use_peer_memory and hasattr(self.ops, "partition_scatter") and not self.peer.failed and P - 1 <= 7
+                   and vb in (0, 4, 8))
+        # Preferred plan: ONE stable partition pass (bucket = number of splitters <= transformed key) whose stores go
+        # straight into the destination ranks' receive buffers over NVLink -> one local sort out of the receive buffer.
+        # Splitters and send counts come, when the keys allow it, from ONE exchange: the all-gathered 256-bin
+        # histograms of the most significant digit deal whole digit values to the ranks (exact counts, no sampling, no
+        # count pass); skewed keys (a few digit values hold most of them) fall back to regular samples of the
+        # unsorted shard + a count pass.
+        if peer_ok and self.use_histogram_plan and hasattr(self.ops, "top_histogram"):
+            hist = self.ops.top_histogram(keys, descending) if n_local else np.zeros(256, np.int64)
+            plan = histogram_plan(self._all_gather_np(hist), P, keys.element_size() * 8)
+            self._phase("histogram")
+            if plan is not None:
+                done = self._sort_peer(keys, values, descending, plan[0], vb, counts=plan[1])
+                if done is not None:
+                    return done
         splitters = sample_splitters(keys)
         self._phase("sample")
-        vb = 0 if values is None else values.element_size() * (values.numel() // max(1, values.shape[0]))
-        if (self.use_peer_memory and hasattr(self.ops, "partition_scatter") and not self.peer.failed and P - 1 <= 7
-                and vb in (0, 4, 8)):
+        if peer_ok and not self.peer.failed:
             done = self._sort_peer(keys, values, descending, splitters, vb)
             if done is not None:
                 return done
@@ -416,13 +466,18 @@ class Context:
                            "imbalance": float(counts.sum(axis=0).max() * P / max(1, counts.sum()))}
         return out_keys if values is None else (out_keys, out_vals)
 
-    def _sort_peer(self, keys, values, descending, splitters, vb):
-        """The peer-memory plan (see sort).  Returns None -- collectively -- when the buffers cannot be mapped."""
+    def _sort_peer(self, keys, values, descending, splitters, vb, counts=None):
+        """The peer-memory plan (see sort).  Returns None -- collectively -- when the buffers cannot be mapped.
+        ``counts``: the P x P matrix when the caller already has it (histogram plan); else a count pass + all-gather."""
         P, me = self.world, self.rank
         ksize = keys.element_size()
-        send = self.ops.partition_counts(keys, splitters, descending)
-        self._phase("counts")
-        counts = self._all_gather_np(send)                               # counts[src][dst]
+        from_histogram = counts is not None
+        if counts is None:
+            send = self.ops.partition_counts(keys, splitters, descending)
+            self._phase("counts")
+            counts = self._all_gather_np(send)                           # counts[src][dst]
+        else:
+            send = counts[me]
         recv_tot = counts.sum(axis=0)
         max_recv = int(recv_tot.max())
         val_off = (max_recv * ksize + 255) & ~255                        # values region of every receive buffer
@@ -441,7 +496,8 @@ class Context:
         out_vals = self.ops.empty(n_out, values) if values is not None else None
         self.ops.sort_copy(self.peer.local, out_keys, self.peer.local + val_off, out_vals, descending)
         self._phase("sort")
-        self.last_stats = {"plan": "peer-scatter", "phases_ms": dict(self._phases) if self.profile else None,
+        self.last_stats = {"plan": "peer-scatter", "splitters": "top-digit histogram" if from_histogram else "regular samples",
+                           "phases_ms": dict(self._phases) if self.profile else None,
                            "sent": int(send.sum() - send[me]), "received": n_out,
                            "imbalance": float(recv_tot.max() * P / max(1, counts.sum()))}
         return out_keys if values is None else (out_keys, out_vals)

@@ -153,6 +153,13 @@ BCB_API int bcb_partition_by_splitters(bcb_stream stream, int key_dtype, int asc
                                        const unsigned long long *splitters_host, size_t num_splitters,
                                        unsigned long long *counts_host);
 
+/* 256-bin histogram of the MOST SIGNIFICANT 8-bit digit of the transformed keys (the order the sort is defined by), one
+ * read of the range -- the first step of the multi-GPU sort when the key distribution lets whole digit values be dealt
+ * to the ranks: the all-gathered histograms give the splitters AND the P x P count matrix in one exchange (no sampling,
+ * no separate count pass).  Blocks. */
+BCB_API int bcb_radix_top_histogram(bcb_stream stream, int key_dtype, int ascending, const void *keys, size_t n,
+                                    unsigned long long *counts_host /* [256] */);
+
 /* The two halves of the partition as separate calls, for the multi-GPU sort that scatters straight into its peers'
  * receive buffers: bcb_partition_counts returns the bucket sizes (blocks); the host layer exchanges them, derives where
  * this rank's slice of every bucket starts inside each destination rank's buffer, and bcb_partition_scatter then writes

@@ -43,6 +43,27 @@ def test_splitters_and_plan():
     assert cbd.fold_carry(p, 2, "max", None) == 7
 
 
+def test_histogram_plan_deals_whole_digit_values():
+    rng = np.random.default_rng(7)
+    for world in (2, 3, 4, 8):
+        keys = [rng.integers(0, 2**32, size=50_000 + 1000 * r, dtype=np.uint64) for r in range(world)]
+        allh = np.stack([np.bincount((k >> np.uint64(24)).astype(np.int64), minlength=256) for k in keys])
+        plan = cbd.histogram_plan(allh, world, 32)
+        assert plan is not None
+        splitters, counts, imbalance = plan
+        assert splitters.size == world - 1 and np.all(np.diff(splitters.astype(np.int64)) >= 0) and imbalance < 1.06
+        for src, k in enumerate(keys):  # the counts ARE the bucket sizes the exchange pass will produce
+            bucket = np.searchsorted(splitters, k, side="right")
+            np.testing.assert_array_equal(np.bincount(bucket, minlength=world), counts[src])
+    # skewed keys (everything in three digit values): no even deal of whole digit values -> None (the caller samples)
+    skew = np.zeros((4, 256), dtype=np.int64)
+    skew[:, 7] = 1000
+    skew[:, 8] = 10
+    skew[:, 200] = 5
+    assert cbd.histogram_plan(skew, 4, 32) is None
+    assert cbd.histogram_plan(np.zeros((2, 256), np.int64), 2, 32) is None  # globally empty range
+
+
 class OracleLocalOps:
     """CPU stand-in for CudaLocalOps used ONLY by this test: same interface, oracle semantics, CPU tensors."""
     device_type = "cpu"
@@ -88,6 +109,13 @@ class OracleLocalOps:
         bits = k.view({1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[k.dtype.itemsize])
         tk = cbd.transformed_keys(bits, dtype_code(k.dtype), not descending)
         return np.searchsorted(splitters, tk, side="right")
+
+    def top_histogram(self, keys, descending):
+        k = self._np(keys)
+        w = k.dtype.itemsize
+        bits = k.view({1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[w])
+        tk = cbd.transformed_keys(bits, dtype_code(k.dtype), not descending)
+        return np.bincount((tk >> np.uint64(8 * w - 8)).astype(np.int64), minlength=256).astype(np.int64)
 
     def partition_counts(self, keys, splitters, descending):
         return np.bincount(self._buckets(keys, splitters, descending), minlength=splitters.size + 1).astype(np.int64)
@@ -210,6 +238,7 @@ def _worker(rank, world, port, results):
         big = rng.integers(0, 2**32, size=60_000, dtype=np.uint64).astype(np.uint32)
         blo, bhi = rank * 60_000 // world, (rank + 1) * 60_000 // world
         out["big"] = ctx.sort(torch.from_numpy(big[blo:bhi].copy())).numpy().copy()
+        out["stats_big"] = dict(ctx.last_stats)
         ctx.use_peer_memory = False     # NCCL-style all-to-all plan: same bytes
         k1, v1 = ctx.sort(torch.from_numpy(keys[lo:hi].copy()), torch.from_numpy(vals[lo:hi].copy()))
         out["pairs_k1"], out["pairs_v1"] = k1.numpy().copy(), v1.numpy().copy()
@@ -279,6 +308,11 @@ def test_gloo_ranks_match_single_device_oracle(world):
     assert [r["stats_fb"]["plan"] for r in res] == ["partition"] * world
     assert all(r["empty"] == 0 for r in res)
     assert res[0]["stats"]["plan"] == "peer-scatter" and res[0]["stats1"]["plan"] == "partition"
+    # uniform 32-bit keys are dealt by the top-digit histogram (one exchange).  The small ints of the pair sort occupy two
+    # digit values (negative / non-negative): an even deal for 2 ranks, too skewed for 3 (regular samples + count pass)
+    assert all(r["stats_big"]["splitters"] == "top-digit histogram" for r in res), res[0]["stats_big"]
+    want = "top-digit histogram" if world == 2 else "regular samples"
+    assert all(r["stats"]["splitters"] == want for r in res), res[0]["stats"]
     assert res[0]["stats2"]["plan"] == "sort-and-cut"
     assert res[0]["stats"]["imbalance"] < 1.6
     x = rng.integers(-2**31, 2**31 - 1, size=9001).astype(np.int32)

@@ -780,3 +780,26 @@ def test_extrema_first_occurrence(dtype, gpu):
     assert gpu.min_element(x) == 0 and gpu.max_element(x) == 0
     x[77_777] = 1
     assert gpu.max_element(x) == 77_777 and gpu.min_element(x) == 0
+
+
+@pytest.mark.parametrize("dtype", ["uchar", "short", "int", "uint", "float", "long", "double"])
+def test_top_digit_histogram_matches_transformed_keys(dtype, gpu):
+    """bcb_radix_top_histogram (first step of the multi-GPU sort's histogram plan): 256 bins of the most significant digit
+    of the TRANSFORMED key, both orders, small (plain kernel) and large (lane-column kernel) ranges."""
+    import ctypes
+    import compute_b200 as cb
+    from compute_b200 import distributed as cbd
+    from compute_b200.core import dtype_code
+    npdt = np.dtype(NPD[dtype])
+    w = npdt.itemsize
+    for n in (0, 1, 1000, 100_003, (1 << 22) + 77):
+        k = random_keys(dtype, n, seed=n % 97, mode="bits") if n else np.zeros(0, npdt)
+        d = gpu.to_dev(k) if n else None
+        bits = k.view({1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[w])
+        for desc in (False, True):
+            counts = np.zeros(256, dtype=np.uint64)
+            cb._capi.check(cb.lib().bcb_radix_top_histogram(cb.command_queue().handle, dtype_code(npdt), int(not desc),
+                                                            d.data_ptr() if n else None, n, counts.ctypes.data))
+            tk = cbd.transformed_keys(bits, dtype_code(npdt), not desc)
+            exp = np.bincount((tk >> np.uint64(8 * w - 8)).astype(np.int64), minlength=256)
+            np.testing.assert_array_equal(counts.astype(np.int64), exp, err_msg=f"{dtype} n={n} desc={desc}")
