@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libcompute_b200.so")
-SOURCES = ["runtime.cu", "reduce.cu", "scan.cu", "radix_sort.cu", "radix_pass_ws.cu", "stream_ops.cu", "set_ops.cu"]
+SOURCES = ["runtime.cu", "reduce.cu", "scan.cu", "radix_sort.cu", "radix_pass_ws.cu", "radix_exchange_ws.cu", "stream_ops.cu", "set_ops.cu"]
 HEADERS = ["common.cuh", "ops.cuh", "radix_common.cuh", "tma.cuh", "tile_state.cuh", "scan_ws.cuh", os.path.join("..", "..", "include", "compute_b200.h")]
 NVCC = os.environ.get("NVCC", "nvcc")
 FLAGS = [
@@ -49,10 +49,12 @@ def build(force: bool = False) -> str:
     with cf.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(_compile, SOURCES))
     if force or _mtime(LIB) < max(_mtime(o) for o in objs):
-        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+        tmp = LIB + ".tmp"  # link next to the target, then rename: a reader never sees a half-written library
+        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        os.replace(tmp, LIB)
     return LIB
 
 

@@ -160,4 +160,8 @@ int ws_launch_pass(StreamState *st, int key_bytes, const void *kin, void *kout, 
 size_t ws_tile_size(int key_bytes, int value_bytes, bool deterministic);
 bool ws_supports(int key_bytes, int value_bytes, bool deterministic);
 
+// warp-specialised exchange pass of the multi-GPU sort (radix_exchange_ws.cu): bucket b of the stable partition by the
+// splitters in tf goes to tf.dst_keys[b] / tf.dst_vals[b].  BCB_EUNSUPPORTED for shapes it does not cover.
+int ws_exchange_pass(StreamState *st, int key_bytes, const void *kin, const void *vin, int value_bytes, size_t n, const Transform &tf);
+
 }  // namespace bcb

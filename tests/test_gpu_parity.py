@@ -418,9 +418,16 @@ def test_radix_sort_copy_leaves_source_untouched(dtype, value_bytes, n, gpu):
 
 
 @pytest.mark.parametrize("dtype,value_bytes,nsplit,n", [("uint", 0, 1, 1 << 21), ("uint", 0, 7, 1_000_003), ("float", 4, 3, 200_000),
-                                                         ("long", 8, 7, 77_777), ("short", 0, 2, 50_001), ("int", 0, 5, 100)])
-def test_partition_counts_and_scatter_to_separate_buffers(dtype, value_bytes, nsplit, n, gpu):
-    """The multi-GPU exchange on one GPU: every bucket goes to its own destination buffer, stable, with exact counts."""
+                                                         ("long", 8, 7, 77_777), ("short", 0, 2, 50_001), ("int", 0, 5, 100),
+                                                         # >= 2^24 keys: the (opt-in) warp-specialised exchange kernel
+                                                         ("uint", 0, 7, (1 << 24) + 12_345), ("float", 4, 3, (1 << 24) + 5),
+                                                         ("int", 8, 7, 1 << 24), ("ulong", 0, 1, (1 << 24) + 3), ("double", 0, 6, (1 << 24) + 777),
+                                                         ("uint", 0, 0, (1 << 24) + 1)])
+def test_partition_counts_and_scatter_to_separate_buffers(dtype, value_bytes, nsplit, n, gpu, monkeypatch):
+    """The multi-GPU exchange on one GPU: every bucket goes to its own destination buffer (at every 16-byte phase, like a
+    slice inside a peer's receive buffer), stable, with exact counts, nothing written outside the bucket.  Shards of
+    >= 2^24 keys go through the opt-in warp-specialised exchange kernel (BCB_SPLIT_WS=1), the others through the default."""
+    monkeypatch.setenv("BCB_SPLIT_WS", "1" if n >= (1 << 24) else "0")
     import ctypes
     import torch
     import compute_b200 as cb
@@ -444,10 +451,13 @@ def test_partition_counts_and_scatter_to_separate_buffers(dtype, value_bytes, ns
         cb._capi.check(cb.lib().bcb_partition_counts(q.handle, dtype_code(k.dtype), int(not desc), dk.data_ptr(), n, sp.ctypes.data, nsplit,
                                                      counts.ctypes.data))
         np.testing.assert_array_equal(counts.astype(np.int64), exp_counts)
-        outs_k = [torch.zeros(int(c) * w + 16, dtype=torch.uint8, device="cuda") for c in exp_counts]
-        outs_v = [torch.zeros(int(c) * value_bytes + 16, dtype=torch.uint8, device="cuda") for c in exp_counts]
-        pk = (ctypes.c_void_p * (nsplit + 1))(*[t.data_ptr() for t in outs_k])
-        pv = (ctypes.c_void_p * (nsplit + 1))(*[t.data_ptr() for t in outs_v])
+        # bucket b starts `ph` elements into its buffer: keys and values share the element phase, as slices of one
+        # receive buffer do
+        phase = [(b * 3 + 1) % max(1, 16 // w) for b in range(nsplit + 1)]
+        outs_k = [torch.zeros(int(c) * w + 64, dtype=torch.uint8, device="cuda") for c in exp_counts]
+        outs_v = [torch.zeros(int(c) * value_bytes + 128, dtype=torch.uint8, device="cuda") for c in exp_counts]
+        pk = (ctypes.c_void_p * (nsplit + 1))(*[t.data_ptr() + ph * w for t, ph in zip(outs_k, phase)])
+        pv = (ctypes.c_void_p * (nsplit + 1))(*[t.data_ptr() + ph * value_bytes for t, ph in zip(outs_v, phase)])
         cb._capi.check(cb.lib().bcb_partition_scatter(q.handle, dtype_code(k.dtype), int(not desc), dk.data_ptr(),
                                                       None if v is None else dv.data_ptr(), value_bytes, n, sp.ctypes.data, nsplit, pk,
                                                       pv if v is not None else None))
@@ -455,11 +465,14 @@ def test_partition_counts_and_scatter_to_separate_buffers(dtype, value_bytes, ns
         for b in range(nsplit + 1):
             sel = np.flatnonzero(bucket == b)
             got = outs_k[b].cpu().numpy()
-            assert got[: sel.size * w].tobytes() == k[sel].tobytes(), (dtype, desc, b)
-            assert not got[sel.size * w:].any()  # nothing written past the bucket
+            lo = phase[b] * w
+            assert got[lo: lo + sel.size * w].tobytes() == k[sel].tobytes(), (dtype, desc, b)
+            assert not got[:lo].any() and not got[lo + sel.size * w:].any()  # nothing written outside the bucket
             if v is not None:
                 gv = outs_v[b].cpu().numpy()
-                assert gv[: sel.size * value_bytes].tobytes() == v[sel].tobytes(), (dtype, desc, b)
+                lo = phase[b] * value_bytes
+                assert gv[lo: lo + sel.size * value_bytes].tobytes() == v[sel].tobytes(), (dtype, desc, b)
+                assert not gv[:lo].any() and not gv[lo + sel.size * value_bytes:].any()
 
 
 @pytest.mark.parametrize("dtype", ["float", "double"])
