@@ -41,7 +41,7 @@ template <typename K, int VB> struct ExShape {
     static constexpr int A = 16 / MINB;                    // elements per 16-byte chunk of the narrower array
     static constexpr int PER32 = 32 / KB;                  // keys per 32-byte sector
     // keys per worker thread: ONE CONTIGUOUS range of whole sectors (64 u32 / 32 u64 keys, 32 u32+u32 / 16 u32+u64 pairs)
-    static constexpr int ITEMS = 200 * 1024 / (KB + VB) / kExWorkers / PER32 * PER32;
+    static constexpr int ITEMS = 196 * 1024 / (KB + VB) / kExWorkers / PER32 * PER32;
     static constexpr int NS = ITEMS / PER32;               // key sectors per lane
     static constexpr int W = VB == 0 ? 4 : (VB == 4 ? 2 : 1);  // key sectors (+ their values) a lane holds in registers at a time
     static constexpr int SEG = ITEMS * 32;
@@ -49,7 +49,7 @@ template <typename K, int VB> struct ExShape {
     static constexpr int PAD = (A - 1) * kExBuckets + A;
     static constexpr size_t KBUF_BYTES = ((size_t)(TILE + PAD) * KB + 127) / 128 * 128;
     static constexpr size_t VBUF_BYTES = ((size_t)(TILE + PAD) * VB + 127) / 128 * 128;
-    static constexpr size_t CUR_BYTES = (size_t)kExBuckets * kExWorkers * sizeof(unsigned short);    // [8][768] per-thread cursors
+    static constexpr size_t CUR_BYTES = (size_t)kExBuckets * kExWorkers * sizeof(unsigned);          // [8][768] per-thread cursors (bank = thread)
     static constexpr size_t TAB_BYTES = 2 * (size_t)kExWorkerWarps * kExBuckets * sizeof(unsigned);  // [2][24][8]
     static constexpr size_t MISC_BYTES = 64 + 256 + 64;  // tile-id ring, bucket look-up table, splitters
     static constexpr size_t SMEM_BYTES = KBUF_BYTES + VBUF_BYTES + CUR_BYTES + TAB_BYTES + MISC_BYTES;
@@ -71,7 +71,7 @@ __device__ __forceinline__ Sector ld_sector(const void *p, unsigned long long po
 template <typename K, int VB, bool IDENT>
 __global__ void __launch_bounds__(kExThreads, 1)
 exchange_ws(const K *__restrict__ keys_in, const void *__restrict__ vals_in_v, unsigned long long *lookback, unsigned epoch, size_t n,
-            unsigned num_tiles, const __grid_constant__ Transform tf, unsigned long long *ticket, unsigned long long ticket_base)
+            unsigned num_tiles, const __grid_constant__ Transform tf, unsigned long long *ticket, unsigned long long ticket_base, int flags)
 {
     typedef ExShape<K, VB> C;
     typedef typename ex_value<VB>::type V;
@@ -80,7 +80,7 @@ exchange_ws(const K *__restrict__ keys_in, const void *__restrict__ vals_in_v, u
     extern __shared__ __align__(128) unsigned char smem[];
     K *buf = reinterpret_cast<K *>(smem);
     V *vbuf = reinterpret_cast<V *>(smem + C::KBUF_BYTES);
-    unsigned short *cursor = reinterpret_cast<unsigned short *>(smem + C::KBUF_BYTES + C::VBUF_BYTES);  // [8][768]: thread-private next slot per bucket
+    unsigned *cursor = reinterpret_cast<unsigned *>(smem + C::KBUF_BYTES + C::VBUF_BYTES);  // [8][768]: thread-private next slot per bucket
     unsigned *tab = reinterpret_cast<unsigned *>(smem + C::KBUF_BYTES + C::VBUF_BYTES + C::CUR_BYTES);  // [2][24][8]: counts, then run starts
     volatile unsigned *ring = reinterpret_cast<volatile unsigned *>(smem + C::KBUF_BYTES + C::VBUF_BYTES + C::CUR_BYTES + C::TAB_BYTES);  // [4] tile ids
     unsigned char *lut = smem + C::KBUF_BYTES + C::VBUF_BYTES + C::CUR_BYTES + C::TAB_BYTES + 64;  // [256]: bucket of the first key of a top-byte bin | 8 if a splitter lies inside the bin
@@ -111,7 +111,12 @@ exchange_ws(const K *__restrict__ keys_in, const void *__restrict__ vals_in_v, u
         const unsigned long long keep = l2_policy_evict_last(), drop = l2_policy_evict_first();
         // branch-free: the second look-up is done even where no splitter lies inside the bin (ssplit[lo] is then a
         // splitter beyond the bin or all-ones, and the flag masks the compare out)
+        // Default: the splitter compares in registers (3.5 / 3.6 / 4.0 ms per 2^30 keys for 1 / 3 / 7 splitters).  The table
+        // look-up (BCB_SPLIT_WS_FLAGS=1) needs fewer instructions but puts two dependent shared-memory loads in front of
+        // every key: 4.3 ms whatever the splitter count -- the sweeps are latency bound, not issue bound.
+        const bool by_compares = (flags & 1) == 0;
         auto bucket = [&](K raw) -> unsigned {
+            if (by_compares) return pass_digit<K, kDigitSplit>(raw, 0, tf);
             const U t = IDENT ? (U)raw : transform_fwd<K>(raw, tf);
             const unsigned e = lut[(unsigned)(t >> TOPSHIFT)];
             return (e & 7u) + ((e >> 3) & (t >= ssplit[e & 7u] ? 1u : 0u));
@@ -200,19 +205,19 @@ exchange_ws(const K *__restrict__ keys_in, const void *__restrict__ vals_in_v, u
             {   // this thread's cursors: start of the (warp, bucket) run + the keys of that bucket in the lower lanes
                 const uint4 a = *reinterpret_cast<const uint4 *>(tab + (p * kExWorkerWarps + w) * NB);
                 const uint4 c = *reinterpret_cast<const uint4 *>(tab + (p * kExWorkerWarps + w) * NB + 4);
-                cursor[0 * kExWorkers + tid] = (unsigned short)(a.x + (unsigned)(lx.lo & 0xffffu));
-                cursor[1 * kExWorkers + tid] = (unsigned short)(a.y + (unsigned)((lx.lo >> 16) & 0xffffu));
-                cursor[2 * kExWorkers + tid] = (unsigned short)(a.z + (unsigned)((lx.lo >> 32) & 0xffffu));
-                cursor[3 * kExWorkers + tid] = (unsigned short)(a.w + (unsigned)(lx.lo >> 48));
-                cursor[4 * kExWorkers + tid] = (unsigned short)(c.x + (unsigned)(lx.hi & 0xffffu));
-                cursor[5 * kExWorkers + tid] = (unsigned short)(c.y + (unsigned)((lx.hi >> 16) & 0xffffu));
-                cursor[6 * kExWorkers + tid] = (unsigned short)(c.z + (unsigned)((lx.hi >> 32) & 0xffffu));
-                cursor[7 * kExWorkers + tid] = (unsigned short)(c.w + (unsigned)(lx.hi >> 48));
+                cursor[0 * kExWorkers + tid] = a.x + (unsigned)(lx.lo & 0xffffu);
+                cursor[1 * kExWorkers + tid] = a.y + (unsigned)((lx.lo >> 16) & 0xffffu);
+                cursor[2 * kExWorkers + tid] = a.z + (unsigned)((lx.lo >> 32) & 0xffffu);
+                cursor[3 * kExWorkers + tid] = a.w + (unsigned)(lx.lo >> 48);
+                cursor[4 * kExWorkers + tid] = c.x + (unsigned)(lx.hi & 0xffffu);
+                cursor[5 * kExWorkers + tid] = c.y + (unsigned)((lx.hi >> 16) & 0xffffu);
+                cursor[6 * kExWorkers + tid] = c.z + (unsigned)((lx.hi >> 32) & 0xffffu);
+                cursor[7 * kExWorkers + tid] = c.w + (unsigned)(lx.hi >> 48);
             }
             auto place = [&](K key, [[maybe_unused]] V val) {
-                unsigned short *cp = cursor + bucket(key) * kExWorkers + tid;
+                unsigned *cp = cursor + bucket(key) * kExWorkers + tid;
                 const unsigned pos = *cp;
-                *cp = (unsigned short)(pos + 1);
+                *cp = pos + 1;
                 buf[pos] = key;
                 if constexpr (VB > 0) vbuf[pos] = val;
             };
@@ -419,9 +424,11 @@ static int exchange_launch_typed(StreamState *st, const void *kin, const void *v
     unsigned epoch;
     BCB_TRY(next_epoch(st, kArenaPacked, &epoch));
     const unsigned long long ticket_base = ticket_reserve(st, tiles + grid);  // every CTA draws one void ticket
+    const char *fe = std::getenv("BCB_SPLIT_WS_FLAGS");  // experiments
+    const int ex_flags = fe ? std::atoi(fe) : 0;
     LaunchTimer timer(st, BCB_K_EXCHANGE_PASS);
     kernel<<<(unsigned)grid, kExThreads, C::SMEM_BYTES, st->stream>>>((const K *)kin, vin, (unsigned long long *)lb, epoch, n, (unsigned)tiles, tf,
-                                                                      st->control + kControlTicket, ticket_base);
+                                                                      st->control + kControlTicket, ticket_base, ex_flags);
     BCB_CUDA_TRY(cudaGetLastError());
     return BCB_SUCCESS;
 }

@@ -1381,9 +1381,9 @@ int bcb_partition_scatter(bcb_stream stream, int key_dtype, int ascending, const
     BCB_TRY(stream_state((cudaStream_t)stream, &st));
     // BCB_SPLIT_WS=1 (opt-in, read per call): the warp-specialised exchange kernel of radix_exchange_ws.cu (lane-private
     // ranking, one bulk copy per bucket run) for shards of >= 2^BCB_SPLIT_WS_MIN_LOG2 (default 24) keys.  Measured on
-    // one B200 with local destinations, 2^30 u32 keys: 4.1 ms for 1 / 3 / 7 splitters against 3.5 / 4.0 / 5.0 ms for the
-    // LSU kernel below -- ahead only for 8 ranks, and its bulk copies into PEER memory are not yet measured on 8 GPUs,
-    // so the LSU kernel stays the default.
+    // one B200 with local destinations, 2^30 u32 keys: 3.5 / 3.6 / 4.0 ms for 1 / 3 / 7 splitters against 3.5 / 4.0 / 5.0 ms
+    // for the LSU kernel below -- ahead for 4 and 8 ranks, but its bulk copies into PEER memory are not yet measured on
+    // more than one GPU, so the LSU kernel stays the default.
     {
         const char *e = std::getenv("BCB_SPLIT_WS");
         if (e && e[0] == '1') {
