@@ -46,6 +46,8 @@ SIGNATURES = {
     "bcb_partition_points": ([_vp, _i, _i, _vp, _sz, _vp, _sz, _vp], _i),
     "bcb_partition_by_splitters": ([_vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _sz, _vp, _sz, _vp], _i),
     "bcb_radix_top_histogram": ([_vp, _i, _i, _vp, _sz, _vp], _i),
+    "bcb_radix_exchange_scatter": ([_vp, _i, _i, _vp, _vp, _sz, _sz, _vp, _vp, _vp], _i),
+    "bcb_radix_sort_segments": ([_vp, _i, _i, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _sz], _i),
     "bcb_partition_counts": ([_vp, _i, _i, _vp, _sz, _vp, _sz, _vp], _i),
     "bcb_partition_scatter": ([_vp, _i, _i, _vp, _vp, _sz, _sz, _vp, _sz, _vp, _vp], _i),
     "bcb_ipc_export": ([_vp, _vp], _i),

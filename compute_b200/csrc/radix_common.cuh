@@ -156,7 +156,12 @@ __device__ __forceinline__ unsigned pass_digit(K raw, int shift, const Transform
 // two-sweep ranking; 32-bit keys + 4- / 8-byte payload, or keys only with a non-injective transform, with the
 // deterministic atomic-OR ranking.  Returns BCB_EUNSUPPORTED for shapes it does not cover (arrays not 16-byte aligned).
 int ws_launch_pass(StreamState *st, int key_bytes, const void *kin, void *kout, const void *vin, void *vout, int value_bytes,
-                   const unsigned *base, unsigned long long *lookback, size_t n, int shift, const Transform &tf, int xf, bool deterministic);
+                   const unsigned *base, unsigned long long *lookback, size_t n, int shift, const Transform &tf, int xf, bool deterministic,
+                   const unsigned long long *dst_tab = nullptr, const uint4 *tile_tab = nullptr, size_t tab_tiles = 0);
+// tile_tab (device, one uint4 per tile: {first key, end, first tile of the segment, segment}): segmented pass -- every
+// segment is sorted on its own, base is indexed [segment][256] (see bcb_radix_sort_segments).
+// dst_tab (device, [2][256]): the pass is the exchange pass of the multi-GPU sort -- the run of digit value d is written to
+// the array at dst_tab[d] (values: dst_tab[256 + d]) starting at element base[d], instead of kout / vout (may be null).
 size_t ws_tile_size(int key_bytes, int value_bytes, bool deterministic);
 bool ws_supports(int key_bytes, int value_bytes, bool deterministic);
 

@@ -75,7 +75,7 @@ template <typename K, int VB, bool DET> struct WsShape {
     static constexpr size_t VBUF_BYTES = (size_t)(TILE + PAD) * VB;
     static constexpr size_t TAB_BYTES = 2 * (size_t)kWsWorkerWarps * kRadixSize * sizeof(unsigned);  // [2][24][256]
     static constexpr size_t MASK_BYTES = DET ? (size_t)kWsWorkerWarps * kRadixSize * sizeof(unsigned) : 0;  // [24][256]
-    static constexpr size_t MISC_BYTES = 128;
+    static constexpr size_t MISC_BYTES = 256;
     static constexpr size_t SMEM_BYTES = KBUF_BYTES + VBUF_BYTES + TAB_BYTES + MASK_BYTES + MISC_BYTES;
     static_assert(KBUF_BYTES % 128 == 0 && VBUF_BYTES % 128 == 0, "the buffers and tables stay aligned");
     static_assert(ITEMS % CHUNK == 0, "whole chunks");
@@ -86,7 +86,8 @@ template <typename K, int VB, bool DET, int XF, int LB>
 __global__ void __launch_bounds__(kWsThreads, 1)
 onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *__restrict__ vals_in_v, void *__restrict__ vals_out_v,
             const unsigned *__restrict__ digit_base, unsigned long long *lookback, unsigned epoch, size_t n, unsigned num_tiles, int shift,
-            const __grid_constant__ Transform tf, unsigned long long *ticket, unsigned long long ticket_base, int flags)
+            const __grid_constant__ Transform tf, unsigned long long *ticket, unsigned long long ticket_base, int flags,
+            const unsigned long long *__restrict__ dst_tab, const uint4 *__restrict__ tile_tab)
 {
     typedef WsShape<K, VB, DET> C;
     typedef typename ws_value<VB>::type V;
@@ -104,7 +105,14 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
     unsigned *masks = tab + 2 * kWsWorkerWarps * ROW;                                           // [24][ROW] (DET only)
     volatile unsigned *ring = reinterpret_cast<volatile unsigned *>(smem + C::KBUF_BYTES + C::VBUF_BYTES + C::TAB_BYTES + C::MASK_BYTES);  // [4] tile ids
     unsigned *hscan = const_cast<unsigned *>(ring) + 4;                                        // [2][8] helper warp sums
+    // [4] tile descriptors {first key, end (one past the last key), first tile of the tile's segment, segment}.  A plain
+    // sort is one segment: tile t covers [t * TILE, min((t + 1) * TILE, n)).  The segmented passes of the multi-GPU sort
+    // (bcb_radix_sort_segments) bring a tile table: tiles never straddle two segments, the look-back stops at the
+    // segment's first tile, and digit_base is indexed [segment][digit].
+    volatile unsigned *ring_d = ring + 20;
     const unsigned tid = threadIdx.x;
+    auto tile_start = [&](unsigned i) -> unsigned { return ring_d[(i & 3u) * 4 + 0]; };
+    auto tile_end = [&](unsigned i) -> unsigned { return ring_d[(i & 3u) * 4 + 1]; };
 
     for (unsigned i = tid; i < (DET ? 3 : 2) * kWsWorkerWarps * ROW; i += kWsThreads) tab[i] = 0;  // (the mask table follows the count tables)
     __syncthreads();
@@ -124,20 +132,28 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
             if (tid == 0) {
                 const unsigned long long t = atomicAdd(ticket, 1ull) - ticket_base;
                 ring[i & 3u] = t < num_tiles ? (unsigned)t : kWsNoTile;
-                // BCB_WS_FLAGS=1 (experiment, measured 5 % SLOWER): pull the tile that will be drawn one round from now into
-                // L2 with the bulk-copy engine.  The counting sweep gets faster, but the pass is bound by the memory
-                // system (scattered writes), and the stores of the previous tile then simply drain later.
-                const unsigned long long ahead = t + gridDim.x;
-                if ((flags & 1) && (ahead + 1) * TILE <= n) tma_prefetch_l2(keys_in + ahead * TILE, (unsigned)(TILE * sizeof(K)), keep);
-                if ((flags & 1) && i == 0 && (t + 1) * TILE <= n) tma_prefetch_l2(keys_in + t * TILE, (unsigned)(TILE * sizeof(K)), keep);
+                if (t < num_tiles) {
+                    uint4 desc;
+                    if (tile_tab) {
+                        desc = __ldg(tile_tab + t);
+                    } else {
+                        const unsigned long long s0 = t * TILE, e0 = s0 + TILE;
+                        desc = make_uint4((unsigned)s0, (unsigned)(e0 < n ? e0 : n), 0u, 0u);
+                    }
+                    volatile unsigned *rd = ring_d + (i & 3u) * 4;
+                    rd[0] = desc.x; rd[1] = desc.y; rd[2] = desc.z; rd[3] = desc.w;
+                }
+                // (An experiment that pulled the tile one round ahead into L2 with cp.async.bulk.prefetch was measured
+                // 5 % SLOWER: the pass is bound by the scattered writes, whose drain the prefetch only delays.)
             }
             named_bar_sync(kBarWorkers, kWsWorkers);
             return ring[i & 3u];
         };
-        auto count = [&](unsigned p, unsigned t) {
-            const size_t base = (size_t)t * TILE + (size_t)w * SEG;
+        auto count = [&](unsigned p, unsigned i) {
+            const unsigned t_first = tile_start(i), t_end = tile_end(i);
+            const size_t base = (size_t)t_first + (size_t)w * SEG;
             unsigned *row = tab + (p * kWsWorkerWarps + w) * ROW;
-            if ((size_t)t * TILE + TILE <= n) {
+            if (t_end - t_first == (unsigned)TILE) {
                 // any order inside the warp's segment: 128-bit loads, a window of WIN per lane in flight.  The lines are
                 // asked to STAY in L2 (evict_last): the scatter sweep reads them again one tile later.
                 const uint4 *src = reinterpret_cast<const uint4 *>(keys_in + base) + lane;
@@ -159,14 +175,15 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
                 for (int i = 0; i < ITEMS; i++) {
                     const size_t idx = base + (size_t)i * 32 + lane;
                     // padding counts as digit 255: sorts last
-                    atomicAdd(&row[idx < n ? digit(sortable(__ldg(keys_in + idx))) : (unsigned)(kRadixSize - 1)], 1u);
+                    atomicAdd(&row[idx < t_end ? digit(sortable(__ldg(keys_in + idx))) : (unsigned)(kRadixSize - 1)], 1u);
                 }
             }
             named_bar_arrive(kBarCounted + p, kWsThreads);
         };
-        auto scatter_tile = [&](unsigned p, unsigned t, bool first, auto full_tag) {
+        auto scatter_tile = [&](unsigned p, unsigned i_tile, bool first, auto full_tag) {
             constexpr bool FULL = decltype(full_tag)::value;
-            const size_t base = (size_t)t * TILE + (size_t)w * SEG + lane;
+            const size_t n = tile_end(i_tile);  // (shadows the range length: the bound of THIS tile)
+            const size_t base = (size_t)tile_start(i_tile) + (size_t)w * SEG + lane;
             unsigned *row = tab + (p * kWsWorkerWarps + w) * ROW;
             K cur[CHUNK], nxt[CHUNK];
             V vcur[VB ? CHUNK : 1], vnxt[VB ? CHUNK : 1];
@@ -232,44 +249,49 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
             named_bar_arrive(kBarScattered, kWsThreads);
             WS_PROF_END(4);
         };
-        auto scatter = [&](unsigned p, unsigned t, bool first) {
-            if ((size_t)t * TILE + TILE <= n) scatter_tile(p, t, first, std::true_type());
-            else scatter_tile(p, t, first, std::false_type());
+        auto scatter = [&](unsigned p, unsigned i_tile, bool first) {
+            if (tile_end(i_tile) - tile_start(i_tile) == (unsigned)TILE) scatter_tile(p, i_tile, first, std::true_type());
+            else scatter_tile(p, i_tile, first, std::false_type());
         };
         unsigned t_cur = draw(0);
-        if (t_cur != kWsNoTile) count(0, t_cur);
+        if (t_cur != kWsNoTile) count(0, 0);
         else named_bar_arrive(kBarCounted + 0, kWsThreads);
         for (unsigned i = 0; t_cur != kWsNoTile; ++i) {
             WS_PROF_BEGIN();
             const unsigned t_next = draw(i + 1);
             WS_PROF_END(0);
-            if (t_next != kWsNoTile) count((i + 1) & 1u, t_next);
+            if (t_next != kWsNoTile) count((i + 1) & 1u, i + 1);
             else named_bar_arrive(kBarCounted + ((i + 1) & 1u), kWsThreads);  // the helpers learn from the ring that it is void
             WS_PROF_END(1);
-            scatter(i & 1u, t_cur, i == 0);
+            scatter(i & 1u, i, i == 0);
             t_cur = t_next;
         }
         if (tid == 0) WS_PROF_DUMP(0);
     } else {
         // ======================= helpers: digit scan, look-back, bulk stores (one digit value per thread) =======================
         const unsigned d = tid - kWsWorkers, lane = d & 31u, hw = d >> 5;
-        const unsigned gbase = __ldg(digit_base + d);
+        // dst_tab (multi-GPU exchange pass, bcb_radix_sort_exchange): every digit value has its own destination array --
+        // [d] keys, [256 + d] values, 16-byte aligned, possibly another GPU's memory -- and digit_base[d] counts from there
+        K *const kout_d = dst_tab ? reinterpret_cast<K *>(__ldg(dst_tab + d)) : keys_out;
+        V *const vout_d = (VB > 0 && dst_tab) ? reinterpret_cast<V *>(__ldg(dst_tab + kRadixSize + d)) : vals_out;
         const unsigned long long drop = l2_policy_evict_first();  // written lines are not read again in this pass
         const unsigned long long tag_p = (unsigned long long)((epoch << 2) | kLbPartial) << 32;
         const unsigned long long tag_i = (unsigned long long)((epoch << 2) | kLbInclusive) << 32;
         struct Run { unsigned g, s, c; };  // first index in keys_out, first index in the tile buffer, length
         WS_PROF_DECL;
-        struct Scan { unsigned pub, e; };
+        struct Scan { unsigned pub, e, gbase, first_tile; };
         // part 1: digit counts of the tile, exclusive scan over the digit values, publish the tile's count of this digit
-        auto scan_publish = [&](unsigned p, unsigned t, Scan &sc) {
+        auto scan_publish = [&](unsigned p, unsigned i_tile, unsigned t, Scan &sc) {
             WS_PROF_BEGIN();
+            const unsigned t_first = tile_start(i_tile), t_end = tile_end(i_tile);
+            sc.first_tile = ring_d[(i_tile & 3u) * 4 + 2];
+            sc.gbase = __ldg(digit_base + (size_t)ring_d[(i_tile & 3u) * 4 + 3] * kRadixSize + d);  // (in flight during the scan)
             unsigned *col = tab + p * kWsWorkerWarps * ROW + d;
             unsigned count = 0;
 #pragma unroll
             for (int w = 0; w < kWsWorkerWarps; w++) count += col[w * ROW];
             unsigned pub = count;  // without the padding of a partial tile (counted as digit 255)
-            const size_t tile_end = (size_t)t * TILE + TILE;
-            if (tile_end > n && d == kRadixSize - 1) pub -= (unsigned)(tile_end - n);
+            if (d == kRadixSize - 1) pub -= (unsigned)TILE - (t_end - t_first);
             // exclusive scan over the 256 digit values -> start of each run in the digit-sorted tile
             unsigned incl = count;
 #pragma unroll
@@ -284,7 +306,7 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
             for (int j = 0; j < 7; j++) add += (j < (int)hw) ? hscan[p * 8 + j] : 0u;
             sc.e = incl - count + add;
             sc.pub = pub;
-            st_relaxed_u64(lookback + (size_t)t * kRadixSize + d, (t == 0 ? tag_i : tag_p) | pub);
+            st_relaxed_u64(lookback + (size_t)t * kRadixSize + d, (t == sc.first_tile ? tag_i : tag_p) | pub);
             WS_PROF_END(0);
         };
         // part 2: walk back over the earlier tiles (LB descriptors in flight per step), publish the inclusive count, turn
@@ -294,7 +316,8 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
             unsigned *col = tab + p * kWsWorkerWarps * ROW + d;
             unsigned long long *mine = lookback + (size_t)t * kRadixSize + d;
             unsigned excl = 0;
-            if (t != 0) {
+            if (t != sc.first_tile) {
+                const long long lowest = (long long)sc.first_tile;  // the walk ends at the segment's first tile at the latest
                 long long j = (long long)t - 1;
                 bool done = false;
                 while (!done) {
@@ -302,7 +325,7 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
 #pragma unroll
                     for (int k = 0; k < LB; k++) {
                         const long long idx = j - k;
-                        v[k] = idx >= 0 ? ld_relaxed_u64(lookback + (size_t)idx * kRadixSize + d) : tag_i;  // before tile 0: inclusive zero
+                        v[k] = idx >= lowest ? ld_relaxed_u64(lookback + (size_t)idx * kRadixSize + d) : tag_i;  // before the first tile: inclusive zero
                     }
                     int consumed = 0;
 #pragma unroll
@@ -324,7 +347,7 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
             WS_PROF_END(1);
             // shared-memory start of the run: after the runs before it, shifted to its destination's 16-byte phase
             Run r;
-            r.g = gbase + excl;
+            r.g = sc.gbase + excl;
             const unsigned nat = sc.e + (A - 1) * d;
             r.s = nat + ((r.g - nat) & (A - 1));
             r.c = sc.pub;
@@ -346,14 +369,14 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
             // body: the 16-byte chunks that lie entirely inside the run, as one bulk copy
             const unsigned m = r.g & (A - 1), end = m + r.c;  // the run covers keys [m, end) counted from the chunk-aligned base
             const K *src0 = buf + (r.s - m);
-            K *dst0 = keys_out + ((size_t)r.g - m);
+            K *dst0 = kout_d + ((size_t)r.g - m);
             const unsigned first = (m + A - 1) / A, last = end / A;  // full chunks [first, last)
             if (r.c && last > first) {
                 // (first * A keys / values are a whole number of 16-byte chunks in BOTH arrays: A counts elements of the narrower one)
                 if (flags & 2) tma_store_issue(dst0 + first * A, src0 + first * A, (last - first) * A * (unsigned)sizeof(K));
                 else tma_store_issue_hint(dst0 + first * A, src0 + first * A, (last - first) * A * (unsigned)sizeof(K), drop);
                 if constexpr (VB > 0)
-                    tma_store_issue_hint(vals_out + ((size_t)r.g - m) + first * A, vbuf + (r.s - m) + first * A, (last - first) * A * (unsigned)VB, drop);
+                    tma_store_issue_hint(vout_d + ((size_t)r.g - m) + first * A, vbuf + (r.s - m) + first * A, (last - first) * A * (unsigned)VB, drop);
             }
             WS_PROF_END(4);
             tma_commit();
@@ -368,6 +391,8 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
                     const unsigned srcl = (r0 + sub) & 31u;
                     const unsigned og = __shfl_sync(0xffffffffu, r.g, srcl), os = __shfl_sync(0xffffffffu, r.s, srcl),
                                    oc = __shfl_sync(0xffffffffu, r.c, srcl);
+                    K *const okout = reinterpret_cast<K *>(__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)kout_d, srcl));
+                    V *const ovout = reinterpret_cast<V *>(__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)vout_d, srcl));
                     if (sub < (unsigned)PER && r0 + sub < 32 && oc) {
                         const unsigned om = og & (A - 1), oend = om + oc;
                         const unsigned ofirst = (om + A - 1) / A, olast = oend / A;
@@ -381,8 +406,8 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
                             on = olast >= ofirst && k < oend;
                         }
                         if (on) {
-                            keys_out[(size_t)og - om + k] = buf[os - om + k];
-                            if constexpr (VB > 0) vals_out[(size_t)og - om + k] = vbuf[os - om + k];
+                            okout[(size_t)og - om + k] = buf[os - om + k];
+                            if constexpr (VB > 0) ovout[(size_t)og - om + k] = vbuf[os - om + k];
                         }
                     }
                 }
@@ -397,7 +422,7 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
         Run r_cur{0, 0, 0};
         Scan sc;
         if (t_cur != kWsNoTile) {
-            scan_publish(0, t_cur, sc);
+            scan_publish(0, 0, t_cur, sc);
             r_cur = resolve(0, t_cur, sc);
         }
         // Per iteration: offsets (scan, publish, look-back) of the next tile, then the stores of the current one.
@@ -412,7 +437,7 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
             const unsigned t_next = ring[(i + 1) & 3u];
             Run r_next{0, 0, 0};
             if (t_next != kWsNoTile) {
-                scan_publish((i + 1) & 1u, t_next, sc);
+                scan_publish((i + 1) & 1u, i + 1, t_next, sc);
                 if (!(flags & 4)) r_next = resolve((i + 1) & 1u, t_next, sc);
             }
             store(r_cur, t_next != kWsNoTile);
@@ -426,7 +451,8 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
 
 template <typename K, int VB, bool DET, int XF>
 static int ws_launch_typed(StreamState *st, const void *kin, void *kout, const void *vin, void *vout, const unsigned *base,
-                           unsigned long long *lookback, size_t n, int shift, const Transform &tf)
+                           unsigned long long *lookback, size_t n, int shift, const Transform &tf, const unsigned long long *dst_tab,
+                           const uint4 *tile_tab, size_t tab_tiles)
 {
     typedef WsShape<K, VB, DET> C;
     auto kernel = onesweep_ws<K, VB, DET, XF, 8>;
@@ -436,16 +462,17 @@ static int ws_launch_typed(StreamState *st, const void *kin, void *kout, const v
         BCB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
         configured.fetch_or(bit, std::memory_order_release);
     }
-    const size_t tiles = (n + C::TILE - 1) / C::TILE;
+    const size_t tiles = tile_tab ? tab_tiles : (n + C::TILE - 1) / C::TILE;
     size_t grid = (size_t)st->sm_count;
     if (grid > tiles) grid = tiles;
     unsigned epoch;
     BCB_TRY(next_epoch(st, kArenaPacked, &epoch));
     const unsigned long long ticket_base = ticket_reserve(st, tiles + grid);  // every CTA draws one void ticket
     static const int ws_flags = [] { const char *e = std::getenv("BCB_WS_FLAGS"); return e ? std::atoi(e) : 0; }();  // experiments
-    LaunchTimer timer(st, BCB_K_ONESWEEP_PASS);
+    LaunchTimer timer(st, dst_tab ? BCB_K_EXCHANGE_PASS : BCB_K_ONESWEEP_PASS);
     kernel<<<(unsigned)grid, kWsThreads, C::SMEM_BYTES, st->stream>>>((const K *)kin, (K *)kout, vin, vout, base, lookback, epoch, n,
-                                                                      (unsigned)tiles, shift, tf, st->control + kControlTicket, ticket_base, ws_flags);
+                                                                      (unsigned)tiles, shift, tf, st->control + kControlTicket, ticket_base, ws_flags,
+                                                                      dst_tab, tile_tab);
     BCB_CUDA_TRY(cudaGetLastError());
 #ifdef BCB_WS_PROFILE
     {   // mean cycles per CTA and phase (workers 0-7, helpers 8-15); see the WS_PROF_END(k) sites for what k is
@@ -465,13 +492,14 @@ static int ws_launch_typed(StreamState *st, const void *kin, void *kout, const v
 
 template <typename K, int VB, bool DET>
 static int ws_launch_xf(StreamState *st, const void *kin, void *kout, const void *vin, void *vout, const unsigned *base,
-                        unsigned long long *lookback, size_t n, int shift, const Transform &tf, int xf)
+                        unsigned long long *lookback, size_t n, int shift, const Transform &tf, int xf, const unsigned long long *dst_tab,
+                        const uint4 *tile_tab, size_t tab_tiles)
 {
     switch (xf) {
-    case kXfNone: return ws_launch_typed<K, VB, DET, kXfNone>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
-    case kXfIn: return ws_launch_typed<K, VB, DET, kXfIn>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
-    case kXfOut: return ws_launch_typed<K, VB, DET, kXfOut>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
-    default: return ws_launch_typed<K, VB, DET, kXfBoth>(st, kin, kout, vin, vout, base, lookback, n, shift, tf);
+    case kXfNone: return ws_launch_typed<K, VB, DET, kXfNone>(st, kin, kout, vin, vout, base, lookback, n, shift, tf, dst_tab, tile_tab, tab_tiles);
+    case kXfIn: return ws_launch_typed<K, VB, DET, kXfIn>(st, kin, kout, vin, vout, base, lookback, n, shift, tf, dst_tab, tile_tab, tab_tiles);
+    case kXfOut: return ws_launch_typed<K, VB, DET, kXfOut>(st, kin, kout, vin, vout, base, lookback, n, shift, tf, dst_tab, tile_tab, tab_tiles);
+    default: return ws_launch_typed<K, VB, DET, kXfBoth>(st, kin, kout, vin, vout, base, lookback, n, shift, tf, dst_tab, tile_tab, tab_tiles);
     }
 }
 
@@ -491,16 +519,17 @@ bool ws_supports(int key_bytes, int value_bytes, bool deterministic)
 }
 
 int ws_launch_pass(StreamState *st, int key_bytes, const void *kin, void *kout, const void *vin, void *vout, int value_bytes,
-                   const unsigned *base, unsigned long long *lookback, size_t n, int shift, const Transform &tf, int xf, bool deterministic)
+                   const unsigned *base, unsigned long long *lookback, size_t n, int shift, const Transform &tf, int xf, bool deterministic,
+                   const unsigned long long *dst_tab, const uint4 *tile_tab, size_t tab_tiles)
 {
-    // bulk copies need 16-byte aligned arrays
+    // bulk copies need 16-byte aligned arrays (with dst_tab the caller has checked the destinations it holds)
     if ((((uintptr_t)kin | (uintptr_t)kout | (uintptr_t)vin | (uintptr_t)vout) & 15) != 0) return BCB_EUNSUPPORTED;
     if (!ws_supports(key_bytes, value_bytes, deterministic)) return BCB_EUNSUPPORTED;
-    if (value_bytes == 4) return ws_launch_xf<unsigned, 4, true>(st, kin, kout, vin, vout, base, lookback, n, shift, tf, xf);
-    if (value_bytes == 8) return ws_launch_xf<unsigned, 8, true>(st, kin, kout, vin, vout, base, lookback, n, shift, tf, xf);
-    if (key_bytes == 8) return ws_launch_xf<unsigned long long, 0, false>(st, kin, kout, nullptr, nullptr, base, lookback, n, shift, tf, xf);
-    return deterministic ? ws_launch_xf<unsigned, 0, true>(st, kin, kout, nullptr, nullptr, base, lookback, n, shift, tf, xf)
-                         : ws_launch_xf<unsigned, 0, false>(st, kin, kout, nullptr, nullptr, base, lookback, n, shift, tf, xf);
+    if (value_bytes == 4) return ws_launch_xf<unsigned, 4, true>(st, kin, kout, vin, vout, base, lookback, n, shift, tf, xf, dst_tab, tile_tab, tab_tiles);
+    if (value_bytes == 8) return ws_launch_xf<unsigned, 8, true>(st, kin, kout, vin, vout, base, lookback, n, shift, tf, xf, dst_tab, tile_tab, tab_tiles);
+    if (key_bytes == 8) return ws_launch_xf<unsigned long long, 0, false>(st, kin, kout, nullptr, nullptr, base, lookback, n, shift, tf, xf, dst_tab, tile_tab, tab_tiles);
+    return deterministic ? ws_launch_xf<unsigned, 0, true>(st, kin, kout, nullptr, nullptr, base, lookback, n, shift, tf, xf, dst_tab, tile_tab, tab_tiles)
+                         : ws_launch_xf<unsigned, 0, false>(st, kin, kout, nullptr, nullptr, base, lookback, n, shift, tf, xf, dst_tab, tile_tab, tab_tiles);
 }
 
 }  // namespace bcb

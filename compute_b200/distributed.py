@@ -76,6 +76,23 @@ def select_splitters(all_samples: np.ndarray, world: int) -> np.ndarray:
     return s[np.minimum(pos, s.size - 1)]
 
 
+def _digit_edges(tot: np.ndarray, world: int) -> np.ndarray:
+    """Bin edges e[0..world] (e[0] = 0, e[world] = 256): rank d is dealt the digit values [e[d], e[d+1]); each edge is the
+    one whose cumulative global count is closest to d * N / P."""
+    n = int(tot.sum())
+    cum = np.cumsum(tot)                                        # cum[b - 1] = keys with digit < b
+    edges = np.zeros(world + 1, dtype=np.int64)
+    edges[world] = 256
+    for d in range(1, world):
+        target = (d * n) // world
+        b = int(np.searchsorted(cum, target, side="left")) + 1  # first edge with at least `target` keys below it
+        below = int(cum[b - 2]) if b >= 2 else 0                # the edge before it
+        if b >= 2 and target - below < int(cum[b - 1]) - target:
+            b -= 1
+        edges[d] = min(max(b, edges[d - 1]), 256)
+    return edges
+
+
 def histogram_plan(all_hist: np.ndarray, world: int, key_bits: int, max_imbalance: float = 1.06):
     """Splitters and the P x P count matrix from the all-gathered 256-bin histograms of the keys' most significant digit
     (all_hist[src][digit]).  Rank d is dealt the digit values [b_d, b_(d+1)); the boundaries are the bin edges whose
@@ -87,16 +104,7 @@ def histogram_plan(all_hist: np.ndarray, world: int, key_bits: int, max_imbalanc
     n = int(tot.sum())
     if n == 0 or world <= 1:
         return None
-    cum = np.cumsum(tot)                                        # cum[b - 1] = keys with digit < b
-    edges = np.zeros(world + 1, dtype=np.int64)
-    edges[world] = 256
-    for d in range(1, world):
-        target = (d * n) // world
-        b = int(np.searchsorted(cum, target, side="left")) + 1  # first edge with at least `target` keys below it
-        below = int(cum[b - 2]) if b >= 2 else 0                # the edge before it
-        if b >= 2 and target - below < int(cum[b - 1]) - target:
-            b -= 1
-        edges[d] = min(max(b, edges[d - 1]), 256)
+    edges = _digit_edges(tot, world)
     recv = np.array([int(tot[edges[d]:edges[d + 1]].sum()) for d in range(world)], dtype=np.int64)
     imbalance = float(recv.max() * world / n)
     if imbalance > max_imbalance:
@@ -104,6 +112,34 @@ def histogram_plan(all_hist: np.ndarray, world: int, key_bits: int, max_imbalanc
     counts = np.stack([[int(h[src, edges[d]:edges[d + 1]].sum()) for d in range(world)] for src in range(world)]).astype(np.int64)
     splitters = (edges[1:world].astype(np.uint64) << np.uint64(key_bits - 8))
     return splitters, counts, imbalance
+
+
+def digit_exchange_plan(all_hist: np.ndarray, world: int, max_imbalance: float = 1.06, align: int = 32):
+    """Placement of every (source rank, top digit value) run when the pass over the most significant digit is the exchange
+    (bcb_radix_exchange_scatter / bcb_radix_sort_segments).  Whole digit values are dealt to the ranks as in
+    histogram_plan; inside the owner's receive buffer every digit value g has a segment that starts on a multiple of
+    ``align`` elements, and source s's run of g lies after the runs of the sources before it (equal keys keep their global
+    input order).  Returns (owner int64[256], first int64[P][256] = element index of (src, g)'s run in the owner's receive
+    buffer, seg_begin int64[256], seg_len int64[256] (= global count of g), recv int64[P], span int64[P] = elements of
+    receive buffer in use, imbalance) or None when no even deal exists."""
+    h = np.asarray(all_hist, dtype=np.int64).reshape(world, 256)
+    tot = h.sum(axis=0)
+    n = int(tot.sum())
+    if n == 0 or world <= 1:
+        return None
+    edges = _digit_edges(tot, world)
+    recv = np.array([int(tot[edges[d]:edges[d + 1]].sum()) for d in range(world)], dtype=np.int64)
+    imbalance = float(recv.max() * world / n)
+    if imbalance > max_imbalance:
+        return None
+    owner = np.searchsorted(edges[1:], np.arange(256), side="right").astype(np.int64)   # edges[owner] <= g < edges[owner + 1]
+    owner = np.minimum(owner, world - 1)
+    padded = (tot + align - 1) // align * align
+    before = np.cumsum(padded) - padded                             # aligned slots of the smaller digits, globally
+    seg_begin = before - before[edges[owner]]                       # ... among the owner's digits
+    first = seg_begin[None, :] + (np.cumsum(h, axis=0) - h)         # + the same digit on the sources before src
+    span = np.array([int((seg_begin + tot)[owner == d].max()) if np.any(owner == d) else 0 for d in range(world)], dtype=np.int64)
+    return owner, first.astype(np.int64), seg_begin.astype(np.int64), tot.astype(np.int64), recv, span, imbalance
 
 
 def exchange_plan(points: np.ndarray, n_local: int):
@@ -192,6 +228,31 @@ class CudaLocalOps:
         self._check(self._lib.bcb_radix_top_histogram(self.queue.handle, dtype_code(keys.dtype), int(not descending), keys.data_ptr(),
                                                       keys.shape[0], counts.ctypes.data))
         return counts.astype(np.int64)
+
+    def exchange_scatter(self, keys, values, descending: bool, dst_keys, dst_values, dst_first) -> bool:
+        """One stable pass over the most significant digit: digit g's run goes to the array at dst_keys[g] (possibly a
+        peer's memory) from element dst_first[g] on.  Asynchronous; the shard is not modified.  False: shape not supported
+        (decided from the types: the same answer on every rank)."""
+        dk = (ctypes.c_void_p * 256)(*[int(a) for a in dst_keys])
+        dv = (ctypes.c_void_p * 256)(*[int(a) for a in dst_values]) if values is not None else None
+        df = np.ascontiguousarray(dst_first, dtype=np.uint64)
+        rc = self._lib.bcb_radix_exchange_scatter(self.queue.handle, dtype_code(keys.dtype), int(not descending), keys.data_ptr(),
+                                                  None if values is None else values.data_ptr(), self._row_bytes(values), keys.shape[0],
+                                                  dk, dv, df.ctypes.data)
+        if rc == 10002:  # BCB_EUNSUPPORTED
+            return False
+        self._check(rc)
+        return True
+
+    def sort_segments(self, recv_keys_ptr: int, recv_values_ptr: int, out_keys, out_values, descending: bool, seg_begin, seg_len) -> None:
+        """Every segment of the receive buffer sorted by the remaining digits (all segments in one launch per digit); the
+        last pass writes them back to back into out_keys / out_values.  Asynchronous."""
+        sb = np.ascontiguousarray(seg_begin, dtype=np.uint64)
+        sl = np.ascontiguousarray(seg_len, dtype=np.uint64)
+        self._check(self._lib.bcb_radix_sort_segments(self.queue.handle, dtype_code(out_keys.dtype), int(not descending), recv_keys_ptr,
+                                                      None if out_values is None else recv_values_ptr, self._row_bytes(out_values),
+                                                      out_keys.data_ptr(), None if out_values is None else out_values.data_ptr(),
+                                                      sb.ctypes.data, sl.ctypes.data, sb.size))
 
     def partition_counts(self, keys, splitters: np.ndarray, descending: bool) -> np.ndarray:
         counts = np.zeros(splitters.size + 1, dtype=np.uint64)
@@ -339,6 +400,7 @@ class Context:
         # and record last_stats["phases_ms"] (diagnostics only -- the synchronisation costs time)
         self.use_peer_memory = os.environ.get("BCB_DIST_PEER", "1") != "0"
         self.use_histogram_plan = os.environ.get("BCB_DIST_HISTOGRAM", "1") != "0"  # 0: always sample (A/B comparison)
+        self.use_digit_exchange = os.environ.get("BCB_DIST_DIGIT_EXCHANGE", "1") != "0"  # 0: partition pass + local sort (A/B)
         self.profile = os.environ.get("BCB_DIST_PROFILE", "0") == "1"
         self._flag = None
 
@@ -426,9 +488,22 @@ class Context:
         # count pass); skewed keys (a few digit values hold most of them) fall back to regular samples of the
         # unsorted shard + a count pass.
         if peer_ok and self.use_histogram_plan and hasattr(self.ops, "top_histogram"):
+            # Best plan: the exchange is ONE of the sort's radix passes (digit_exchange_plan) -- the pass over the most
+            # significant digit writes into the owners' receive buffers, the owners sort every digit value's segment by
+            # the remaining digits: as many passes over the data as on one GPU.  Needs the warp-specialised pass kernel:
+            # 32-bit keys (payload 0 / 4 / 8 bytes) or 64-bit keys alone with an injective transform (the decision depends
+            # on shapes only: the same on every rank).
+            ksize = keys.element_size()
+            digit_ok = (self.use_digit_exchange and hasattr(self.ops, "exchange_scatter")
+                        and (ksize == 4 or (ksize == 8 and vb == 0 and not (keys.dtype == torch.float64 and descending))))
             hist = self.ops.top_histogram(keys, descending) if n_local else np.zeros(256, np.int64)
-            plan = histogram_plan(self._all_gather_np(hist), P, keys.element_size() * 8)
+            all_hist = self._all_gather_np(hist)
             self._phase("histogram")
+            if digit_ok:
+                done = self._sort_digit_exchange(keys, values, descending, vb, all_hist)
+                if done is not None:
+                    return done
+            plan = histogram_plan(all_hist, P, keys.element_size() * 8)
             if plan is not None:
                 done = self._sort_peer(keys, values, descending, plan[0], vb, counts=plan[1])
                 if done is not None:
@@ -464,6 +539,44 @@ class Context:
         self._phase("sort")
         self.last_stats = {"plan": plan, "phases_ms": dict(getattr(self, "_phases", {})) if self.profile else None, "sent": int(send.sum() - send[self.rank]), "received": int(recv.sum()),
                            "imbalance": float(counts.sum(axis=0).max() * P / max(1, counts.sum()))}
+        return out_keys if values is None else (out_keys, out_vals)
+
+    def _sort_digit_exchange(self, keys, values, descending, vb, all_hist):
+        """The digit-exchange plan (see sort).  Returns None -- collectively -- when whole digit values cannot be dealt
+        evenly, the buffers cannot be mapped or the kernels do not cover the shape; the shard is then still untouched."""
+        P, me = self.world, self.rank
+        plan = digit_exchange_plan(all_hist, P)
+        if plan is None:
+            return None
+        owner, first, seg_begin, seg_len, recv_tot, span, imbalance = plan
+        ksize = keys.element_size()
+        max_span = int(span.max())
+        val_off = (max_span * ksize + 255) & ~255                        # values region of every receive buffer
+        # (the all-gather of the histograms also ordered this call after every rank's previous use of its receive buffer)
+        if not self.peer.ensure(max(256, val_off + max_span * vb)):
+            return None
+        dst_k = [self.peer.peers[int(owner[g])] for g in range(256)]
+        dst_v = [self.peer.peers[int(owner[g])] + val_off for g in range(256)]
+        self._phase("plan")
+        if self.ops.device_type == "cuda":  # the pass moves whole 16-byte chunks: a misaligned view is copied first
+            if keys.data_ptr() % 16:
+                keys = keys.clone()
+            if values is not None and values.data_ptr() % 16:
+                values = values.clone()
+        if not self.ops.exchange_scatter(keys, values, descending, dst_k, dst_v, first[me]):
+            return None
+        self._stream_barrier()                                           # all incoming runs have landed
+        self._phase("exchange pass")
+        n_out = int(recv_tot[me])
+        out_keys = self.ops.empty(n_out, keys)
+        out_vals = self.ops.empty(n_out, values) if values is not None else None
+        mine = owner == me
+        self.ops.sort_segments(self.peer.local, self.peer.local + val_off, out_keys, out_vals, descending, seg_begin[mine], seg_len[mine])
+        self._phase("segment passes")
+        sent = int(all_hist[me].sum() - all_hist[me][mine].sum())
+        self.last_stats = {"plan": "digit-exchange", "splitters": "top-digit histogram",
+                           "phases_ms": dict(self._phases) if self.profile else None,
+                           "sent": sent, "received": n_out, "imbalance": imbalance}
         return out_keys if values is None else (out_keys, out_vals)
 
     def _sort_peer(self, keys, values, descending, splitters, vb, counts=None):

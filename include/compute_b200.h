@@ -174,6 +174,32 @@ BCB_API int bcb_partition_scatter(bcb_stream stream, int key_dtype, int ascendin
                                   const unsigned long long *splitters_host, size_t num_splitters, void *const *dst_keys,
                                   void *const *dst_values);
 
+/* The multi-GPU sort whose exchange is ONE of its radix passes (new functionality; the single-GPU counterpart is
+ * radix_sort_impl, algorithm/detail/radix_sort.hpp:308-425): as many passes over the data as on one GPU, instead of a
+ * partition pass plus a full local sort.
+ *   1. bcb_radix_top_histogram on every rank, all-gathered by the host layer: whole values of the most significant digit
+ *      are dealt to the ranks; inside the owner's receive buffer every digit value has a SEGMENT (starting on a 16-byte
+ *      boundary), in which rank r's keys of that digit follow those of the ranks < r.
+ *   2. bcb_radix_exchange_scatter (source side, asynchronous): one stable pass over the most significant digit that
+ *      writes the run of digit d to dst_keys[d] (dst_values[d]) -- host arrays of 256 device addresses, 16-byte aligned,
+ *      possibly another GPU's memory opened with bcb_ipc_open -- from element dst_first[d] on.  Every digit run of a
+ *      tile leaves the SM as one bulk copy (cp.async.bulk), also over NVLink.  The input is not modified.  Keys with an
+ *      invertible transform travel in their sortable form.
+ *   3. after a stream-ordered barrier across the ranks, bcb_radix_sort_segments (destination side, asynchronous): every
+ *      segment [seg_begin[i], seg_begin[i] + seg_len[i]) (elements; ascending, disjoint, 16-byte aligned starts) of the
+ *      receive buffer is sorted on its own by the remaining digits -- stable LSD passes, ALL segments in one launch per
+ *      digit -- and the last pass writes the segments back to back into out_keys / out_values.  recv_* are scratch.
+ *      Keys-only sorts with an injective transform rank speculatively and are verified on out_keys (gated deterministic
+ *      re-sort on the device, as in bcb_radix_sort).
+ * Keys: 32-bit with value_bytes 0, 4 or 8, or 64-bit keys only with an injective transform; anything else returns
+ * BCB_EUNSUPPORTED (decided from the types alone: every rank of a collective call gets the same answer). */
+BCB_API int bcb_radix_exchange_scatter(bcb_stream stream, int key_dtype, int ascending, const void *keys, const void *values,
+                                       size_t value_bytes, size_t n, void *const *dst_keys /* [256] */,
+                                       void *const *dst_values /* [256] or NULL */, const unsigned long long *dst_first /* [256] */);
+BCB_API int bcb_radix_sort_segments(bcb_stream stream, int key_dtype, int ascending, void *recv_keys, void *recv_values,
+                                    size_t value_bytes, void *out_keys, void *out_values, const unsigned long long *seg_begin,
+                                    const unsigned long long *seg_len, size_t num_segments);
+
 /* Peer memory for the above: export a bcb_malloc'ed buffer as a 64-byte handle, open a peer's handle in this process
  * (cudaIpcGetMemHandle / cudaIpcOpenMemHandle with lazy peer access), close it again. */
 BCB_API int bcb_ipc_export(void *device_ptr, unsigned char *handle64);

@@ -64,6 +64,38 @@ def test_histogram_plan_deals_whole_digit_values():
     assert cbd.histogram_plan(np.zeros((2, 256), np.int64), 2, 32) is None  # globally empty range
 
 
+def test_digit_exchange_plan_places_every_run():
+    rng = np.random.default_rng(11)
+    for world in (2, 3, 8):
+        keys = [rng.integers(0, 2**32, size=30_000 + 777 * r, dtype=np.uint64) for r in range(world)]
+        allh = np.stack([np.bincount((k >> np.uint64(24)).astype(np.int64), minlength=256) for k in keys])
+        owner, first, seg_begin, seg_len, recv, span, imbalance = cbd.digit_exchange_plan(allh, world)
+        assert np.all(np.diff(owner) >= 0) and owner[0] == 0 and owner[-1] == world - 1 and imbalance < 1.06
+        assert int(recv.sum()) == sum(k.size for k in keys) and np.all(seg_begin % 32 == 0)
+        # emulate the exchange: every (src, digit) run copied to first[src][g] in the owner's receive buffer, then every
+        # segment sorted on its own and the segments concatenated = the global sort
+        bufs = [np.full(int(span[d]), -1, dtype=np.int64) for d in range(world)]
+        for src, k in enumerate(keys):
+            top = (k >> np.uint64(24)).astype(np.int64)
+            for g in np.unique(top):
+                run = k[top == g]
+                o = bufs[int(owner[g])]
+                assert np.all(o[first[src][g]:first[src][g] + run.size] == -1)   # runs never overlap
+                o[first[src][g]:first[src][g] + run.size] = run
+        outs = []
+        for d in range(world):
+            for g in np.flatnonzero(owner == d):
+                seg = bufs[d][seg_begin[g]:seg_begin[g] + seg_len[g]]
+                assert np.all(seg >= 0) and np.all(seg >> 24 == g)
+                outs.append(np.sort(seg, kind="stable"))
+            assert sum(int(seg_len[g]) for g in np.flatnonzero(owner == d)) == recv[d]
+        np.testing.assert_array_equal(np.concatenate(outs), np.sort(np.concatenate(keys)).astype(np.int64))
+    skew = np.zeros((4, 256), dtype=np.int64)
+    skew[:, 7] = 1000
+    assert cbd.digit_exchange_plan(skew, 4) is None
+    assert cbd.digit_exchange_plan(np.zeros((2, 256), np.int64), 2) is None
+
+
 class OracleLocalOps:
     """CPU stand-in for CudaLocalOps used ONLY by this test: same interface, oracle semantics, CPU tensors."""
     device_type = "cpu"
@@ -116,6 +148,50 @@ class OracleLocalOps:
         bits = k.view({1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[w])
         tk = cbd.transformed_keys(bits, dtype_code(k.dtype), not descending)
         return np.bincount((tk >> np.uint64(8 * w - 8)).astype(np.int64), minlength=256).astype(np.int64)
+
+    def exchange_scatter(self, keys, values, descending, dst_keys, dst_values, dst_first):
+        """Stand-in for bcb_radix_exchange_scatter: stable partition by the most significant digit of the transformed
+        key; every digit value's run is stored where the plan says (memmove = the bulk copies over NVLink)."""
+        import ctypes
+        if getattr(self, "no_digit_exchange", False):
+            return False
+        k = self._np(keys)
+        w = k.dtype.itemsize
+        bits = k.view({1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[w])
+        top = (cbd.transformed_keys(bits, dtype_code(k.dtype), not descending) >> np.uint64(8 * w - 8)).astype(np.int64)
+        v = self._np(values) if values is not None else None
+        row = 0 if v is None else v.dtype.itemsize * (v.size // max(1, v.shape[0]))
+        for g in np.unique(top):
+            sel = np.flatnonzero(top == g)  # ascending positions: stable
+            kb = np.ascontiguousarray(k[sel])
+            ctypes.memmove(int(dst_keys[g]) + int(dst_first[g]) * w, kb.ctypes.data, kb.nbytes)
+            if v is not None:
+                vb = np.ascontiguousarray(v[sel])
+                ctypes.memmove(int(dst_values[g]) + int(dst_first[g]) * row, vb.ctypes.data, vb.nbytes)
+        return True
+
+    def sort_segments(self, recv_keys_ptr, recv_values_ptr, out_keys, out_values, descending, seg_begin, seg_len):
+        """Stand-in for bcb_radix_sort_segments: every segment stably sorted on its own, results back to back."""
+        import ctypes
+        k = self._np(out_keys)
+        v = self._np(out_values) if out_values is not None else None
+        row = 0 if v is None else v.dtype.itemsize * (v.size // max(1, v.shape[0]))
+        pos = 0
+        for b, l in zip(seg_begin, seg_len):
+            b, l = int(b), int(l)
+            if l == 0:
+                continue
+            seg_k = k[pos:pos + l]
+            ctypes.memmove(seg_k.ctypes.data, int(recv_keys_ptr) + b * k.dtype.itemsize, l * k.dtype.itemsize)
+            if v is None:
+                seg_k[:] = oracle.radix_sort(seg_k.copy(), descending)
+            else:
+                seg_v = v[pos:pos + l]
+                ctypes.memmove(seg_v.ctypes.data, int(recv_values_ptr) + b * row, l * row)
+                sk, sv = oracle.radix_sort(seg_k.copy(), descending, seg_v.copy())
+                seg_k[:] = sk
+                seg_v[:] = sv
+            pos += l
 
     def partition_counts(self, keys, splitters, descending):
         return np.bincount(self._buckets(keys, splitters, descending), minlength=splitters.size + 1).astype(np.int64)
@@ -239,6 +315,16 @@ def _worker(rank, world, port, results):
         blo, bhi = rank * 60_000 // world, (rank + 1) * 60_000 // world
         out["big"] = ctx.sort(torch.from_numpy(big[blo:bhi].copy())).numpy().copy()
         out["stats_big"] = dict(ctx.last_stats)
+        # the plans behind the digit exchange: partition pass into the peers' buffers + local sort (same bytes)
+        ctx.use_digit_exchange = False
+        out["big_ps"] = ctx.sort(torch.from_numpy(big[blo:bhi].copy())).numpy().copy()
+        out["stats_big_ps"] = dict(ctx.last_stats)
+        ctx.use_digit_exchange = True
+        ops.no_digit_exchange = True    # the kernels refuse the shape: every rank moves on to the next plan together
+        k3, v3 = ctx.sort(torch.from_numpy(keys[lo:hi].copy()), torch.from_numpy(vals[lo:hi].copy()))
+        out["pairs_k3"], out["pairs_v3"] = k3.numpy().copy(), v3.numpy().copy()
+        out["stats3"] = dict(ctx.last_stats)
+        ops.no_digit_exchange = False
         ctx.use_peer_memory = False     # NCCL-style all-to-all plan: same bytes
         k1, v1 = ctx.sort(torch.from_numpy(keys[lo:hi].copy()), torch.from_numpy(vals[lo:hi].copy()))
         out["pairs_k1"], out["pairs_v1"] = k1.numpy().copy(), v1.numpy().copy()
@@ -307,12 +393,19 @@ def test_gloo_ranks_match_single_device_oracle(world):
     assert np.concatenate([r["fb"] for r in res]).tobytes() == oracle.radix_sort(allk, True).tobytes()
     assert [r["stats_fb"]["plan"] for r in res] == ["partition"] * world
     assert all(r["empty"] == 0 for r in res)
-    assert res[0]["stats"]["plan"] == "peer-scatter" and res[0]["stats1"]["plan"] == "partition"
-    # uniform 32-bit keys are dealt by the top-digit histogram (one exchange).  The small ints of the pair sort occupy two
+    assert res[0]["stats1"]["plan"] == "partition"
+    assert np.concatenate([r["big_ps"] for r in res]).tobytes() == oracle.radix_sort(big, False).tobytes()
+    assert np.concatenate([r["pairs_k3"] for r in res]).tobytes() == ek.tobytes()
+    assert np.concatenate([r["pairs_v3"] for r in res]).tobytes() == ev.tobytes()
+    # uniform 32-bit keys: the exchange is the sort's last radix pass; with that plan switched off they are dealt by the
+    # top-digit histogram to the partition pass (one exchange, no sampling).  The small ints of the pair sort occupy two
     # digit values (negative / non-negative): an even deal for 2 ranks, too skewed for 3 (regular samples + count pass)
-    assert all(r["stats_big"]["splitters"] == "top-digit histogram" for r in res), res[0]["stats_big"]
-    want = "top-digit histogram" if world == 2 else "regular samples"
-    assert all(r["stats"]["splitters"] == want for r in res), res[0]["stats"]
+    assert all(r["stats_big"]["plan"] == "digit-exchange" for r in res), res[0]["stats_big"]
+    assert all(r["stats_big_ps"]["plan"] == "peer-scatter" and r["stats_big_ps"]["splitters"] == "top-digit histogram" for r in res)
+    want = ("digit-exchange", "top-digit histogram") if world == 2 else ("peer-scatter", "regular samples")
+    assert all((r["stats"]["plan"], r["stats"]["splitters"]) == want for r in res), res[0]["stats"]
+    want3 = "top-digit histogram" if world == 2 else "regular samples"
+    assert all(r["stats3"]["plan"] == "peer-scatter" and r["stats3"]["splitters"] == want3 for r in res), res[0]["stats3"]
     assert res[0]["stats2"]["plan"] == "sort-and-cut"
     assert res[0]["stats"]["imbalance"] < 1.6
     x = rng.integers(-2**31, 2**31 - 1, size=9001).astype(np.int32)

@@ -475,6 +475,80 @@ def test_partition_counts_and_scatter_to_separate_buffers(dtype, value_bytes, ns
                 assert not gv[:lo].any() and not gv[lo + sel.size * value_bytes:].any()
 
 
+@pytest.mark.parametrize("dtype,value_bytes,world,n,desc", [
+    ("uint", 0, 2, 300_001, False), ("uint", 0, 8, (1 << 22) + 4321, False), ("int", 0, 3, 1_000_003, True), ("float", 0, 4, 777_777, False),
+    ("float", 0, 2, 500_000, True), ("uint", 4, 4, 600_001, False), ("int", 8, 2, 400_003, True), ("float", 4, 3, 250_000, True),
+    ("ulong", 0, 2, 500_009, False), ("long", 0, 4, 300_000, True), ("double", 0, 3, 400_001, False),
+    ("uint", 0, 2, 1000, False), ("uint", 8, 5, 5000, False)])
+def test_digit_exchange_on_one_gpu_matches_oracle(dtype, value_bytes, world, n, desc, gpu):
+    """The multi-GPU sort whose exchange is its pass over the most significant digit, with all ranks emulated on one GPU:
+    every shard's bcb_radix_exchange_scatter writes its digit runs into the owners' receive buffers (placement from
+    digit_exchange_plan), every owner's bcb_radix_sort_segments sorts its segments by the remaining digits.  The
+    concatenation must equal the oracle's stable sort of the whole range byte for byte (keys and payload), and nothing
+    may be written outside the segments."""
+    import ctypes
+    import torch
+    import compute_b200 as cb
+    from compute_b200 import distributed as cbd
+    from compute_b200.core import dtype_code
+    k = random_keys(dtype, n, seed=91, mode="bits")
+    if dtype in ("float", "double") and desc:
+        k[::50] = -0.0
+        k[1::50] = np.finfo(k.dtype).smallest_subnormal  # collides with -0.0 in the reference's descending transform
+    w = k.dtype.itemsize
+    code = dtype_code(k.dtype)
+    v = np.arange(n * (value_bytes // 4), dtype=np.uint32).reshape(n, value_bytes // 4) if value_bytes else None
+    cuts = [n * r // world for r in range(world + 1)]
+    cuts[1] = min(cuts[1], 7) if world > 2 else cuts[1]   # a tiny shard
+    bits = k.view({4: np.uint32, 8: np.uint64}[w])
+    tk = cbd.transformed_keys(bits, code, not desc)
+    allh = np.stack([np.bincount((tk[cuts[r]:cuts[r + 1]] >> np.uint64(8 * w - 8)).astype(np.int64), minlength=256) for r in range(world)])
+    plan = cbd.digit_exchange_plan(allh, world, max_imbalance=1e9)
+    owner, first, seg_begin, seg_len, recv, span, _ = plan
+    q = cb.command_queue()
+    lib = cb.lib()
+    guard = 64
+    rk = [torch.full((int(span[d]) * w + 2 * guard,), 0xAB, dtype=torch.uint8, device="cuda") for d in range(world)]
+    rv = [torch.full((int(span[d]) * value_bytes + 2 * guard,), 0xAB, dtype=torch.uint8, device="cuda") for d in range(world)]
+    for r in range(world):
+        dk = gpu.to_dev(k[cuts[r]:cuts[r + 1]])
+        dv = gpu.to_dev(v[cuts[r]:cuts[r + 1]]) if v is not None else None
+        pk = (ctypes.c_void_p * 256)(*[rk[int(owner[g])].data_ptr() + guard for g in range(256)])
+        pv = (ctypes.c_void_p * 256)(*[rv[int(owner[g])].data_ptr() + guard for g in range(256)])
+        df = np.ascontiguousarray(first[r], dtype=np.uint64)
+        before = dk.clone()
+        cb._capi.check(lib.bcb_radix_exchange_scatter(q.handle, code, int(not desc), dk.data_ptr(), None if v is None else dv.data_ptr(),
+                                                      value_bytes, dk.shape[0], pk, pv if v is not None else None, df.ctypes.data))
+        q.finish()
+        assert torch.equal(dk.view(torch.uint8), before.view(torch.uint8))  # the shard is not modified
+    # the receive buffers: guards and the alignment gaps between segments untouched
+    for d in range(world):
+        got = rk[d].cpu().numpy()
+        used = np.zeros(got.size, dtype=bool)
+        for g in np.flatnonzero(owner == d):
+            used[guard + int(seg_begin[g]) * w: guard + int(seg_begin[g] + seg_len[g]) * w] = True
+        assert np.all(got[~used] == 0xAB), (d, "keys written outside the segments")
+    outs_k, outs_v = [], []
+    for d in range(world):
+        ok = torch.empty(int(recv[d]) * w, dtype=torch.uint8, device="cuda")
+        ov = torch.empty(int(recv[d]) * value_bytes, dtype=torch.uint8, device="cuda")
+        mine = owner == d
+        sb = np.ascontiguousarray(seg_begin[mine], dtype=np.uint64)
+        sl = np.ascontiguousarray(seg_len[mine], dtype=np.uint64)
+        cb._capi.check(lib.bcb_radix_sort_segments(q.handle, code, int(not desc), rk[d].data_ptr() + guard,
+                                                   (rv[d].data_ptr() + guard) if v is not None else None, value_bytes, ok.data_ptr(),
+                                                   ov.data_ptr() if v is not None else None, sb.ctypes.data, sl.ctypes.data, sb.size))
+        q.finish()
+        outs_k.append(ok.cpu().numpy())
+        outs_v.append(ov.cpu().numpy())
+    if v is None:
+        exp_k = oracle.radix_sort(k, desc)
+    else:
+        exp_k, exp_v = oracle.radix_sort(k, desc, v)
+        assert np.concatenate(outs_v).tobytes() == exp_v.tobytes(), (dtype, value_bytes, world, "payload")
+    assert np.concatenate(outs_k).tobytes() == exp_k.tobytes(), (dtype, value_bytes, world, "keys")
+
+
 @pytest.mark.parametrize("dtype", ["float", "double"])
 def test_large_descending_float_sort_with_colliding_keys_stays_deterministic(dtype, gpu):
     """Descending float keys: -0.0 / +denorm_min (and +0.0 / -denorm_min) share a transformed key in the reference
