@@ -128,7 +128,8 @@ def digit_exchange_plan(all_hist: np.ndarray, world: int, max_imbalance: float =
     if n == 0 or world <= 1:
         return None
     edges = _digit_edges(tot, world)
-    recv = np.array([int(tot[edges[d]:edges[d + 1]].sum()) for d in range(world)], dtype=np.int64)
+    cum = np.concatenate([[0], np.cumsum(tot)])
+    recv = cum[edges[1:]] - cum[edges[:-1]]
     imbalance = float(recv.max() * world / n)
     if imbalance > max_imbalance:
         return None
@@ -138,8 +139,9 @@ def digit_exchange_plan(all_hist: np.ndarray, world: int, max_imbalance: float =
     before = np.cumsum(padded) - padded                             # aligned slots of the smaller digits, globally
     seg_begin = before - before[edges[owner]]                       # ... among the owner's digits
     first = seg_begin[None, :] + (np.cumsum(h, axis=0) - h)         # + the same digit on the sources before src
-    span = np.array([int((seg_begin + tot)[owner == d].max()) if np.any(owner == d) else 0 for d in range(world)], dtype=np.int64)
-    return owner, first.astype(np.int64), seg_begin.astype(np.int64), tot.astype(np.int64), recv, span, imbalance
+    last = np.maximum(edges[1:] - 1, 0)                             # the owner's last digit value ends its span
+    span = np.where(edges[1:] > edges[:-1], (seg_begin + tot)[last], 0).astype(np.int64)
+    return owner, first.astype(np.int64), seg_begin.astype(np.int64), tot.astype(np.int64), recv.astype(np.int64), span, imbalance
 
 
 def exchange_plan(points: np.ndarray, n_local: int):
@@ -233,12 +235,12 @@ class CudaLocalOps:
         """One stable pass over the most significant digit: digit g's run goes to the array at dst_keys[g] (possibly a
         peer's memory) from element dst_first[g] on.  Asynchronous; the shard is not modified.  False: shape not supported
         (decided from the types: the same answer on every rank)."""
-        dk = (ctypes.c_void_p * 256)(*[int(a) for a in dst_keys])
-        dv = (ctypes.c_void_p * 256)(*[int(a) for a in dst_values]) if values is not None else None
+        dk = np.ascontiguousarray(dst_keys, dtype=np.uint64)  # (void *const *: 256 device addresses)
+        dv = np.ascontiguousarray(dst_values, dtype=np.uint64)
         df = np.ascontiguousarray(dst_first, dtype=np.uint64)
         rc = self._lib.bcb_radix_exchange_scatter(self.queue.handle, dtype_code(keys.dtype), int(not descending), keys.data_ptr(),
                                                   None if values is None else values.data_ptr(), self._row_bytes(values), keys.shape[0],
-                                                  dk, dv, df.ctypes.data)
+                                                  dk.ctypes.data, dv.ctypes.data if values is not None else None, df.ctypes.data)
         if rc == 10002:  # BCB_EUNSUPPORTED
             return False
         self._check(rc)
@@ -401,6 +403,7 @@ class Context:
         self.use_peer_memory = os.environ.get("BCB_DIST_PEER", "1") != "0"
         self.use_histogram_plan = os.environ.get("BCB_DIST_HISTOGRAM", "1") != "0"  # 0: always sample (A/B comparison)
         self.use_digit_exchange = os.environ.get("BCB_DIST_DIGIT_EXCHANGE", "1") != "0"  # 0: partition pass + local sort (A/B)
+        self.digit_exchange_wide = os.environ.get("BCB_DIST_DIGIT_EXCHANGE", "1") == "2"  # also for 64-bit keys
         self.profile = os.environ.get("BCB_DIST_PROFILE", "0") == "1"
         self._flag = None
 
@@ -494,8 +497,12 @@ class Context:
             # 32-bit keys (payload 0 / 4 / 8 bytes) or 64-bit keys alone with an injective transform (the decision depends
             # on shapes only: the same on every rank).
             ksize = keys.element_size()
+            # (64-bit keys alone are covered by the kernels too, but measured slower than the partition pass + local sort:
+            # the warp-specialised kernel's 21504-key tiles lose more per pass than the saved ninth pass gains --
+            # 40.7 against 44.8 Gkeys/s on 2 GPUs; BCB_DIST_DIGIT_EXCHANGE=2 forces the plan for them)
             digit_ok = (self.use_digit_exchange and hasattr(self.ops, "exchange_scatter")
-                        and (ksize == 4 or (ksize == 8 and vb == 0 and not (keys.dtype == torch.float64 and descending))))
+                        and (ksize == 4 or (self.digit_exchange_wide and ksize == 8 and vb == 0
+                                            and not (keys.dtype == torch.float64 and descending))))
             hist = self.ops.top_histogram(keys, descending) if n_local else np.zeros(256, np.int64)
             all_hist = self._all_gather_np(hist)
             self._phase("histogram")
@@ -555,8 +562,8 @@ class Context:
         # (the all-gather of the histograms also ordered this call after every rank's previous use of its receive buffer)
         if not self.peer.ensure(max(256, val_off + max_span * vb)):
             return None
-        dst_k = [self.peer.peers[int(owner[g])] for g in range(256)]
-        dst_v = [self.peer.peers[int(owner[g])] + val_off for g in range(256)]
+        dst_k = np.asarray(self.peer.peers, dtype=np.uint64)[owner]
+        dst_v = dst_k + np.uint64(val_off)
         self._phase("plan")
         if self.ops.device_type == "cuda":  # the pass moves whole 16-byte chunks: a misaligned view is copied first
             if keys.data_ptr() % 16:

@@ -118,11 +118,12 @@ BCB_API int bcb_radix_sort(bcb_stream stream, int key_dtype, int ascending, void
 BCB_API int bcb_radix_sort_copy(bcb_stream stream, int key_dtype, int ascending, const void *keys_in, void *keys_out,
                                 size_t n, const void *values_in, void *values_out, size_t value_bytes);
 
-/* Keys-only sorts of >= 2^22 32/64-bit keys (except descending float / double keys, whose reference transform is not
- * injective) run a faster, speculatively stable pass kernel, verify the result (sorted by the transformed key <=>
- * correct, because every pass is a permutation) and fall back to the deterministic kernel if the check fails; such
- * calls block until the verification is done.  These counters report how often that happened on the
- * stream.  BCB_SORT_SPECULATIVE=0 in the environment disables speculation. */
+/* Keys-only sorts of >= 2^24 32/64-bit keys (except descending float / double keys, whose reference transform is not
+ * injective) run a faster, speculatively stable pass kernel and verify the result on the device (sorted by the
+ * transformed key <=> correct, because every pass is a permutation); the deterministic sort of the same buffer is
+ * enqueued behind the check with every launch gated on its flag, so nothing waits on the host and the call stays
+ * enqueue-and-return.  These counters report how often that happened on the stream (the read waits for the stream).
+ * BCB_SORT_SPECULATIVE=0 in the environment disables speculation. */
 BCB_API int bcb_sort_speculation_stats(bcb_stream stream, unsigned long long *verified_runs, unsigned long long *fallbacks);
 /* is the range sorted by the transformed radix key of radix_sort.hpp:100-127 (the order radix_sort defines, which for
  * floats differs from operator< on +-0 / NaN)?  This is the check the speculative sort runs on its own output. Blocks. */
