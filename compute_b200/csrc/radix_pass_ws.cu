@@ -130,6 +130,8 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
         WS_PROF_DECL;
         auto draw = [&](unsigned i) {  // tile id of the CTA's i-th tile -> ring[i & 3], visible after the workers' barrier
             if (tid == 0) {
+                // (Spreading the CTAs' first draws over one tile period -- so that the SMs do not all read their next tile
+                // from HBM at the same moment -- was measured: 9.64 against 9.69 ms for the four passes of 2^30 keys, noise.)
                 const unsigned long long t = atomicAdd(ticket, 1ull) - ticket_base;
                 ring[i & 3u] = t < num_tiles ? (unsigned)t : kWsNoTile;
                 if (t < num_tiles) {
