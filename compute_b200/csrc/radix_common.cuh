@@ -157,7 +157,14 @@ __device__ __forceinline__ unsigned pass_digit(K raw, int shift, const Transform
 // deterministic atomic-OR ranking.  Returns BCB_EUNSUPPORTED for shapes it does not cover (arrays not 16-byte aligned).
 int ws_launch_pass(StreamState *st, int key_bytes, const void *kin, void *kout, const void *vin, void *vout, int value_bytes,
                    const unsigned *base, unsigned long long *lookback, size_t n, int shift, const Transform &tf, int xf, bool deterministic,
-                   const unsigned long long *dst_tab = nullptr, const uint4 *tile_tab = nullptr, size_t tab_tiles = 0);
+                   const unsigned long long *dst_tab = nullptr, const uint4 *tile_tab = nullptr, size_t tab_tiles = 0,
+                   const unsigned *hot = nullptr);
+// hot (device, [2]): digit values of this pass that hold so many keys that same-address shared atomics would serialise
+// (digit_scan finds them); the kernel ranks those by ballot.  kNoHotDigit = none.
+constexpr unsigned kNoHotDigit = 0xffffffffu;
+// layout of StreamState::hist (unsigned words): [0, 2048) digit counts, [2048, 4096) digit bases, [4096, 5120) destination
+// table of the exchange pass (512 x u64), [5120, 5136) hot digits
+constexpr int kHistHotOffset = 5120;
 // tile_tab (device, one uint4 per tile: {first key, end, first tile of the segment, segment}): segmented pass -- every
 // segment is sorted on its own, base is indexed [segment][256] (see bcb_radix_sort_segments).
 // dst_tab (device, [2][256]): the pass is the exchange pass of the multi-GPU sort -- the run of digit value d is written to

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(kWsThreads, 1)
 onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *__restrict__ vals_in_v, void *__restrict__ vals_out_v,
             const unsigned *__restrict__ digit_base, unsigned long long *lookback, unsigned epoch, size_t n, unsigned num_tiles, int shift,
             const __grid_constant__ Transform tf, unsigned long long *ticket, unsigned long long ticket_base, int flags,
-            const unsigned long long *__restrict__ dst_tab, const uint4 *__restrict__ tile_tab)
+            const unsigned long long *__restrict__ dst_tab, const uint4 *__restrict__ tile_tab, const unsigned *__restrict__ hot)
 {
     typedef WsShape<K, VB, DET> C;
     typedef typename ws_value<VB>::type V;
@@ -127,6 +127,35 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
         auto sortable = [&](K raw) -> U { return (XF == kXfIn || XF == kXfBoth) ? transform_fwd<K>(raw, tf) : (U)raw; };
         auto digit = [&](U t) -> unsigned { return (unsigned)(t >> shift) & (kRadixSize - 1); };
         auto stored = [&](K raw, U t) -> K { return XF == kXfOut ? transform_inv<K>(t, tf) : (XF == kXfIn ? (K)t : raw); };
+        // Digit values that hold a large share of the keys (constant high bytes of small integers, the exponent byte of
+        // floats): 32 lanes adding to ONE shared-memory counter serialise, a pass over such a digit took 2-8x as long.
+        // digit_scan names up to two such values; their lanes are ranked by ballot (one atomic per warp instruction and
+        // value, by the first of them), which is also the lane order the speculative ranking assumes anyway.
+        const unsigned h0 = hot ? __ldg(hot) : kNoHotDigit, h1 = hot ? __ldg(hot + 1) : kNoHotDigit;
+        const bool hot_mode = !DET && h0 != kNoHotDigit;
+        // hot lanes touch no shared memory at all: their counts / positions are kept in two (warp-uniform) registers per
+        // sweep -- the count of the hot value is added to the table once per tile, the positions are start-of-run +
+        // keys of that value seen so far + lanes below in the ballot
+        auto count_one = [&](unsigned *row, unsigned d, unsigned &acc0, unsigned &acc1, auto hot_tag) {
+            if constexpr (!decltype(hot_tag)::value) {
+                atomicAdd(&row[d], 1u);
+            } else {
+                const bool a = d == h0, b = d == h1;
+                acc0 += __popc(__ballot_sync(0xffffffffu, a));
+                acc1 += __popc(__ballot_sync(0xffffffffu, b));
+                if (!(a || b)) atomicAdd(&row[d], 1u);
+            }
+        };
+        auto rank_one = [&](unsigned *row, unsigned d, unsigned &run0, unsigned &run1, auto hot_tag) -> unsigned {
+            if constexpr (!decltype(hot_tag)::value) return atomicAdd(&row[d], 1u);  // start of the (warp, digit) run + rank: the same adds as count_one
+            const bool a = d == h0, b = d == h1;
+            const unsigned ma = __ballot_sync(0xffffffffu, a), mb = __ballot_sync(0xffffffffu, b);
+            unsigned pos = (a ? run0 : run1) + __popc((a ? ma : mb) & lanemask_lt());
+            if (!(a || b)) pos = atomicAdd(&row[d], 1u);
+            run0 += __popc(ma);
+            run1 += __popc(mb);
+            return pos;
+        };
         WS_PROF_DECL;
         auto draw = [&](unsigned i) {  // tile id of the CTA's i-th tile -> ring[i & 3], visible after the workers' barrier
             if (tid == 0) {
@@ -151,17 +180,19 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
             named_bar_sync(kBarWorkers, kWsWorkers);
             return ring[i & 3u];
         };
-        auto count = [&](unsigned p, unsigned i) {
+        auto count = [&](unsigned p, unsigned i, auto hot_tag) {
             const unsigned t_first = tile_start(i), t_end = tile_end(i);
             const size_t base = (size_t)t_first + (size_t)w * SEG;
             unsigned *row = tab + (p * kWsWorkerWarps + w) * ROW;
+            unsigned acc0 = 0, acc1 = 0;  // keys of the hot digit values in this warp's segment
             if (t_end - t_first == (unsigned)TILE) {
                 // any order inside the warp's segment: 128-bit loads, a window of WIN per lane in flight.  The lines are
                 // asked to STAY in L2 (evict_last): the scatter sweep reads them again one tile later.
                 const uint4 *src = reinterpret_cast<const uint4 *>(keys_in + base) + lane;
                 constexpr int VECK = 16 / (int)sizeof(K);                                     // keys per 128-bit vector
                 constexpr int NV = SEG / VECK / 32;                                           // vectors per lane
-                constexpr int WIN = NV % 7 == 0 ? 7 : (NV % 6 == 0 ? 6 : (NV % 4 == 0 ? 4 : 1));  // vectors in flight per lane
+                constexpr int WIN0 = NV % 7 == 0 ? 7 : (NV % 6 == 0 ? 6 : (NV % 4 == 0 ? 4 : 1));  // vectors in flight per lane
+                constexpr int WIN = (decltype(hot_tag)::value && WIN0 > 4) ? (NV % 4 == 0 ? 4 : (NV % 3 == 0 ? 3 : 2)) : WIN0;  // (the ballot ranking needs registers)
                 uint4 v[WIN];
 #pragma unroll
                 for (int u = 0; u < WIN; u++) v[u] = ld_hint_v4(src + u * 32, keep);
@@ -169,7 +200,7 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
                 for (int j = 0; j < NV; j++) {
                     const K *e = reinterpret_cast<const K *>(&v[j % WIN]);
 #pragma unroll
-                    for (int c = 0; c < VECK; c++) atomicAdd(&row[digit(sortable(e[c]))], 1u);
+                    for (int c = 0; c < VECK; c++) count_one(row, digit(sortable(e[c])), acc0, acc1, hot_tag);
                     if (j + WIN < NV) v[j % WIN] = ld_hint_v4(src + (j + WIN) * 32, keep);
                 }
             } else {
@@ -177,16 +208,21 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
                 for (int i = 0; i < ITEMS; i++) {
                     const size_t idx = base + (size_t)i * 32 + lane;
                     // padding counts as digit 255: sorts last
-                    atomicAdd(&row[idx < t_end ? digit(sortable(__ldg(keys_in + idx))) : (unsigned)(kRadixSize - 1)], 1u);
+                    count_one(row, idx < t_end ? digit(sortable(__ldg(keys_in + idx))) : (unsigned)(kRadixSize - 1), acc0, acc1, hot_tag);
                 }
+            }
+            if constexpr (decltype(hot_tag)::value) {
+                if (lane == 0 && acc0) atomicAdd(&row[h0], acc0);
+                if (lane == 1 && acc1) atomicAdd(&row[h1], acc1);  // (acc1 stays 0 when there is no second hot value)
             }
             named_bar_arrive(kBarCounted + p, kWsThreads);
         };
-        auto scatter_tile = [&](unsigned p, unsigned i_tile, bool first, auto full_tag) {
+        auto scatter_tile = [&](unsigned p, unsigned i_tile, bool first, auto full_tag, auto hot_tag) {
             constexpr bool FULL = decltype(full_tag)::value;
             const size_t n = tile_end(i_tile);  // (shadows the range length: the bound of THIS tile)
             const size_t base = (size_t)tile_start(i_tile) + (size_t)w * SEG + lane;
             unsigned *row = tab + (p * kWsWorkerWarps + w) * ROW;
+            constexpr int CHUNK = (decltype(hot_tag)::value && C::CHUNK % 2 == 0) ? C::CHUNK / 2 : C::CHUNK;  // (the ballot ranking needs registers)
             K cur[CHUNK], nxt[CHUNK];
             V vcur[VB ? CHUNK : 1], vnxt[VB ? CHUNK : 1];
             auto load = [&](K (&dst)[CHUNK], V (&vdst)[VB ? CHUNK : 1], int c) {
@@ -204,6 +240,11 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
             if (!first) named_bar_sync(kBarDrained, kWsThreads);  // the previous tile's bulk copies have read the buffer
             WS_PROF_END(3);
             unsigned *mrow = masks + w * ROW;
+            unsigned run0 = 0, run1 = 0;  // next position of the hot digit values in this warp's runs
+            if constexpr (decltype(hot_tag)::value) {
+                run0 = row[h0];
+                run1 = row[h1 != kNoHotDigit ? h1 : h0];
+            }
 #pragma unroll 1
             for (int c = 0; c < ITEMS / CHUNK; c++) {
                 if (c + 1 < ITEMS / CHUNK) load(nxt, vnxt, c + 1);
@@ -230,7 +271,7 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
                     } else {
                         // same atomics, same order as count(): start of the run + rank.  (Issuing all atomics of the chunk
                         // before the first store was measured 3 % slower: the LSU queue, not the latency, is the limit.)
-                        pos = atomicAdd(&row[d], 1u);
+                        pos = rank_one(row, d, run0, run1, hot_tag);
                     }
                     buf[pos] = stored(cur[i], t);
                     if constexpr (VB > 0) vbuf[pos] = vcur[i];
@@ -251,22 +292,32 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
             named_bar_arrive(kBarScattered, kWsThreads);
             WS_PROF_END(4);
         };
-        auto scatter = [&](unsigned p, unsigned i_tile, bool first) {
-            if (tile_end(i_tile) - tile_start(i_tile) == (unsigned)TILE) scatter_tile(p, i_tile, first, std::true_type());
-            else scatter_tile(p, i_tile, first, std::false_type());
+        auto scatter = [&](unsigned p, unsigned i_tile, bool first, auto hot_tag) {
+            if (tile_end(i_tile) - tile_start(i_tile) == (unsigned)TILE) scatter_tile(p, i_tile, first, std::true_type(), hot_tag);
+            else scatter_tile(p, i_tile, first, std::false_type(), hot_tag);
         };
-        unsigned t_cur = draw(0);
-        if (t_cur != kWsNoTile) count(0, 0);
-        else named_bar_arrive(kBarCounted + 0, kWsThreads);
-        for (unsigned i = 0; t_cur != kWsNoTile; ++i) {
-            WS_PROF_BEGIN();
-            const unsigned t_next = draw(i + 1);
-            WS_PROF_END(0);
-            if (t_next != kWsNoTile) count((i + 1) & 1u, i + 1);
-            else named_bar_arrive(kBarCounted + ((i + 1) & 1u), kWsThreads);  // the helpers learn from the ring that it is void
-            WS_PROF_END(1);
-            scatter(i & 1u, i, i == 0);
-            t_cur = t_next;
+        // (two copies of the loop, chosen once: the ballot ranking costs nothing -- not even registers -- where no digit
+        // value is hot)
+        auto work = [&](auto hot_tag) {
+            unsigned t_cur = draw(0);
+            if (t_cur != kWsNoTile) count(0, 0, hot_tag);
+            else named_bar_arrive(kBarCounted + 0, kWsThreads);
+            for (unsigned i = 0; t_cur != kWsNoTile; ++i) {
+                WS_PROF_BEGIN();
+                const unsigned t_next = draw(i + 1);
+                WS_PROF_END(0);
+                if (t_next != kWsNoTile) count((i + 1) & 1u, i + 1, hot_tag);
+                else named_bar_arrive(kBarCounted + ((i + 1) & 1u), kWsThreads);  // the helpers learn from the ring that it is void
+                WS_PROF_END(1);
+                scatter(i & 1u, i, i == 0, hot_tag);
+                t_cur = t_next;
+            }
+        };
+        if constexpr (DET) {
+            work(std::false_type());
+        } else {
+            if (hot_mode) work(std::true_type());
+            else work(std::false_type());
         }
         if (tid == 0) WS_PROF_DUMP(0);
     } else {
@@ -454,7 +505,7 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
 template <typename K, int VB, bool DET, int XF>
 static int ws_launch_typed(StreamState *st, const void *kin, void *kout, const void *vin, void *vout, const unsigned *base,
                            unsigned long long *lookback, size_t n, int shift, const Transform &tf, const unsigned long long *dst_tab,
-                           const uint4 *tile_tab, size_t tab_tiles)
+                           const uint4 *tile_tab, size_t tab_tiles, const unsigned *hot)
 {
     typedef WsShape<K, VB, DET> C;
     auto kernel = onesweep_ws<K, VB, DET, XF, 8>;
@@ -474,7 +525,7 @@ static int ws_launch_typed(StreamState *st, const void *kin, void *kout, const v
     LaunchTimer timer(st, dst_tab ? BCB_K_EXCHANGE_PASS : BCB_K_ONESWEEP_PASS);
     kernel<<<(unsigned)grid, kWsThreads, C::SMEM_BYTES, st->stream>>>((const K *)kin, (K *)kout, vin, vout, base, lookback, epoch, n,
                                                                       (unsigned)tiles, shift, tf, st->control + kControlTicket, ticket_base, ws_flags,
-                                                                      dst_tab, tile_tab);
+                                                                      dst_tab, tile_tab, hot);
     BCB_CUDA_TRY(cudaGetLastError());
 #ifdef BCB_WS_PROFILE
     {   // mean cycles per CTA and phase (workers 0-7, helpers 8-15); see the WS_PROF_END(k) sites for what k is
@@ -495,13 +546,13 @@ static int ws_launch_typed(StreamState *st, const void *kin, void *kout, const v
 template <typename K, int VB, bool DET>
 static int ws_launch_xf(StreamState *st, const void *kin, void *kout, const void *vin, void *vout, const unsigned *base,
                         unsigned long long *lookback, size_t n, int shift, const Transform &tf, int xf, const unsigned long long *dst_tab,
-                        const uint4 *tile_tab, size_t tab_tiles)
+                        const uint4 *tile_tab, size_t tab_tiles, const unsigned *hot)
 {
     switch (xf) {
-    case kXfNone: return ws_launch_typed<K, VB, DET, kXfNone>(st, kin, kout, vin, vout, base, lookback, n, shift, tf, dst_tab, tile_tab, tab_tiles);
-    case kXfIn: return ws_launch_typed<K, VB, DET, kXfIn>(st, kin, kout, vin, vout, base, lookback, n, shift, tf, dst_tab, tile_tab, tab_tiles);
-    case kXfOut: return ws_launch_typed<K, VB, DET, kXfOut>(st, kin, kout, vin, vout, base, lookback, n, shift, tf, dst_tab, tile_tab, tab_tiles);
-    default: return ws_launch_typed<K, VB, DET, kXfBoth>(st, kin, kout, vin, vout, base, lookback, n, shift, tf, dst_tab, tile_tab, tab_tiles);
+    case kXfNone: return ws_launch_typed<K, VB, DET, kXfNone>(st, kin, kout, vin, vout, base, lookback, n, shift, tf, dst_tab, tile_tab, tab_tiles, hot);
+    case kXfIn: return ws_launch_typed<K, VB, DET, kXfIn>(st, kin, kout, vin, vout, base, lookback, n, shift, tf, dst_tab, tile_tab, tab_tiles, hot);
+    case kXfOut: return ws_launch_typed<K, VB, DET, kXfOut>(st, kin, kout, vin, vout, base, lookback, n, shift, tf, dst_tab, tile_tab, tab_tiles, hot);
+    default: return ws_launch_typed<K, VB, DET, kXfBoth>(st, kin, kout, vin, vout, base, lookback, n, shift, tf, dst_tab, tile_tab, tab_tiles, hot);
     }
 }
 
@@ -522,16 +573,16 @@ bool ws_supports(int key_bytes, int value_bytes, bool deterministic)
 
 int ws_launch_pass(StreamState *st, int key_bytes, const void *kin, void *kout, const void *vin, void *vout, int value_bytes,
                    const unsigned *base, unsigned long long *lookback, size_t n, int shift, const Transform &tf, int xf, bool deterministic,
-                   const unsigned long long *dst_tab, const uint4 *tile_tab, size_t tab_tiles)
+                   const unsigned long long *dst_tab, const uint4 *tile_tab, size_t tab_tiles, const unsigned *hot)
 {
     // bulk copies need 16-byte aligned arrays (with dst_tab the caller has checked the destinations it holds)
     if ((((uintptr_t)kin | (uintptr_t)kout | (uintptr_t)vin | (uintptr_t)vout) & 15) != 0) return BCB_EUNSUPPORTED;
     if (!ws_supports(key_bytes, value_bytes, deterministic)) return BCB_EUNSUPPORTED;
-    if (value_bytes == 4) return ws_launch_xf<unsigned, 4, true>(st, kin, kout, vin, vout, base, lookback, n, shift, tf, xf, dst_tab, tile_tab, tab_tiles);
-    if (value_bytes == 8) return ws_launch_xf<unsigned, 8, true>(st, kin, kout, vin, vout, base, lookback, n, shift, tf, xf, dst_tab, tile_tab, tab_tiles);
-    if (key_bytes == 8) return ws_launch_xf<unsigned long long, 0, false>(st, kin, kout, nullptr, nullptr, base, lookback, n, shift, tf, xf, dst_tab, tile_tab, tab_tiles);
-    return deterministic ? ws_launch_xf<unsigned, 0, true>(st, kin, kout, nullptr, nullptr, base, lookback, n, shift, tf, xf, dst_tab, tile_tab, tab_tiles)
-                         : ws_launch_xf<unsigned, 0, false>(st, kin, kout, nullptr, nullptr, base, lookback, n, shift, tf, xf, dst_tab, tile_tab, tab_tiles);
+    if (value_bytes == 4) return ws_launch_xf<unsigned, 4, true>(st, kin, kout, vin, vout, base, lookback, n, shift, tf, xf, dst_tab, tile_tab, tab_tiles, hot);
+    if (value_bytes == 8) return ws_launch_xf<unsigned, 8, true>(st, kin, kout, vin, vout, base, lookback, n, shift, tf, xf, dst_tab, tile_tab, tab_tiles, hot);
+    if (key_bytes == 8) return ws_launch_xf<unsigned long long, 0, false>(st, kin, kout, nullptr, nullptr, base, lookback, n, shift, tf, xf, dst_tab, tile_tab, tab_tiles, hot);
+    return deterministic ? ws_launch_xf<unsigned, 0, true>(st, kin, kout, nullptr, nullptr, base, lookback, n, shift, tf, xf, dst_tab, tile_tab, tab_tiles, hot)
+                         : ws_launch_xf<unsigned, 0, false>(st, kin, kout, nullptr, nullptr, base, lookback, n, shift, tf, xf, dst_tab, tile_tab, tab_tiles, hot);
 }
 
 }  // namespace bcb

@@ -144,11 +144,13 @@ radix_histogram_columns(const K *__restrict__ keys, size_t n, unsigned *__restri
 
 // ---- 2. exclusive scan of each digit histogram: hist[p][d] -> base[p][d] -------------------------
 __global__ void __launch_bounds__(kRadixSize) digit_scan(const unsigned *__restrict__ hist, unsigned *__restrict__ base,
-                                                         const int *__restrict__ gate = nullptr, unsigned long long *fallbacks = nullptr)
+                                                         const int *__restrict__ gate = nullptr, unsigned long long *fallbacks = nullptr,
+                                                         unsigned *__restrict__ hot = nullptr)
 {
     if (gate && *gate == 0) return;
     if (fallbacks && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(fallbacks, 1ull);  // a gated launch that runs IS a fallback
     __shared__ unsigned wsum[kRadixSize / 32];
+    __shared__ unsigned long long wmax[kRadixSize / 32];
     const unsigned d = threadIdx.x, lane = d & 31u, warp = d >> 5;
     const unsigned c = hist[blockIdx.x * kRadixSize + d];
     unsigned s = c;
@@ -159,9 +161,39 @@ __global__ void __launch_bounds__(kRadixSize) digit_scan(const unsigned *__restr
     }
     if (lane == 31) wsum[warp] = s;
     __syncthreads();
-    unsigned add = 0;
-    for (unsigned w = 0; w < warp; w++) add += wsum[w];
+    unsigned add = 0, total = 0;
+    for (unsigned w = 0; w < kRadixSize / 32; w++) {
+        if (w < warp) add += wsum[w];
+        total += wsum[w];
+    }
     base[blockIdx.x * kRadixSize + d] = s - c + add;
+    if (!hot) return;
+    // a digit value that holds at least half of the keys (and then a second one with at least a quarter): the
+    // warp-specialised pass ranks those by ballot instead of same-address shared atomics, which serialise
+    // (hot[2 * pass + {0, 1}], kNoHotDigit when there is none).  Measured on B200, 2^28 u32 keys: keys < 2^16 61 -> 83
+    // Gkeys/s, keys < 1000 59 -> 76; with shares of 30-40 % (perf_sort_float's exponent byte) the ballots cost what they
+    // save (81.4 against 79.9 Gkeys/s), hence the thresholds.
+    unsigned long long mine = ((unsigned long long)c << 8) | d, first = 0;
+    for (int round = 0; round < 2; round++) {
+        unsigned long long m = mine;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, m, off);
+            m = o > m ? o : m;
+        }
+        __syncthreads();  // (wmax of the previous round has been read)
+        if (lane == 0) wmax[warp] = m;
+        __syncthreads();
+        unsigned long long best = 0;
+        for (unsigned w = 0; w < kRadixSize / 32; w++) best = wmax[w] > best ? wmax[w] : best;
+        const bool is_hot = total != 0 && (round == 0 ? (best >> 8) * 2 >= (unsigned long long)total
+                                                      : ((first >> 8) * 2 >= (unsigned long long)total && (best >> 8) * 4 >= (unsigned long long)total));
+        if (d == 0) hot[blockIdx.x * 2 + round] = is_hot ? (unsigned)(best & 0xffu) : kNoHotDigit;
+        if (round == 0) {
+            first = best;
+            if (mine == first) mine = 0;  // the runner-up comes from the others
+        }
+    }
 }
 
 // ---- 3. one onesweep pass ---------------------------------------------------------------------------
@@ -667,6 +699,7 @@ static int launch_pass_impl(StreamState *st, const void *kin, void *kout, const 
 //   BCB_SORT_SPECULATIVE=0       always use the deterministic atomic-OR kernel
 //   BCB_SORT_FORCE_FALLBACK=1    test hook: treat every verification as failed
 //   BCB_SORT_WS=0                keep the r01 two-sweep kernel for large sorts (A/B comparison)
+//   BCB_SORT_HOT=0               warp-specialised kernel: no ballot ranking of frequent digit values (A/B comparison)
 //   BCB_SORT_SPEC_MIN_LOG2=k, BCB_SORT_WS_MIN_LOG2=k   test hooks: move the size thresholds below
 // Size thresholds, measured on B200 (2^k uint32 keys, ms per sort: deterministic / two-sweep + verification / onesweep_ws +
 // verification): 2^23 0.26 / - / 0.33; 2^24 0.45 / 0.34 / -; 2^25 0.70 / 0.52 / 0.61; 2^26 1.19 / 0.90 / 0.95; 2^27 2.19 / - / 1.63;
@@ -675,7 +708,7 @@ static int launch_pass_impl(StreamState *st, const void *kin, void *kout, const 
 constexpr int kSpeculativeMinLog2 = 24;
 constexpr int kWsMinLog2 = 27;
 struct SortEnv {
-    bool speculative, force_fallback, ws;
+    bool speculative, force_fallback, ws, hot;
     size_t spec_min, ws_min;
     SortEnv()
     {
@@ -692,6 +725,8 @@ struct SortEnv {
         force_fallback = e && e[0] == '1';
         e = std::getenv("BCB_SORT_WS");
         ws = !(e && e[0] == '0');
+        e = std::getenv("BCB_SORT_HOT");  // 0: no ballot ranking of frequent digit values (A/B comparison)
+        hot = !(e && e[0] == '0');
     }
 };
 static const SortEnv &sort_env()
@@ -821,7 +856,8 @@ static size_t tile_size_for(int pass_kind)
 
 template <typename K, int VB>
 static int run_pass(StreamState *st, const void *kin, void *kout, const void *vin, void *vout, const unsigned *base,
-                    unsigned long long *lookback, size_t n, int shift, const Transform &tf, int pass_kind, const int *gate)
+                    unsigned long long *lookback, size_t n, int shift, const Transform &tf, int pass_kind, const int *gate,
+                    const unsigned *hot = nullptr)
 {
     if (pass_kind == kPassWs || pass_kind == kPassWsDet) {
         // keys travel between the passes in transformed form (one transform in the first pass, its inverse in the last)
@@ -829,7 +865,8 @@ static int run_pass(StreamState *st, const void *kin, void *kout, const void *vi
         const bool ident = (tf.nm | tf.xc | tf.fa) == 0, injective = !(tf.fa != 0 && tf.nm != 0);
         constexpr int kLastShift = ((int)sizeof(K) - 1) * kRadixBits;
         const int xf = ident ? kXfNone : (!injective ? kXfBoth : (shift == 0 ? kXfIn : (shift == kLastShift ? kXfOut : kXfNone)));
-        return ws_launch_pass(st, (int)sizeof(K), kin, kout, vin, vout, VB, base, lookback, n, shift, tf, xf, pass_kind == kPassWsDet);
+        return ws_launch_pass(st, (int)sizeof(K), kin, kout, vin, vout, VB, base, lookback, n, shift, tf, xf, pass_kind == kPassWsDet,
+                              nullptr, nullptr, 0, hot);
     }
     if constexpr (VB == 0 && (sizeof(K) == 4 || sizeof(K) == 8)) {
         if (pass_kind == kPassTwoSweep)
@@ -1033,19 +1070,21 @@ static int sort_passes(StreamState *st, void *keys, void *values, size_t n, cons
 
     unsigned *hist = st->hist;
     unsigned *base = st->hist + 8 * kRadixSize;
+    unsigned *hot = st->hist + kHistHotOffset;  // [8 passes][2] digit values the warp-specialised pass ranks by ballot
+    const bool ws_kind = (pass_kind == kPassWs || pass_kind == kPassWsDet) && sort_env().hot;
     BCB_CUDA_TRY(cudaMemsetAsync(hist, 0, NPASS * kRadixSize * sizeof(unsigned), st->stream));
     {
         BCB_TRY((launch_histogram<K>(st, src_keys, n, hist, tf, gate)));
         {
             LaunchTimer timer(st, gate ? BCB_K_OTHER : BCB_K_DIGIT_SCAN);
-            digit_scan<<<NPASS, kRadixSize, 0, st->stream>>>(hist, base, gate, gate ? spec_fallback_counter(st) : nullptr);
+            digit_scan<<<NPASS, kRadixSize, 0, st->stream>>>(hist, base, gate, gate ? spec_fallback_counter(st) : nullptr, ws_kind ? hot : nullptr);
         }
         BCB_CUDA_TRY(cudaGetLastError());
     }
     void *kin = keys, *kout = tmp_keys, *vin = values, *vout = tmp_vals;
     for (int p = 0; p < NPASS; p++) {
         BCB_TRY((run_pass<K, VB>(st, p == 0 ? src_keys : kin, kout, p == 0 ? src_vals : vin, vout, base + p * kRadixSize,
-                                 (unsigned long long *)lb, n, p * kRadixBits, tf, pass_kind, gate)));
+                                 (unsigned long long *)lb, n, p * kRadixBits, tf, pass_kind, gate, ws_kind ? hot + 2 * p : nullptr)));
         void *t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;
     }

@@ -22,7 +22,7 @@ struct KeyHash {
 std::mutex g_mutex;
 std::unordered_map<Key, StreamState *, KeyHash> g_states;
 constexpr size_t kControlBytes = 256;
-constexpr size_t kHistBytes = 8 * 256 * sizeof(uint32_t) * 2 + 2 * 256 * sizeof(unsigned long long);  // counts + bases + destination table of the exchange pass
+constexpr size_t kHistBytes = 8 * 256 * sizeof(uint32_t) * 2 + 2 * 256 * sizeof(unsigned long long) + 256;  // counts + bases + destination table of the exchange pass + hot digits (radix_common.cuh)
 constexpr size_t kPinnedSlotBytes = 64;
 }  // namespace
 

@@ -475,6 +475,31 @@ def test_partition_counts_and_scatter_to_separate_buffers(dtype, value_bytes, ns
                 assert not gv[:lo].any() and not gv[lo + sel.size * value_bytes:].any()
 
 
+@pytest.mark.parametrize("kind", ["small_ints", "two_values", "float_range", "one_hot_rest_uniform", "constant"])
+def test_hot_digit_values_are_ranked_by_ballot_bit_exact(kind, gpu):
+    """Keys whose digits are far from uniform (constant high bytes of small integers, the exponent byte of floats, a
+    handful of distinct keys): the warp-specialised pass ranks the lanes of the one or two most frequent digit values of
+    a pass by ballot instead of same-address shared atomics.  >= 2^23 keys so that kernel runs (tests/conftest.py);
+    byte-exact against the oracle."""
+    n = (1 << 23) + 7777
+    rng = np.random.default_rng(5)
+    if kind == "small_ints":
+        k = rng.integers(0, 3000, size=n).astype(np.uint32)          # two constant digits, one with 12 values
+    elif kind == "two_values":
+        k = np.where(rng.random(n) < 0.7, np.uint32(0x01020304), np.uint32(0xF1F2F3F4)).astype(np.uint32)
+    elif kind == "float_range":
+        k = ((rng.random(n, dtype=np.float32) - np.float32(0.5)) * np.float32(1e5)).astype(np.float32)  # perf_sort_float's keys
+    elif kind == "one_hot_rest_uniform":
+        k = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
+        k[rng.random(n) < 0.3] = np.uint32(0xABABABAB)                 # one hot value in every digit, 70 % uniform
+    else:
+        k = np.full(n, 12345, dtype=np.int32)
+    for desc in (False, True):
+        if kind == "float_range" and desc:
+            continue  # (descending floats take the deterministic kernel: covered elsewhere)
+        assert gpu.radix_sort(k, desc).tobytes() == oracle.radix_sort(k, desc).tobytes(), (kind, desc)
+
+
 @pytest.mark.parametrize("dtype,value_bytes,world,n,desc", [
     ("uint", 0, 2, 300_001, False), ("uint", 0, 8, (1 << 22) + 4321, False), ("int", 0, 3, 1_000_003, True), ("float", 0, 4, 777_777, False),
     ("float", 0, 2, 500_000, True), ("uint", 4, 4, 600_001, False), ("int", 8, 2, 400_003, True), ("float", 4, 3, 250_000, True),
