@@ -132,7 +132,7 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
         // digit_scan names up to two such values; their lanes are ranked by ballot (one atomic per warp instruction and
         // value, by the first of them), which is also the lane order the speculative ranking assumes anyway.
         const unsigned h0 = hot ? __ldg(hot) : kNoHotDigit, h1 = hot ? __ldg(hot + 1) : kNoHotDigit;
-        const bool hot_mode = !DET && h0 != kNoHotDigit;
+        const bool hot_mode = h0 != kNoHotDigit;
         // hot lanes touch no shared memory at all: their counts / positions are kept in two (warp-uniform) registers per
         // sweep -- the count of the hot value is added to the table once per tile, the positions are start-of-run +
         // keys of that value seen so far + lanes below in the ballot
@@ -257,17 +257,28 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
                     if constexpr (DET) {
                         // deterministic by construction: the lanes OR their bit into the mask of their digit; after a warp
                         // barrier the mask holds the complete peer set whatever order the atomics were applied in; the
-                        // highest peer clears it and advances the run's cursor
-                        atomicOr(&mrow[d], 1u << lane);
+                        // highest peer clears it and advances the run's cursor.  (Lanes of a hot digit value take no part:
+                        // their peer set is a ballot and their cursor a register.)
+                        bool cold = true;
+                        unsigned hot_pos = 0;
+                        if constexpr (decltype(hot_tag)::value) {
+                            const bool a = d == h0, b = d == h1;
+                            const unsigned ma = __ballot_sync(0xffffffffu, a), mb = __ballot_sync(0xffffffffu, b);
+                            hot_pos = (a ? run0 : run1) + __popc((a ? ma : mb) & lanemask_lt());
+                            run0 += __popc(ma);
+                            run1 += __popc(mb);
+                            cold = !(a || b);
+                        }
+                        if (cold) atomicOr(&mrow[d], 1u << lane);
                         __syncwarp();
-                        const unsigned m = mrow[d], o = row[d];
+                        const unsigned m = cold ? mrow[d] : 0u, o = cold ? row[d] : 0u;
                         __syncwarp();
-                        if ((m >> lane) == 1u) {
+                        if (cold && (m >> lane) == 1u) {
                             mrow[d] = 0;
                             row[d] = o + __popc(m);
                         }
                         __syncwarp();
-                        pos = o + __popc(m & lanemask_lt());
+                        pos = cold ? o + __popc(m & lanemask_lt()) : hot_pos;
                     } else {
                         // same atomics, same order as count(): start of the run + rank.  (Issuing all atomics of the chunk
                         // before the first store was measured 3 % slower: the LSU queue, not the latency, is the limit.)
@@ -313,12 +324,8 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
                 t_cur = t_next;
             }
         };
-        if constexpr (DET) {
-            work(std::false_type());
-        } else {
-            if (hot_mode) work(std::true_type());
-            else work(std::false_type());
-        }
+        if (hot_mode) work(std::true_type());
+        else work(std::false_type());
         if (tid == 0) WS_PROF_DUMP(0);
     } else {
         // ======================= helpers: digit scan, look-back, bulk stores (one digit value per thread) =======================

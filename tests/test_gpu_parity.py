@@ -500,6 +500,27 @@ def test_hot_digit_values_are_ranked_by_ballot_bit_exact(kind, gpu):
         assert gpu.radix_sort(k, desc).tobytes() == oracle.radix_sort(k, desc).tobytes(), (kind, desc)
 
 
+@pytest.mark.parametrize("value_bytes", [0, 4, 8])
+def test_hot_digit_values_with_the_deterministic_ranking(value_bytes, gpu):
+    """The same for the kernels that rank deterministically: key-value sorts (stability of the payload inside the long
+    runs of equal keys) and descending float keys (non-injective transform), >= 2^23 elements."""
+    n = (1 << 23) + 4099
+    rng = np.random.default_rng(6)
+    if value_bytes:
+        k = rng.integers(0, 700, size=n).astype(np.int32)              # three constant digits
+        k[rng.random(n) < 0.01] = -5                                    # ... with a few stragglers in another value
+        v = np.arange(n * (value_bytes // 4), dtype=np.uint32).reshape(n, value_bytes // 4)
+        for desc in (False, True):
+            gk, gv = gpu.radix_sort(k, desc, v)
+            ek, ev = oracle.radix_sort(k, desc, v)
+            assert gk.tobytes() == ek.tobytes() and gv.tobytes() == ev.tobytes(), (value_bytes, desc)
+    else:
+        k = rng.integers(0, 40, size=n).astype(np.float32)              # a handful of exponents, constant low mantissa bytes
+        k[::97] = -0.0
+        k[1::97] = np.finfo(np.float32).smallest_subnormal             # collides with -0.0 when descending
+        assert gpu.radix_sort(k, True).tobytes() == oracle.radix_sort(k, True).tobytes()
+
+
 @pytest.mark.parametrize("dtype,value_bytes,world,n,desc", [
     ("uint", 0, 2, 300_001, False), ("uint", 0, 8, (1 << 22) + 4321, False), ("int", 0, 3, 1_000_003, True), ("float", 0, 4, 777_777, False),
     ("float", 0, 2, 500_000, True), ("uint", 4, 4, 600_001, False), ("int", 8, 2, 400_003, True), ("float", 4, 3, 250_000, True),
