@@ -632,14 +632,20 @@ def e2e_run(args, cb, L, stream, kind, dt, vb, n, pristine, unit, bpe):
         # staged by the driver
         pageable = None
         try:
-            hp = pristine.cpu().view(torch.uint8).numpy().view(NP[dt]).copy()  # plain malloc'ed memory
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            check(L.bcb_sort_host(stream, code, 0, hp.ctypes.data, n))
-            pe = time.perf_counter() - t0
-            pageable = {"value": (n / 1e9) / pe, "unit": unit, "ms_per_step": pe * 1e3, "steps": 1,
+            src = pristine.cpu().view(torch.uint8).numpy().view(NP[dt])
+            hp = src.copy()  # plain malloc'ed memory
+            pes = []
+            for _ in range(2):  # (the first call also allocates the library's pinned staging slots)
+                np.copyto(hp, src)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                check(L.bcb_sort_host(stream, code, 0, hp.ctypes.data, n))
+                pes.append(time.perf_counter() - t0)
+            pe = min(pes)
+            pageable = {"value": (n / 1e9) / pe, "unit": unit, "ms_per_step": pe * 1e3, "steps": 2, "first_call_ms": pes[0] * 1e3,
+                        "staging": "library: 8 host threads through pinned slots (runtime.cu staged_copy_pageable)",
                         "checked": bool(np.all(hp[:m][:-1] <= hp[:m][1:]))}
-            del hp
+            del hp, src
         except MemoryError:
             pageable = None
         return {"value": (n / 1e9) / (ms / 1e3), "unit": unit, "h2d_bytes_per_step": n * w, "d2h_bytes_per_step": n * w,

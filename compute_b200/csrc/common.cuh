@@ -84,6 +84,13 @@ struct LaunchTimer {
 };
 
 int stream_state(cudaStream_t stream, StreamState **out);
+// Copies between PAGEABLE host memory and the device, staged by the library instead of the driver: several host threads
+// move chunks through their own pinned slots and streams, so the memcpy into / out of pinned memory runs at the speed of
+// several cores and overlaps the DMA (the driver's own staging of a pageable cudaMemcpy is single-threaded: ~14 GB/s
+// against ~50 GB/s of the link).  Blocking; the device range must be ready (the caller has synchronised with whatever
+// produced it).  Returns BCB_EUNSUPPORTED when the range is not pageable or too small to be worth it: the caller then
+// uses cudaMemcpyAsync.
+int staged_copy_pageable(void *device_ptr, void *host_ptr, size_t bytes, bool to_device);
 int scratch_reserve(StreamState *st, size_t bytes, void **out);
 enum { kArenaPacked = 0, kArenaWide = 1, kArenaSegmented = 2, kArenaCount = 3 };
 // Reserve FIRST, then draw the epoch: a (re)allocation zeroes the arena and restarts its epoch counter, so an epoch

@@ -1771,14 +1771,33 @@ int bcb_sort_host(bcb_stream stream, int key_dtype, int descending, void *host_k
     void *dev;
     BCB_CUDA_TRY(cudaMallocAsync(&dev, n * w, st->stream));
     int rc = BCB_SUCCESS;
-    cudaError_t e = cudaMemcpyAsync(dev, host_keys, n * w, cudaMemcpyHostToDevice, st->stream);
-    if (e != cudaSuccess) rc = (int)e;
+    cudaError_t e = cudaSuccess;
+    // a large range in pageable memory (sort(v.begin(), v.end()) on a std::vector) is staged through pinned slots by
+    // several host threads (runtime.cu); anything else is one DMA on the stream
+    bool staged = false;
+    if (n * w >= ((size_t)32 << 20)) {
+        e = cudaStreamSynchronize(st->stream);  // the allocation is ready for the staging streams
+        if (e != cudaSuccess) rc = (int)e;
+        if (rc == BCB_SUCCESS) {
+            const int s = staged_copy_pageable(dev, host_keys, n * w, true);
+            if (s == BCB_SUCCESS) staged = true;
+            else if (s != BCB_EUNSUPPORTED) rc = s;
+        }
+    }
+    if (rc == BCB_SUCCESS && !staged) {
+        e = cudaMemcpyAsync(dev, host_keys, n * w, cudaMemcpyHostToDevice, st->stream);
+        if (e != cudaSuccess) rc = (int)e;
+    }
     if (rc == BCB_SUCCESS) {
         // dispatch_gpu_sort, sort.hpp:34-81
         rc = (n <= 32) ? insertion_sort_impl(st, key_dtype, descending, dev, n, nullptr, 0)
                        : radix_sort_impl(st, key_dtype, !descending, dev, n, nullptr, 0);
     }
-    if (rc == BCB_SUCCESS) {
+    if (rc == BCB_SUCCESS && staged) {
+        e = cudaStreamSynchronize(st->stream);
+        if (e != cudaSuccess) rc = (int)e;
+        if (rc == BCB_SUCCESS) rc = staged_copy_pageable(dev, host_keys, n * w, false);
+    } else if (rc == BCB_SUCCESS) {
         e = cudaMemcpyAsync(host_keys, dev, n * w, cudaMemcpyDeviceToHost, st->stream);
         if (e != cudaSuccess) rc = (int)e;
     }

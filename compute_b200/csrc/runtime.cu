@@ -4,9 +4,12 @@
 #include "common.cuh"
 
 #include <mutex>
+#include <thread>
 #include <unordered_map>
+#include <vector>
 #include <cstring>
 #include <cstdio>
+#include <cstdlib>
 
 namespace bcb {
 
@@ -62,6 +65,111 @@ int stream_state(cudaStream_t stream, StreamState **out)
     }
     g_states.emplace(key, st);
     *out = st;
+    return BCB_SUCCESS;
+}
+
+// ---- staged copies of pageable host ranges ------------------------------------------------------------------
+namespace {
+constexpr size_t kStageChunk = (size_t)8 << 20;       // bytes per pinned slot
+constexpr size_t kStageMinBytes = (size_t)32 << 20;   // below this the driver's own staging is not worth beating
+constexpr int kStageMaxThreads = 8;
+struct StageLane {
+    cudaStream_t stream = nullptr;
+    void *slot[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+};
+struct StagePool {
+    std::mutex mutex;  // one staged copy at a time per process
+    int device = -1;
+    std::vector<StageLane> lanes;
+};
+StagePool g_stage;
+
+int stage_prepare(int device, int threads)
+{
+    if (g_stage.device == device && (int)g_stage.lanes.size() >= threads) return BCB_SUCCESS;
+    for (StageLane &l : g_stage.lanes) {  // (another device, or more lanes wanted: start over)
+        for (int s = 0; s < 2; s++) {
+            if (l.slot[s]) (void)cudaFreeHost(l.slot[s]);
+            if (l.done[s]) (void)cudaEventDestroy(l.done[s]);
+        }
+        if (l.stream) (void)cudaStreamDestroy(l.stream);
+    }
+    g_stage.lanes.clear();
+    g_stage.device = -1;
+    std::vector<StageLane> lanes(threads);
+    cudaError_t e = cudaSuccess;
+    for (StageLane &l : lanes) {
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking);
+        for (int s = 0; s < 2 && e == cudaSuccess; s++) {
+            e = cudaHostAlloc(&l.slot[s], kStageChunk, cudaHostAllocDefault);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&l.done[s], cudaEventDisableTiming);
+        }
+    }
+    g_stage.lanes.swap(lanes);  // (on failure the partial set is released by the next call)
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return (int)e; }
+    g_stage.device = device;
+    return BCB_SUCCESS;
+}
+
+// lane k moves the chunks k, k + T, k + 2T, ...: memcpy and DMA of consecutive chunks overlap through its two slots
+void stage_lane_run(int device, StageLane *lane, int k, int threads, char *dev, char *host, size_t bytes, bool to_device, int *status)
+{
+    cudaError_t e = cudaSetDevice(device);
+    const size_t chunks = (bytes + kStageChunk - 1) / kStageChunk;
+    size_t pending_off[2] = {0, 0}, pending_len[2] = {0, 0};
+    int j = 0;
+    for (size_t c = (size_t)k; c < chunks && e == cudaSuccess; c += (size_t)threads, j++) {
+        const int s = j & 1;
+        const size_t off = c * kStageChunk, len = bytes - off < kStageChunk ? bytes - off : kStageChunk;
+        if (j >= 2) e = cudaEventSynchronize(lane->done[s]);  // the slot's previous transfer has finished
+        if (e != cudaSuccess) break;
+        if (to_device) {
+            std::memcpy(lane->slot[s], host + off, len);
+            e = cudaMemcpyAsync(dev + off, lane->slot[s], len, cudaMemcpyHostToDevice, lane->stream);
+        } else {
+            if (pending_len[s]) std::memcpy(host + pending_off[s], lane->slot[s], pending_len[s]);
+            e = cudaMemcpyAsync(lane->slot[s], dev + off, len, cudaMemcpyDeviceToHost, lane->stream);
+            pending_off[s] = off;
+            pending_len[s] = len;
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(lane->done[s], lane->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(lane->stream);
+    if (e == cudaSuccess && !to_device) {
+        for (int s = 0; s < 2; s++)
+            if (pending_len[s]) std::memcpy(host + pending_off[s], lane->slot[s], pending_len[s]);
+    }
+    if (e != cudaSuccess) (void)cudaGetLastError();
+    *status = (int)e;
+}
+}  // namespace
+
+int staged_copy_pageable(void *device_ptr, void *host_ptr, size_t bytes, bool to_device)
+{
+    if (bytes < kStageMinBytes) return BCB_EUNSUPPORTED;
+    {
+        const char *e = std::getenv("BCB_STAGED_COPY");  // 0: leave pageable ranges to the driver (A/B comparison)
+        if (e && e[0] == '0') return BCB_EUNSUPPORTED;
+    }
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, host_ptr) != cudaSuccess) { (void)cudaGetLastError(); return BCB_EUNSUPPORTED; }
+    if (attr.type != cudaMemoryTypeUnregistered) return BCB_EUNSUPPORTED;  // pinned / registered / managed: plain DMA
+    int device = 0;
+    BCB_CUDA_TRY(cudaGetDevice(&device));
+    unsigned hw = std::thread::hardware_concurrency();
+    int threads = hw >= 4 ? (int)(hw / 2) : 1;
+    if (threads > kStageMaxThreads) threads = kStageMaxThreads;
+    std::lock_guard<std::mutex> lock(g_stage.mutex);
+    BCB_TRY(stage_prepare(device, threads));
+    std::vector<int> status(threads, 0);
+    std::vector<std::thread> pool;
+    for (int k = 1; k < threads; k++)
+        pool.emplace_back(stage_lane_run, device, &g_stage.lanes[k], k, threads, (char *)device_ptr, (char *)host_ptr, bytes, to_device, &status[k]);
+    stage_lane_run(device, &g_stage.lanes[0], 0, threads, (char *)device_ptr, (char *)host_ptr, bytes, to_device, &status[0]);
+    for (std::thread &t : pool) t.join();
+    for (int k = 0; k < threads; k++)
+        if (status[k] != 0) return status[k];
     return BCB_SUCCESS;
 }
 

@@ -500,6 +500,19 @@ def test_hot_digit_values_are_ranked_by_ballot_bit_exact(kind, gpu):
         assert gpu.radix_sort(k, desc).tobytes() == oracle.radix_sort(k, desc).tobytes(), (kind, desc)
 
 
+@pytest.mark.parametrize("dtype,n", [("uint", (1 << 23) + 12345), ("double", (1 << 22) + 99), ("short", (1 << 24) + 7)])
+def test_sort_host_on_a_large_pageable_range(dtype, n, gpu, monkeypatch):
+    """sort(host_first, host_last) on plain malloc'ed memory of >= 32 MB: the library stages the copies itself (several
+    host threads through pinned slots, runtime.cu) -- same bytes as the oracle, also with the staging switched off, and
+    for a range that is not a multiple of the slot size."""
+    k = random_keys(dtype, n, seed=17, mode="bits")
+    exp = oracle.sort(k)
+    assert gpu.sort_host(k).tobytes() == exp.tobytes()
+    assert gpu.sort_host(k, True).tobytes() == oracle.sort(k, True).tobytes()
+    monkeypatch.setenv("BCB_STAGED_COPY", "0")
+    assert gpu.sort_host(k).tobytes() == exp.tobytes()
+
+
 @pytest.mark.parametrize("value_bytes", [0, 4, 8])
 def test_hot_digit_values_with_the_deterministic_ranking(value_bytes, gpu):
     """The same for the kernels that rank deterministically: key-value sorts (stability of the payload inside the long
