@@ -91,6 +91,7 @@ int stream_state(cudaStream_t stream, StreamState **out);
 // produced it).  Returns BCB_EUNSUPPORTED when the range is not pageable or too small to be worth it: the caller then
 // uses cudaMemcpyAsync.
 int staged_copy_pageable(void *device_ptr, void *host_ptr, size_t bytes, bool to_device);
+bool staged_copy_eligible(const void *host_ptr, size_t bytes);
 int scratch_reserve(StreamState *st, size_t bytes, void **out);
 enum { kArenaPacked = 0, kArenaWide = 1, kArenaSegmented = 2, kArenaCount = 3 };
 // Reserve FIRST, then draw the epoch: a (re)allocation zeroes the arena and restarts its epoch counter, so an epoch

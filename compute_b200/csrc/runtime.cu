@@ -145,16 +145,19 @@ void stage_lane_run(int device, StageLane *lane, int k, int threads, char *dev, 
 }
 }  // namespace
 
+bool staged_copy_eligible(const void *host_ptr, size_t bytes)
+{
+    if (bytes < kStageMinBytes) return false;
+    const char *e = std::getenv("BCB_STAGED_COPY");  // 0: leave pageable ranges to the driver (A/B comparison)
+    if (e && e[0] == '0') return false;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, host_ptr) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return attr.type == cudaMemoryTypeUnregistered;  // pinned / registered / managed ranges: plain DMA
+}
+
 int staged_copy_pageable(void *device_ptr, void *host_ptr, size_t bytes, bool to_device)
 {
-    if (bytes < kStageMinBytes) return BCB_EUNSUPPORTED;
-    {
-        const char *e = std::getenv("BCB_STAGED_COPY");  // 0: leave pageable ranges to the driver (A/B comparison)
-        if (e && e[0] == '0') return BCB_EUNSUPPORTED;
-    }
-    cudaPointerAttributes attr;
-    if (cudaPointerGetAttributes(&attr, host_ptr) != cudaSuccess) { (void)cudaGetLastError(); return BCB_EUNSUPPORTED; }
-    if (attr.type != cudaMemoryTypeUnregistered) return BCB_EUNSUPPORTED;  // pinned / registered / managed: plain DMA
+    if (!staged_copy_eligible(host_ptr, bytes)) return BCB_EUNSUPPORTED;
     int device = 0;
     BCB_CUDA_TRY(cudaGetDevice(&device));
     unsigned hw = std::thread::hardware_concurrency();
@@ -525,20 +528,32 @@ int bcb_host_unregister(void *host_ptr)
     return BCB_SUCCESS;
 }
 
+// large pageable host ranges: staged by the library (staged_copy_pageable) once everything enqueued on the stream before
+// the copy has finished -- blocking, as a pageable cudaMemcpyAsync is in effect anyway
+static int copy_host_range(cudaStream_t stream, void *dev, void *host, size_t bytes, bool to_device)
+{
+    if (staged_copy_eligible(host, bytes)) {
+        BCB_CUDA_TRY(cudaStreamSynchronize(stream));
+        const int s = staged_copy_pageable(dev, host, bytes, to_device);
+        if (s != BCB_EUNSUPPORTED) return s;
+    }
+    BCB_CUDA_TRY(to_device ? cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, stream)
+                           : cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, stream));
+    return BCB_SUCCESS;
+}
+
 int bcb_memcpy_h2d(bcb_stream stream, void *dst, const void *src, size_t bytes)
 {
     if (bytes == 0) return BCB_SUCCESS;
     if (!dst || !src) return BCB_EINVAL;
-    BCB_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
-    return BCB_SUCCESS;
+    return copy_host_range((cudaStream_t)stream, dst, const_cast<void *>(src), bytes, true);
 }
 
 int bcb_memcpy_d2h(bcb_stream stream, void *dst, const void *src, size_t bytes)
 {
     if (bytes == 0) return BCB_SUCCESS;
     if (!dst || !src) return BCB_EINVAL;
-    BCB_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-    return BCB_SUCCESS;
+    return copy_host_range((cudaStream_t)stream, const_cast<void *>(src), dst, bytes, false);
 }
 
 int bcb_memcpy_d2d(bcb_stream stream, void *dst, const void *src, size_t bytes)

@@ -85,7 +85,8 @@ BCB_API int bcb_host_free(void *host_ptr);
 BCB_API int bcb_host_register(void *host_ptr, size_t bytes, void **device_ptr);
 BCB_API int bcb_host_unregister(void *host_ptr);
 
-/* enqueue_write_buffer / enqueue_read_buffer / enqueue_copy_buffer (command_queue.hpp:297-675); async on stream */
+/* enqueue_write_buffer / enqueue_read_buffer / enqueue_copy_buffer (command_queue.hpp:297-675); async on stream
+ * (a host range of >= 32 MB in pageable memory is staged by the library, see bcb_sort_host: such a copy blocks) */
 BCB_API int bcb_memcpy_h2d(bcb_stream stream, void *device_dst, const void *host_src, size_t bytes);
 BCB_API int bcb_memcpy_d2h(bcb_stream stream, void *host_dst, const void *device_src, size_t bytes);
 BCB_API int bcb_memcpy_d2d(bcb_stream stream, void *device_dst, const void *device_src, size_t bytes);

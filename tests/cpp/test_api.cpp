@@ -95,6 +95,22 @@ static void test_vector(compute::command_queue &queue)
     CHECK(int(dst[0]) == 5 && int(dst[5]) == 10);
     CHECK((io.begin() + 3).read(queue) == 6);
     CHECK(io.end() - io.begin() == 8);
+    {   // a large std::vector (pageable memory, > 32 MB): the copies are staged by the library; sort in between
+        const size_t n = (size_t(9) << 20) + 12345;
+        std::vector<unsigned> big(n);
+        unsigned x = 12345u;
+        for (size_t i = 0; i < n; i++) { x = x * 1664525u + 1013904223u; big[i] = x; }
+        compute::vector<unsigned> dev(big.begin(), big.end(), queue);
+        std::vector<unsigned> back(n);
+        compute::copy(dev.begin(), dev.end(), back.begin(), queue);
+        queue.finish();
+        CHECK(back == big);
+        compute::sort(dev.begin(), dev.end(), queue);
+        compute::copy(dev.begin(), dev.end(), back.begin(), queue);
+        queue.finish();
+        std::sort(big.begin(), big.end());
+        CHECK(back == big);
+    }
 }
 
 static void test_sort(compute::command_queue &queue)

@@ -57,6 +57,9 @@ def main():
         if vb:
             vals_full = torch.arange(n_total * (vb // 4), device="cuda", dtype=torch.int32).reshape(n_total, vb // 4).contiguous()
         lo, hi = rank * n_total // world, (rank + 1) * n_total // world
+        if n_total == 1 << 22:  # uneven blocks: rank 0 holds NOTHING, the last rank the rest
+            cuts = [0, 0] + [n_total * r // (2 * world) for r in range(2, world)] + [n_total]
+            lo, hi = cuts[rank], cuts[rank + 1]
         shard = full[lo:hi].clone()
         vshard = vals_full[lo:hi].clone() if vb else None
         res = ctx.sort(shard, vshard, descending=desc)

@@ -315,6 +315,10 @@ def _worker(rank, world, port, results):
         blo, bhi = rank * 60_000 // world, (rank + 1) * 60_000 // world
         out["big"] = ctx.sort(torch.from_numpy(big[blo:bhi].copy())).numpy().copy()
         out["stats_big"] = dict(ctx.last_stats)
+        # uneven blocks, rank 0 holds nothing: still the digit exchange
+        ucuts = [0, 0] + [60_000 * r // (2 * world) for r in range(2, world)] + [60_000]
+        out["big_uneven"] = ctx.sort(torch.from_numpy(big[ucuts[rank]:ucuts[rank + 1]].copy())).numpy().copy()
+        out["stats_uneven"] = dict(ctx.last_stats)
         # the plans behind the digit exchange: partition pass into the peers' buffers + local sort (same bytes)
         ctx.use_digit_exchange = False
         out["big_ps"] = ctx.sort(torch.from_numpy(big[blo:bhi].copy())).numpy().copy()
@@ -395,6 +399,8 @@ def test_gloo_ranks_match_single_device_oracle(world):
     assert all(r["empty"] == 0 for r in res)
     assert res[0]["stats1"]["plan"] == "partition"
     assert np.concatenate([r["big_ps"] for r in res]).tobytes() == oracle.radix_sort(big, False).tobytes()
+    assert np.concatenate([r["big_uneven"] for r in res]).tobytes() == oracle.radix_sort(big, False).tobytes()
+    assert all(r["stats_uneven"]["plan"] == "digit-exchange" for r in res)
     assert np.concatenate([r["pairs_k3"] for r in res]).tobytes() == ek.tobytes()
     assert np.concatenate([r["pairs_v3"] for r in res]).tobytes() == ev.tobytes()
     # uniform 32-bit keys: the exchange is the sort's last radix pass; with that plan switched off they are dealt by the
