@@ -38,6 +38,8 @@ from .algorithm import (  # noqa: F401
     sort,
     sort_by_key,
     sort_host,
+    sort_by_field,
+    is_sorted_by_field,
     stable_sort,
     stable_sort_by_key,
 )

@@ -43,6 +43,8 @@ SIGNATURES = {
     "bcb_is_sorted_by_radix_key": ([_vp, _i, _i, _vp, _sz, _pi], _i),
     "bcb_insertion_sort": ([_vp, _i, _i, _vp, _sz, _vp, _sz], _i),
     "bcb_sort_host": ([_vp, _i, _i, _vp, _sz], _i),
+    "bcb_sort_by_field": ([_vp, _vp, _sz, _sz, _sz, _i, _i, _i], _i),
+    "bcb_is_sorted_by_field": ([_vp, _vp, _sz, _sz, _sz, _i, _i, _i, _pi], _i),
     "bcb_partition_points": ([_vp, _i, _i, _vp, _sz, _vp, _sz, _vp], _i),
     "bcb_partition_by_splitters": ([_vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _sz, _vp, _sz, _vp], _i),
     "bcb_radix_top_histogram": ([_vp, _i, _i, _vp, _sz, _vp], _i),

@@ -369,6 +369,33 @@ def sort_by_transform(first: torch.Tensor, function, descending: bool = False, q
     sort_by_key(keys, first, descending, queue)
 
 
+def sort_by_field(records: torch.Tensor, field_offset: int, field_dtype, unary: str = "identity", descending: bool = False,
+                  queue: command_queue | None = None) -> None:
+    """sort / stable_sort / detail::merge_sort_on_gpu with a comparator of the family f(a.field) < f(b.field)
+    (algorithm/sort.hpp:83-106, stable_sort.hpp:34-50, detail/merge_sort_on_gpu.hpp:523-572): ``records`` is a contiguous
+    2-D tensor, one record per row; the scalar field of ``field_dtype`` sits at byte ``field_offset`` of every row;
+    ``unary`` is "identity" or "abs".  Stable, in place."""
+    _range(records, "records")
+    if records.dim() != 2:
+        raise ValueError("sort_by_field needs a 2-D tensor: one record per row")
+    row = records.shape[1] * records.element_size()
+    check(lib().bcb_sort_by_field(_q(queue).handle, records.data_ptr(), records.shape[0], row, int(field_offset), dtype_code(field_dtype),
+                                  UNARY_NAMES.index(unary), int(descending)))
+
+
+def is_sorted_by_field(records: torch.Tensor, field_offset: int, field_dtype, unary: str = "identity", descending: bool = False,
+                       queue: command_queue | None = None) -> bool:
+    """is_sorted(first, last, compare) (is_sorted.hpp:39-68) for the same comparator family; blocks."""
+    _range(records, "records")
+    if records.dim() != 2:
+        raise ValueError("is_sorted_by_field needs a 2-D tensor: one record per row")
+    row = records.shape[1] * records.element_size()
+    out = ctypes.c_int(1)
+    check(lib().bcb_is_sorted_by_field(_q(queue).handle, records.data_ptr(), records.shape[0], row, int(field_offset),
+                                       dtype_code(field_dtype), UNARY_NAMES.index(unary), int(descending), ctypes.byref(out)))
+    return bool(out.value)
+
+
 SET_OPS = ("union", "intersection", "difference", "symmetric_difference")
 
 
@@ -447,7 +474,7 @@ def minmax_element(first: torch.Tensor, queue: command_queue | None = None):
 
 
 __all__ = [
-    "radix_sort", "radix_sort_by_key", "insertion_sort", "sort", "sort_host", "sort_by_key", "stable_sort",
+    "radix_sort", "radix_sort_by_key", "insertion_sort", "sort", "sort_host", "sort_by_field", "is_sorted_by_field", "sort_by_key", "stable_sort",
     "stable_sort_by_key", "is_sorted", "exclusive_scan", "inclusive_scan", "partial_sum", "reduce", "accumulate",
     "predicate", "transform_if", "copy_if", "count_if", "count", "transform_reduce", "inner_product", "reduce_by_key",
     "transform", "equal", "is_permutation", "sort_by_transform", "set_union", "set_intersection", "set_difference",

@@ -7,6 +7,7 @@
 #include <boost/compute/detail/default_queue.hpp>
 #include <boost/compute/detail/dtype.hpp>
 #include <boost/compute/functional/operator.hpp>
+#include <boost/compute/functional/field.hpp>
 #include <boost/compute/iterator/buffer_iterator.hpp>
 
 namespace boost {
@@ -42,6 +43,19 @@ template<class T>
 inline bool is_sorted(buffer_iterator<T> first, buffer_iterator<T> last, greater<T>, command_queue &queue = system::default_queue())
 {
     return detail::is_sorted_impl(first, last, true, queue);
+}
+
+// with a field comparator (functional/field.hpp): no adjacent pair with compare(x[i+1], x[i])
+template<class T, class Compare>
+inline typename std::enable_if<is_field_compare<Compare>::value, bool>::type
+is_sorted(buffer_iterator<T> first, buffer_iterator<T> last, Compare compare, command_queue &queue = system::default_queue())
+{
+    const field_spec f = compare.template resolve<T>();
+    int result = 1;
+    queue.make_current();
+    detail::check(bcb_is_sorted_by_field(queue.get(), first.device_ptr(), detail::iterator_range_size(first, last), sizeof(T), f.offset, f.dtype,
+                                 f.unary, f.descending ? 1 : 0, &result));
+    return result != 0;
 }
 
 } // namespace compute

@@ -3,8 +3,9 @@
 //                                                          otherwise radix sort (ascending / descending)
 //   host range (any random-access contiguous range of T):  copied to the device, sorted, copied back -- the
 //                                                          reference maps the range with a mapped_view (:125-148)
-// Custom comparison functions need run-time OpenCL code generation in the reference (merge sort path) and are
-// outside the hot path: they fail to compile with a clear message.
+//   device range, field comparator (functional/field.hpp):  detail::merge_sort_on_gpu (stable)
+// Arbitrary comparison functions need run-time OpenCL code generation in the reference: they fail to compile with a
+// clear message.
 #ifndef B200_BOOST_COMPUTE_ALGORITHM_SORT_HPP
 #define B200_BOOST_COMPUTE_ALGORITHM_SORT_HPP
 
@@ -12,6 +13,7 @@
 #include <type_traits>
 
 #include <boost/compute/algorithm/detail/insertion_sort.hpp>
+#include <boost/compute/algorithm/detail/merge_sort_on_gpu.hpp>
 #include <boost/compute/algorithm/detail/radix_sort.hpp>
 #include <boost/compute/detail/default_queue.hpp>
 #include <boost/compute/functional/operator.hpp>
@@ -48,11 +50,22 @@ inline void dispatch_gpu_sort(buffer_iterator<T> first, buffer_iterator<T> last,
     }
 }
 
+// custom comparators (sort.hpp:83-106 of the reference: merge_sort_on_gpu): the field-comparator family of
+// functional/field.hpp, as a stable key-value radix sort with the records as payload
 template<class T, class Compare>
-inline void dispatch_gpu_sort(buffer_iterator<T>, buffer_iterator<T>, Compare, command_queue &)
+inline typename std::enable_if<is_field_compare<Compare>::value>::type
+dispatch_gpu_sort(buffer_iterator<T> first, buffer_iterator<T> last, Compare compare, command_queue &queue)
 {
-    static_assert(sizeof(T) == 0, "sort(): only less<T> and greater<T> are supported (custom comparators need the "
-                                  "reference's run-time OpenCL code generation and are outside this path)");
+    merge_sort_on_gpu(first, last, compare, queue);
+}
+
+template<class T, class Compare>
+inline typename std::enable_if<!is_field_compare<Compare>::value>::type
+dispatch_gpu_sort(buffer_iterator<T>, buffer_iterator<T>, Compare, command_queue &)
+{
+    static_assert(sizeof(T) == 0, "sort(): less<T>, greater<T> and the field comparators of functional/field.hpp (less_by, "
+                                  "less_by_component, get<N>(_1) < get<N>(_2), abs(_1) < abs(_2)) are supported; an arbitrary "
+                                  "comparison function needs the reference's run-time OpenCL code generation");
 }
 
 // device iterators

@@ -5,6 +5,7 @@
 
 #include <iterator>
 
+#include <boost/compute/algorithm/detail/merge_sort_on_gpu.hpp>
 #include <boost/compute/algorithm/detail/radix_sort.hpp>
 #include <boost/compute/detail/default_queue.hpp>
 #include <boost/compute/functional/operator.hpp>
@@ -23,10 +24,18 @@ inline void dispatch_gpu_stable_sort(buffer_iterator<T> first, buffer_iterator<T
 {
     radix_sort(first, last, false, queue);
 }
+// custom comparators (stable_sort.hpp:34-50 of the reference: merge_sort_on_gpu with stable = true)
 template<class T, class Compare>
-inline void dispatch_gpu_stable_sort(buffer_iterator<T>, buffer_iterator<T>, Compare, command_queue &)
+inline typename std::enable_if<is_field_compare<Compare>::value>::type
+dispatch_gpu_stable_sort(buffer_iterator<T> first, buffer_iterator<T> last, Compare compare, command_queue &queue)
 {
-    static_assert(sizeof(T) == 0, "stable_sort(): only less<T> and greater<T> are supported on this path");
+    merge_sort_on_gpu(first, last, compare, true, queue);
+}
+template<class T, class Compare>
+inline typename std::enable_if<!is_field_compare<Compare>::value>::type
+dispatch_gpu_stable_sort(buffer_iterator<T>, buffer_iterator<T>, Compare, command_queue &)
+{
+    static_assert(sizeof(T) == 0, "stable_sort(): less<T>, greater<T> and the field comparators of functional/field.hpp are supported");
 }
 
 } // namespace detail

@@ -10,6 +10,9 @@
 
 #include <compute_b200.h>
 
+#include <boost/compute/exception/opencl_error.hpp>
+#include <boost/compute/functional/field.hpp>
+
 namespace boost {
 namespace compute {
 namespace lambda {
@@ -71,9 +74,43 @@ BOOST_COMPUTE_B200_CMP(>=, BCB_CMP_GE)
 
 static const placeholder1 _1 = placeholder1();
 
+// binary comparator expressions of the field-comparator family (functional/field.hpp):  f(_1) < f(_2),  f(_1) > f(_2)  with
+// f = get<N>, abs, or both sides plain (lambda/get.hpp, lambda/functional.hpp of the reference)
+struct placeholder2
+{
+};
+static const placeholder2 _2 = placeholder2();
+
+template<int Arg> struct projected  // get<N>(abs(_Arg)) pieces collected so far
+{
+    int index;
+    int unary;
+};
+template<int N> inline projected<1> get(placeholder1) { projected<1> p = { N, BCB_UN_IDENTITY }; return p; }
+template<int N> inline projected<2> get(placeholder2) { projected<2> p = { N, BCB_UN_IDENTITY }; return p; }
+inline projected<1> abs(placeholder1) { projected<1> p = { 0, BCB_UN_ABS }; return p; }
+inline projected<2> abs(placeholder2) { projected<2> p = { 0, BCB_UN_ABS }; return p; }
+template<int Arg> inline projected<Arg> abs(projected<Arg> p) { p.unary = BCB_UN_ABS; return p; }
+
+namespace detail {
+inline component_compare projected_compare(int i1, int u1, int i2, int u2, bool descending)
+{
+    if(i1 != i2 || u1 != u2){
+        throw opencl_error(BCB_EUNSUPPORTED);  // both sides must look at the same field through the same function
+    }
+    component_compare c = { i1, u1, descending };
+    return c;
+}
+} // namespace detail
+inline component_compare operator<(projected<1> a, projected<2> b) { return detail::projected_compare(a.index, a.unary, b.index, b.unary, false); }
+inline component_compare operator>(projected<1> a, projected<2> b) { return detail::projected_compare(a.index, a.unary, b.index, b.unary, true); }
+inline component_compare operator<(placeholder1, placeholder2) { component_compare c = { 0, BCB_UN_IDENTITY, false }; return c; }
+inline component_compare operator>(placeholder1, placeholder2) { component_compare c = { 0, BCB_UN_IDENTITY, true }; return c; }
+
 } // namespace lambda
 
 using lambda::_1;  // (lambda.hpp: `using lambda::_1`)
+using lambda::_2;
 
 // unary function tags usable with transform_if / transform_reduce (functional/identity.hpp, functional/math.hpp: abs;
 // negate<T> of functional/operator.hpp; `_1 * _1` of the lambda layer -> square)

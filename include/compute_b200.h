@@ -141,6 +141,19 @@ BCB_API int bcb_insertion_sort(bcb_stream stream, int key_dtype, int greater, vo
  * single-threaded path: 2^30 uint32 keys 255 ms against 690 ms (pinned memory: 171 ms).  BCB_STAGED_COPY=0 disables. */
 BCB_API int bcb_sort_host(bcb_stream stream, int key_dtype, int descending, void *host_keys, size_t n);
 
+/* sort() / stable_sort() / detail::merge_sort_on_gpu with a custom comparator (algorithm/sort.hpp:83-106,
+ * stable_sort.hpp:34-50, detail/merge_sort_on_gpu.hpp:523-572).  The reference compiles an arbitrary compare(a, b) at run
+ * time; ahead of time the family  f(a.field) < f(b.field)  ("> " with descending != 0) is provided, which covers every
+ * comparator of the reference's own tests: records of record_bytes bytes each, a scalar field of field_dtype at
+ * field_offset, f = BCB_UN_IDENTITY or BCB_UN_ABS (abs of a signed integer compares as unsigned, like OpenCL's abs).
+ * Implemented as a STABLE key-value radix sort (project the field, sort the keys with the records as payload), in place.
+ * Float fields order by the radix key (-0.0 before +0.0), as stable_sort(less<float>) does in the reference.
+ * bcb_is_sorted_by_field is is_sorted(first, last, compare) for the same comparators (native compare; blocks). */
+BCB_API int bcb_sort_by_field(bcb_stream stream, void *records, size_t n, size_t record_bytes, size_t field_offset,
+                              int field_dtype, int unary, int descending);
+BCB_API int bcb_is_sorted_by_field(bcb_stream stream, const void *records, size_t n, size_t record_bytes, size_t field_offset,
+                                   int field_dtype, int unary, int descending, int *result_host);
+
 /* Partition points of an already sorted range against splitters given in the transformed key space of
  * radix_sort.hpp:100-127 (uint64, non-decreasing): points_host[j] = first index whose transformed key is
  * >= splitters_host[j].  Used by the multi-GPU sample sort to cut a sorted shard into per-destination slices

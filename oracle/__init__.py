@@ -390,6 +390,48 @@ def sort_by_transform(x: np.ndarray, function: str, descending: bool = False) ->
     return sort_by_key(apply_unary(x, function), x.copy(), descending)[1]
 
 
+# ---- sorts with a custom comparator: the comparator family f(a.field) < f(b.field) ----
+def project_field(records: np.ndarray, offset: int, dtype: str, unary: str = "identity") -> np.ndarray:
+    """The value a comparator of the family looks at: the scalar field of type `dtype` at byte `offset` of every record
+    (records: uint8[n, record_bytes]), through `unary` (identity or abs).  abs of a signed integer is UNSIGNED, as
+    OpenCL's abs() is (the reference's abs_sort comparator, test_merge_sort_gpu.cpp:239-242, compares those)."""
+    npdt = np.dtype(NP_DTYPES[dtype])
+    rec = np.ascontiguousarray(records).view(np.uint8).reshape(records.shape[0], -1)
+    f = np.ascontiguousarray(rec[:, offset:offset + npdt.itemsize]).view(npdt).reshape(-1)
+    if unary == "identity":
+        return f
+    if unary != "abs":
+        raise ValueError(unary)
+    if npdt.kind == "i":
+        u = np.dtype("u%d" % npdt.itemsize)
+        return np.where(f < 0, (0 - f.astype(u)).astype(u), f.astype(u)).astype(u)
+    if npdt.kind == "f":
+        return np.where(f < 0, -f, f).astype(npdt)
+    return f
+
+
+def sort_by_field(records: np.ndarray, offset: int, dtype: str, unary: str = "identity", descending: bool = False) -> np.ndarray:
+    """stable_sort(first, last, compare) with compare(a, b) = f(a.field) < f(b.field) (">" when descending):
+    stable_sort.hpp:34-50 -> detail/merge_sort_on_gpu.hpp:523-572 with stable = true, restated as the definition of a
+    stable sort by that comparator (native compare of the projected values; equal elements keep their input order).
+    sort() with the same comparator (sort.hpp:83-106) may return any order of equal elements; this is one of them."""
+    key = project_field(records, offset, dtype, unary)
+    n = key.shape[0]
+    if descending:  # stable for ">": descending keys, ties in input order
+        order = (n - 1 - np.argsort(key[::-1], kind="stable"))[::-1]
+    else:
+        order = np.argsort(key, kind="stable")
+    return np.ascontiguousarray(np.ascontiguousarray(records)[order])
+
+
+def is_sorted_by_field(records: np.ndarray, offset: int, dtype: str, unary: str = "identity", descending: bool = False) -> bool:
+    """is_sorted(first, last, compare) (is_sorted.hpp:39-68): no adjacent pair with compare(x[i+1], x[i])."""
+    key = project_field(records, offset, dtype, unary)
+    if key.shape[0] < 2:
+        return True
+    return not bool(np.any(key[1:] > key[:-1])) if descending else not bool(np.any(key[1:] < key[:-1]))
+
+
 # ---- second batch of callers: set operations on sorted ranges, extrema (SURVEY.md section 8f, ranks 2-3) ----
 def set_operation(which: str, a: np.ndarray, b: np.ndarray) -> np.ndarray:
     """std::set_union / set_intersection / set_difference / set_symmetric_difference restated as the two-pointer merge

@@ -543,6 +543,117 @@ static void test_sort_callers(compute::command_queue &queue)
 }
 
 // second batch of callers: set operations on sorted ranges, extrema, valarray reductions
+// sorts with a custom comparator: the reference's own cases with the comparator spelt as a field comparator
+struct Particle
+{
+    Particle() : x(0.f), y(0.f) {}
+    Particle(float _x, float _y) : x(_x), y(_y) {}
+    float x;
+    float y;
+};
+
+static void test_comparator_sorts(compute::command_queue &queue)
+{
+    using compute::int2_;
+    namespace lambda = compute::lambda;
+    const compute::context &context = compute::system::default_context();
+    {   // test_stable_sort.cpp:41-90: int2_ by the first, then by the second component
+        compute::vector<int2_> vec(context);
+        vec.push_back(int2_(2, 1), queue);
+        vec.push_back(int2_(2, 2), queue);
+        vec.push_back(int2_(1, 2), queue);
+        vec.push_back(int2_(1, 1), queue);
+        CHECK(compute::is_sorted(vec.begin(), vec.end(), compute::less_by_component<0>(), queue) == false);
+        compute::stable_sort(vec.begin(), vec.end(), compute::less_by_component<0>(), queue);
+        CHECK(compute::is_sorted(vec.begin(), vec.end(), compute::less_by_component<0>(), queue) == true);
+        std::vector<int2_> result(vec.size());
+        compute::copy(vec.begin(), vec.end(), result.begin(), queue);
+        queue.finish();
+        CHECK(result[0] == int2_(1, 2) && result[1] == int2_(1, 1) && result[2] == int2_(2, 1) && result[3] == int2_(2, 2));
+        compute::stable_sort(vec.begin(), vec.end(), lambda::get<1>(lambda::_1) < lambda::get<1>(lambda::_2), queue);  // a.y < b.y
+        compute::copy(vec.begin(), vec.end(), result.begin(), queue);
+        queue.finish();
+        CHECK(result[0] == int2_(1, 1) && result[1] == int2_(2, 1) && result[2] == int2_(1, 2) && result[3] == int2_(2, 2));
+    }
+    {   // test_merge_sort_gpu.cpp:330-378: stable merge sort of int2_ by .x
+        int2_ data[] = { int2_(8, 3), int2_(5, 1), int2_(2, 1), int2_(6, 1), int2_(8, 1), int2_(7, 1), int2_(4, 1), int2_(8, 2) };
+        compute::vector<int2_> vector(data, data + 8, queue);
+        CHECK(!compute::is_sorted(vector.begin(), vector.end(), compute::less_by(&int2_::x), queue));
+        compute::detail::merge_sort_on_gpu(vector.begin(), vector.end(), compute::less_by(&int2_::x), true /*stable*/, queue);
+        CHECK(compute::is_sorted(vector.begin(), vector.end(), compute::less_by(&int2_::x), queue));
+        const int2_ expected[] = { int2_(2, 1), int2_(4, 1), int2_(5, 1), int2_(6, 1), int2_(7, 1), int2_(8, 3), int2_(8, 1), int2_(8, 2) };
+        std::vector<int2_> h(8);
+        compute::copy(vector.begin(), vector.end(), h.begin(), queue);
+        queue.finish();
+        CHECK(std::equal(h.begin(), h.end(), expected));
+    }
+    {   // test_sort.cpp:294-326: a struct by its x member
+        std::vector<Particle> particles;
+        particles.push_back(Particle(0.1f, 0.f));
+        particles.push_back(Particle(-0.4f, 0.f));
+        particles.push_back(Particle(10.0f, 0.f));
+        particles.push_back(Particle(0.001f, 0.f));
+        compute::vector<Particle> vector(4, context);
+        compute::copy(particles.begin(), particles.end(), vector.begin(), queue);
+        CHECK(compute::is_sorted(vector.begin(), vector.end(), compute::less_by(&Particle::x), queue) == false);
+        compute::sort(vector.begin(), vector.end(), compute::less_by(&Particle::x), queue);
+        CHECK(compute::is_sorted(vector.begin(), vector.end(), compute::less_by(&Particle::x), queue) == true);
+        compute::copy(vector.begin(), vector.end(), particles.begin(), queue);
+        queue.finish();
+        CHECK(particles[0].x == -0.4f && particles[1].x == 0.001f && particles[2].x == 0.1f && particles[3].x == 10.0f);
+        compute::sort(vector.begin(), vector.end(), compute::greater_by(&Particle::x), queue);
+        compute::copy(vector.begin(), vector.end(), particles.begin(), queue);
+        queue.finish();
+        CHECK(particles[0].x == 10.0f && particles[3].x == -0.4f);
+    }
+    {   // test_sort.cpp:328-360: 100 int2_ by .x, only the ends are pinned
+        const size_t size = 100;
+        std::vector<int2_> host(size, int2_(0, 0));
+        host[0] = int2_(100, 0);
+        host[size / 4] = int2_(20, 0);
+        host[(size * 3) / 4] = int2_(9, 0);
+        host[size - 3] = int2_(-10, 0);
+        host[size / 2 + 1] = int2_(-10, -1);
+        compute::vector<int2_> vector(size, context);
+        compute::copy(host.begin(), host.end(), vector.begin(), queue);
+        CHECK(compute::is_sorted(vector.begin(), vector.end(), compute::less_by_component<0>(), queue) == false);
+        compute::sort(vector.begin(), vector.end(), compute::less_by_component<0>(), queue);
+        CHECK(compute::is_sorted(vector.begin(), vector.end(), compute::less_by_component<0>(), queue) == true);
+        compute::copy(vector.begin(), vector.end(), host.begin(), queue);
+        queue.finish();
+        CHECK(host[0][0] == -10 && host[1][0] == -10 && host[size - 3][0] == 9 && host[size - 2][0] == 20 && host[size - 1][0] == 100);
+        CHECK(host[0] != host[1]);
+    }
+    {   // test_merge_sort_gpu.cpp:223-256: 1024 ints by abs()
+        const int size = 1024;
+        std::vector<int> data(size);
+        for(int i = 0; i < size; i++) data[i] = i % 2 ? size - i : i - size;
+        compute::vector<int> vector(data.begin(), data.end(), queue);
+        CHECK(!compute::is_sorted(vector.begin(), vector.end(), lambda::abs(lambda::_1) < lambda::abs(lambda::_2), queue));
+        compute::detail::merge_sort_on_gpu(vector.begin(), vector.end(), lambda::abs(lambda::_1) < lambda::abs(lambda::_2), queue);
+        CHECK(compute::is_sorted(vector.begin(), vector.end(), compute::less_abs<int>(), queue));
+        std::vector<int> h = to_host(vector, queue);
+        std::stable_sort(data.begin(), data.end(), [](int a, int b) { return std::abs(a) < std::abs(b); });
+        CHECK(h == data);
+        // less / greater go to the radix sort (test_merge_sort_gpu.cpp:65-100)
+        compute::detail::merge_sort_on_gpu(vector.begin(), vector.end(), compute::greater<int>(), queue);
+        CHECK(compute::is_sorted(vector.begin(), vector.end(), compute::greater<int>(), queue));
+    }
+    {   // long8_ by one component (test_merge_sort_gpu.cpp:294-328 compares a.s0 < b.s3, not an ordering; by s0 here)
+        using compute::long8_;
+        std::vector<long8_> data(256);
+        for(long i = 0; i < 256; i++) data[i] = i % 2 ? long8_(i) : long8_(i * i);
+        compute::vector<long8_> vector(data.begin(), data.end(), queue);
+        compute::detail::merge_sort_on_gpu(vector.begin(), vector.end(), compute::less_by(&long8_::s0), queue);
+        CHECK(compute::is_sorted(vector.begin(), vector.end(), compute::less_by(&long8_::s0), queue));
+        std::vector<long8_> h(256);
+        compute::copy(vector.begin(), vector.end(), h.begin(), queue);
+        queue.finish();
+        std::stable_sort(data.begin(), data.end(), [](const long8_ &a, const long8_ &b) { return a.s0 < b.s0; });
+        CHECK(std::equal(h.begin(), h.end(), data.begin()));
+    }
+}
+
 static void test_set_operations_and_extrema(compute::command_queue &queue)
 {
     compute::context context = queue.get_context();
@@ -631,6 +742,7 @@ int main()
         test_array_and_mapped_view(queue);
         test_scan_and_reduce_callers(queue);
         test_sort_callers(queue);
+        test_comparator_sorts(queue);
         test_set_operations_and_extrema(queue);
         queue.finish();
     } catch(std::exception &e) {

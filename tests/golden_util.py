@@ -196,6 +196,31 @@ def check_case(c, api):
         x = _expand_input(c)
         np.testing.assert_array_equal(api.sort_by_transform(x, c["function"], desc), np.array(c["expected"], dtype=x.dtype), err_msg=c["ref"])
         return
+    if fn == "sort_by_field":
+        dt = NP[c["dtype"]]
+        if "records" in c:
+            rec = np.array(c["records"], dtype=dt)
+        else:
+            g = c["records_gen"]
+            if g["kind"] == "sparse_rows":  # zeros with a few rows set (test_sort.cpp:338-344)
+                rec = np.zeros((g["n"], g["width"]), dtype=dt)
+                for i, row in g["rows"].items():
+                    rec[int(i)] = row
+            else:                           # data[i] = i odd ? size - i : i - size (test_merge_sort_gpu.cpp:232-237)
+                i = np.arange(g["n"])
+                rec = np.where(i % 2 == 1, g["n"] - i, i - g["n"]).astype(dt).reshape(-1, 1)
+        w = np.dtype(dt).itemsize
+        got = api.sort_by_field(rec, c["field"] * w, c["dtype"], c["unary"], desc)
+        assert got.dtype == rec.dtype and got.shape == rec.shape
+        assert api.is_sorted_by_field(got, c["field"] * w, c["dtype"], c["unary"], desc), c["ref"]
+        if "expected" in c:
+            np.testing.assert_array_equal(got, np.array(c["expected"], dtype=dt), err_msg=c["ref"])
+        elif "expected_ends" in c:
+            for i, row in c["expected_ends"].items():
+                np.testing.assert_array_equal(got[int(i)], np.array(row, dtype=dt), err_msg=c["ref"])
+        # always a permutation of the input rows
+        np.testing.assert_array_equal(np.sort(got.view(np.uint8).reshape(got.shape[0], -1), axis=0), np.sort(rec.view(np.uint8).reshape(rec.shape[0], -1), axis=0))
+        return
     if fn.startswith("set_"):
         x = _expand_input(c)
         got = api.set_operation(fn[4:], x, np.array(c["input2"], dtype=x.dtype))

@@ -200,6 +200,20 @@ def sort_by_transform(x, function, descending=False):
     return to_host(d, x.dtype)
 
 
+def sort_by_field(records, offset, dtype, unary="identity", descending=False):
+    rec = np.ascontiguousarray(records)
+    d = to_dev(rec.view(np.uint8).reshape(rec.shape[0], -1))
+    cb.sort_by_field(d, offset, dtype, unary, descending)
+    torch.cuda.synchronize()
+    return d.cpu().numpy().view(rec.dtype).reshape(rec.shape)
+
+
+def is_sorted_by_field(records, offset, dtype, unary="identity", descending=False):
+    rec = np.ascontiguousarray(records)
+    d = to_dev(rec.view(np.uint8).reshape(rec.shape[0], -1))
+    return cb.is_sorted_by_field(d, offset, dtype, unary, descending)
+
+
 def set_operation(which, a, b):
     a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
     d_out = to_dev(np.full((a.size + b.size + 3) * a.dtype.itemsize, 0x5A, dtype=np.uint8).view(a.dtype))

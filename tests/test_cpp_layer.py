@@ -48,7 +48,7 @@ def test_custom_comparator_is_a_compile_error(tmp_path):
         "struct my_less { bool operator()(int a, int b) const { return a < b; } };\n"
         "int main() { boost::compute::vector<int> v(100); boost::compute::sort(v.begin(), v.end(), my_less()); }\n")
     r = _compile(str(src), str(tmp_path / "bad"))
-    assert r.returncode != 0 and "only less<T> and greater<T>" in r.stderr
+    assert r.returncode != 0 and "an arbitrary comparison function needs the reference's run-time OpenCL code generation" in r.stderr
 
 
 @pytest.mark.gpu

@@ -500,6 +500,33 @@ def test_hot_digit_values_are_ranked_by_ballot_bit_exact(kind, gpu):
         assert gpu.radix_sort(k, desc).tobytes() == oracle.radix_sort(k, desc).tobytes(), (kind, desc)
 
 
+@pytest.mark.parametrize("record_bytes,offset,dtype,unary,n", [
+    (8, 0, "int", "identity", 100_003), (8, 4, "int", "identity", 50_000), (8, 0, "int", "abs", 70_001), (16, 4, "float", "identity", 33_333),
+    (12, 8, "uint", "identity", 20_011), (5, 1, "char", "abs", 9_999), (24, 8, "long", "abs", 12_345), (6, 2, "ushort", "identity", 40_000),
+    (32, 16, "double", "identity", 25_000), (8, 0, "int", "identity", 2), (8, 0, "int", "identity", 33), (64, 60, "float", "abs", 4_097)])
+def test_sort_by_field_matches_the_stable_comparator_sort(record_bytes, offset, dtype, unary, n, gpu):
+    """sort / stable_sort / merge_sort_on_gpu with a comparator f(a.field) < f(b.field) (and ">"): records of several sizes
+    (native 8 / 16-byte payloads, odd sizes through the index + gather path, an unaligned field), byte-exact against the
+    stable comparator sort of the oracle; is_sorted with the same comparator before and after."""
+    rng = np.random.default_rng(23)
+    rec = rng.integers(0, 256, size=(n, record_bytes), dtype=np.uint8)
+    npdt = np.dtype(NPD[dtype])
+    if npdt.kind == "f":   # finite, non-zero floats with duplicates (the radix order of +-0 / NaN is not the comparator's)
+        vals = (rng.integers(1, 500, size=n) * rng.choice([-0.5, 0.25, 3.0], size=n)).astype(npdt)
+    else:
+        info = np.iinfo(npdt)
+        vals = rng.integers(max(info.min, -300), min(info.max, 300) + 1, size=n).astype(npdt)   # many ties: stability matters
+        if npdt.kind == "i" and n > 10:
+            vals[3] = info.min                                                                    # abs(INT_MIN) is 2^(w-1), unsigned
+    rec[:, offset:offset + npdt.itemsize] = vals.view(np.uint8).reshape(n, npdt.itemsize)
+    for desc in (False, True):
+        exp = oracle.sort_by_field(rec, offset, dtype, unary, desc)
+        got = gpu.sort_by_field(rec, offset, dtype, unary, desc)
+        assert got.tobytes() == exp.tobytes(), (record_bytes, offset, dtype, unary, desc)
+        assert gpu.is_sorted_by_field(got, offset, dtype, unary, desc)
+        assert gpu.is_sorted_by_field(rec, offset, dtype, unary, desc) == oracle.is_sorted_by_field(rec, offset, dtype, unary, desc)
+
+
 @pytest.mark.parametrize("dtype,n", [("uint", (1 << 23) + 12345), ("double", (1 << 22) + 99), ("short", (1 << 24) + 7)])
 def test_sort_host_on_a_large_pageable_range(dtype, n, gpu, monkeypatch):
     """sort(host_first, host_last) on plain malloc'ed memory of >= 32 MB: the library stages the copies itself (several
