@@ -527,6 +527,51 @@ def test_sort_by_field_matches_the_stable_comparator_sort(record_bytes, offset, 
         assert gpu.is_sorted_by_field(rec, offset, dtype, unary, desc) == oracle.is_sorted_by_field(rec, offset, dtype, unary, desc)
 
 
+def test_exchange_and_field_entry_points_reject_bad_arguments(gpu):
+    """Error behaviour of the round-2 entry points: codes, never an exception or a crash (compute_b200.h conventions)."""
+    import ctypes
+    import torch
+    import compute_b200 as cb
+    from compute_b200.core import dtype_code
+    lib, q = cb.lib(), cb.command_queue()
+    EINVAL, EUNSUPPORTED = 10001, 10002
+    keys = torch.zeros(1024, dtype=torch.int32, device="cuda")
+    buf = torch.zeros(4096, dtype=torch.int32, device="cuda")
+    ptrs = np.full(256, buf.data_ptr(), dtype=np.uint64)
+    first = np.zeros(256, dtype=np.uint64)
+    u32, u16, u64, f64 = dtype_code(np.uint32), dtype_code(np.uint16), dtype_code(np.uint64), dtype_code(np.float64)
+    ok = lib.bcb_radix_exchange_scatter(q.handle, u32, 1, keys.data_ptr(), None, 0, 1024, ptrs.ctypes.data, None, first.ctypes.data)
+    assert ok == 0
+    # 16-bit keys, a 3-byte payload, 64-bit keys with a payload, descending doubles: not covered -> the same answer on every rank
+    assert lib.bcb_radix_exchange_scatter(q.handle, u16, 1, keys.data_ptr(), None, 0, 1024, ptrs.ctypes.data, None, first.ctypes.data) == EUNSUPPORTED
+    assert lib.bcb_radix_exchange_scatter(q.handle, u32, 1, keys.data_ptr(), buf.data_ptr(), 3, 1024, ptrs.ctypes.data, ptrs.ctypes.data, first.ctypes.data) == EUNSUPPORTED
+    assert lib.bcb_radix_exchange_scatter(q.handle, u64, 1, keys.data_ptr(), buf.data_ptr(), 4, 512, ptrs.ctypes.data, ptrs.ctypes.data, first.ctypes.data) == EUNSUPPORTED
+    assert lib.bcb_radix_exchange_scatter(q.handle, f64, 0, keys.data_ptr(), None, 0, 512, ptrs.ctypes.data, None, first.ctypes.data) == EUNSUPPORTED
+    bad = ptrs.copy(); bad[7] += 4   # a destination that is not 16-byte aligned
+    assert lib.bcb_radix_exchange_scatter(q.handle, u32, 1, keys.data_ptr(), None, 0, 1024, bad.ctypes.data, None, first.ctypes.data) == EINVAL
+    assert lib.bcb_radix_exchange_scatter(q.handle, u32, 1, keys.data_ptr() + 4, None, 0, 1000, ptrs.ctypes.data, None, first.ctypes.data) == EINVAL
+    assert lib.bcb_radix_exchange_scatter(q.handle, u32, 1, keys.data_ptr(), None, 0, 1024, None, None, first.ctypes.data) == EINVAL
+    out = torch.zeros(4096, dtype=torch.int32, device="cuda")
+    sb, sl = np.array([0, 512], dtype=np.uint64), np.array([100, 200], dtype=np.uint64)
+    assert lib.bcb_radix_sort_segments(q.handle, u32, 1, buf.data_ptr(), None, 0, out.data_ptr(), None, sb.ctypes.data, sl.ctypes.data, 2) == 0
+    sb2 = np.array([0, 50], dtype=np.uint64)    # overlapping, and not 16-byte aligned
+    assert lib.bcb_radix_sort_segments(q.handle, u32, 1, buf.data_ptr(), None, 0, out.data_ptr(), None, sb2.ctypes.data, sl.ctypes.data, 2) == EINVAL
+    sb3 = np.array([0, 513], dtype=np.uint64)
+    assert lib.bcb_radix_sort_segments(q.handle, u32, 1, buf.data_ptr(), None, 0, out.data_ptr(), None, sb3.ctypes.data, sl.ctypes.data, 2) == EINVAL
+    assert lib.bcb_radix_sort_segments(q.handle, u32, 1, buf.data_ptr(), None, 0, None, None, sb.ctypes.data, sl.ctypes.data, 2) == EINVAL
+    assert lib.bcb_radix_sort_segments(q.handle, u16, 1, buf.data_ptr(), None, 0, out.data_ptr(), None, sb.ctypes.data, sl.ctypes.data, 2) == EUNSUPPORTED
+    assert lib.bcb_radix_sort_segments(q.handle, u32, 1, buf.data_ptr(), None, 0, out.data_ptr(), None, sb.ctypes.data, sl.ctypes.data, 0) == 0  # nothing to do
+    # field sorts: the field must lie inside the record; only identity / abs
+    rec = torch.zeros((100, 8), dtype=torch.uint8, device="cuda")
+    assert lib.bcb_sort_by_field(q.handle, rec.data_ptr(), 100, 8, 6, dtype_code(np.int32), 0, 0) == EINVAL
+    assert lib.bcb_sort_by_field(q.handle, rec.data_ptr(), 100, 8, 0, dtype_code(np.int32), 3, 0) == EUNSUPPORTED   # square
+    assert lib.bcb_sort_by_field(q.handle, rec.data_ptr(), 100, 8, 0, 99, 0, 0) == EINVAL
+    assert lib.bcb_sort_by_field(q.handle, None, 1, 8, 0, dtype_code(np.int32), 0, 0) == 0                           # n < 2: nothing to do
+    res = ctypes.c_int(0)
+    assert lib.bcb_is_sorted_by_field(q.handle, rec.data_ptr(), 100, 8, 4, dtype_code(np.int32), 2, 1, ctypes.byref(res)) == 0 and res.value == 1
+    q.finish()
+
+
 @pytest.mark.parametrize("dtype,n", [("uint", (1 << 23) + 12345), ("double", (1 << 22) + 99), ("short", (1 << 24) + 7)])
 def test_sort_host_on_a_large_pageable_range(dtype, n, gpu, monkeypatch):
     """sort(host_first, host_last) on plain malloc'ed memory of >= 32 MB: the library stages the copies itself (several
