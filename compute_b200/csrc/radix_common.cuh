@@ -152,6 +152,35 @@ __device__ __forceinline__ unsigned pass_digit(K raw, int shift, const Transform
 }
 
 
+// streaming copy of n elements by `nthreads` threads (this one is number `g`), every element through `f`: 128-bit accesses,
+// four independent loads in flight per thread when both arrays are 16-byte aligned -- the constant-digit "pass"
+template <typename T, typename F>
+__device__ __forceinline__ void stream_copy(const T *__restrict__ in, T *__restrict__ out, size_t n, size_t g, size_t nthreads, F f)
+{
+    constexpr int VEC = 16 / (int)sizeof(T);
+    size_t done = 0;
+    if (((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0) {
+        const size_t nvec = n / VEC;
+        for (size_t v = g; v < nvec; v += 4 * nthreads) {
+            uint4 x[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (v + u * nthreads < nvec) x[u] = ld_stream_v4(in + (v + u * nthreads) * VEC);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (v + u * nthreads < nvec) {
+                    T *e = reinterpret_cast<T *>(&x[u]);
+#pragma unroll
+                    for (int k = 0; k < VEC; k++) e[k] = f(e[k]);
+                    st_stream_v4(out + (v + u * nthreads) * VEC, x[u]);
+                }
+            }
+        }
+        done = nvec * VEC;
+    }
+    for (size_t i = done + g; i < n; i += nthreads) out[i] = f(__ldg(in + i));
+}
+
 // warp-specialised bulk-copy pass kernel (radix_pass_ws.cu): large sorts.  Keys only (32- / 64-bit) with the speculative
 // two-sweep ranking; 32-bit keys + 4- / 8-byte payload, or keys only with a non-injective transform, with the
 // deterministic atomic-OR ranking.  Returns BCB_EUNSUPPORTED for shapes it does not cover (arrays not 16-byte aligned).
@@ -162,6 +191,9 @@ int ws_launch_pass(StreamState *st, int key_bytes, const void *kin, void *kout, 
 // hot (device, [2]): digit values of this pass that hold so many keys that same-address shared atomics would serialise
 // (digit_scan finds them); the kernel ranks those by ballot.  kNoHotDigit = none.
 constexpr unsigned kNoHotDigit = 0xffffffffu;
+// hot[1] == kConstDigit: EVERY key has the digit value hot[0] -- the stable pass over such a digit is the identity
+// permutation, and both pass kernels turn into a streaming copy (keys < 2^16 in a 32-bit type: two of the four passes)
+constexpr unsigned kConstDigit = 0xfffffffeu;
 // layout of StreamState::hist (unsigned words): [0, 2048) digit counts, [2048, 4096) digit bases, [4096, 5120) destination
 // table of the exchange pass (512 x u64), [5120, 5136) hot digits
 constexpr int kHistHotOffset = 5120;

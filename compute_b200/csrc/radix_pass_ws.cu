@@ -117,6 +117,21 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
     for (unsigned i = tid; i < (DET ? 3 : 2) * kWsWorkerWarps * ROW; i += kWsThreads) tab[i] = 0;  // (the mask table follows the count tables)
     __syncthreads();
 
+    if (hot && __ldg(hot + 1) == kConstDigit) {
+        // Every key has the same value of this digit (digit_scan found one bin holding all of them): the stable pass is the
+        // identity permutation.  The CTAs stream their tiles from keys_in to keys_out (through the pass's key transform, so
+        // that the sortable form between the passes stays what the neighbouring passes expect); no ranking, no look-back.
+        typedef typename key_traits<K>::U U;
+        if (blockIdx.x == 0 && tid == 0) atomicAdd(ticket, (unsigned long long)num_tiles + gridDim.x);  // (the host's reservation)
+        const size_t g = (size_t)blockIdx.x * kWsThreads + tid, nthreads = (size_t)gridDim.x * kWsThreads;
+        stream_copy(keys_in, keys_out, n, g, nthreads, [&](K raw) -> K {
+            const U srt = (XF == kXfIn || XF == kXfBoth) ? transform_fwd<K>(raw, tf) : (U)raw;
+            return XF == kXfOut ? transform_inv<K>(srt, tf) : (XF == kXfIn ? (K)srt : raw);
+        });
+        if constexpr (VB > 0) stream_copy(vals_in, vals_out, n, g, nthreads, [](V v) { return v; });
+        return;
+    }
+
     if (tid < kWsWorkers) {
         // ======================= workers: counting sweep, scatter sweep =======================
         const unsigned w = tid >> 5, lane = tid & 31u;

@@ -189,6 +189,7 @@ __global__ void __launch_bounds__(kRadixSize) digit_scan(const unsigned *__restr
         const bool is_hot = total != 0 && (round == 0 ? (best >> 8) * 2 >= (unsigned long long)total
                                                       : ((first >> 8) * 2 >= (unsigned long long)total && (best >> 8) * 4 >= (unsigned long long)total));
         if (d == 0) hot[blockIdx.x * 2 + round] = is_hot ? (unsigned)(best & 0xffu) : kNoHotDigit;
+        if (round == 1 && d == 0 && total != 0 && (first >> 8) == (unsigned long long)total) hot[blockIdx.x * 2 + 1] = kConstDigit;
         if (round == 0) {
             first = best;
             if (mine == first) mine = 0;  // the runner-up comes from the others
@@ -569,7 +570,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
 onesweep_pass(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *__restrict__ vals_in_v,
               void *__restrict__ vals_out_v, const unsigned *__restrict__ digit_base, unsigned long long *lookback,
               unsigned epoch, size_t n, size_t num_tiles, int shift, unsigned long long *ticket, unsigned long long ticket_base,
-              const int *__restrict__ gate, const __grid_constant__ Transform tf)
+              const int *__restrict__ gate, const __grid_constant__ Transform tf, const unsigned *__restrict__ hot)
 {
     // Persistent CTAs: the grid is sized to the number of CTAs that fit the device; the tiles in flight form one
     // contiguous window of the input (their scattered writes merge in L2), and the next tile's keys are fetched while
@@ -581,6 +582,16 @@ onesweep_pass(const K *__restrict__ keys_in, K *__restrict__ keys_out, const voi
 
     if (gate && *gate == 0) {  // not needed: keep the ticket counter in step with the host's reservation and leave
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(ticket, (unsigned long long)num_tiles + gridDim.x);
+        return;
+    }
+    if (IDENT != kDigitSplit && hot && __ldg(hot + 1) == kConstDigit) {
+        // every key has the same value of this digit: the stable pass is the identity permutation -- a streaming copy
+        // (keys stay raw in memory between the passes of this kernel, so nothing is transformed)
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(ticket, (unsigned long long)num_tiles + gridDim.x);
+        typedef typename value_type<VB>::type V;
+        const size_t g = (size_t)blockIdx.x * THREADS + threadIdx.x, nthreads = (size_t)gridDim.x * THREADS;
+        stream_copy(keys_in, keys_out, n, g, nthreads, [](K k) { return k; });
+        if constexpr (VB > 0) stream_copy(reinterpret_cast<const V *>(vals_in_v), reinterpret_cast<V *>(vals_out_v), n, g, nthreads, [](V v) { return v; });
         return;
     }
     if (threadIdx.x == 0) slot[0] = draw_tile(ticket, ticket_base, num_tiles);
@@ -657,7 +668,8 @@ struct PassLaunchCache {
 
 template <typename K, int VB, int THREADS, int ITEMS, int LBATCH, int RANK, int IDENT, int MINB = default_min_blocks(THREADS)>
 static int launch_pass_impl(StreamState *st, const void *kin, void *kout, const void *vin, void *vout, const unsigned *base,
-                            unsigned long long *lookback, size_t n, int shift, const Transform &tf, const int *gate = nullptr)
+                            unsigned long long *lookback, size_t n, int shift, const Transform &tf, const int *gate = nullptr,
+                            const unsigned *hot = nullptr)
 {
     typedef PassSmem<K, VB, THREADS, ITEMS, RANK> L;
     static_assert((IDENT == kDigitSplit) == (RANK == kRankBallot), "the splitter pass and the ballot ranking go together");
@@ -680,7 +692,7 @@ static int launch_pass_impl(StreamState *st, const void *kin, void *kout, const 
     // (gated fallback launches of a speculative sort return at once: timed as "other", not as pass kernels)
     LaunchTimer timer(st, gate ? BCB_K_OTHER : (IDENT == kDigitSplit ? BCB_K_EXCHANGE_PASS : BCB_K_ONESWEEP_PASS));
     kernel<<<(unsigned)grid, THREADS, kSmemBytes, st->stream>>>((const K *)kin, (K *)kout, vin, vout, base, lookback, epoch, n, tiles,
-                                                               shift, st->control + kControlTicket, ticket_base, gate, tf);
+                                                               shift, st->control + kControlTicket, ticket_base, gate, tf, hot);
     BCB_CUDA_TRY(cudaGetLastError());
     return BCB_SUCCESS;
 }
@@ -805,21 +817,21 @@ __global__ void __launch_bounds__(256) verify_sorted_kernel(const K *__restrict_
 
 template <typename K, int VB, int THREADS, int ITEMS, int LBATCH = kLookbackBatch, int MINB = default_min_blocks(THREADS)>
 static int launch_pass(StreamState *st, const void *kin, void *kout, const void *vin, void *vout, const unsigned *base,
-                       unsigned long long *lookback, size_t n, int shift, const Transform &tf, const int *gate)
+                       unsigned long long *lookback, size_t n, int shift, const Transform &tf, const int *gate, const unsigned *hot)
 {
     const bool ident = (tf.nm | tf.xc | tf.fa) == 0;  // unsigned ascending keys: the digit is a plain bit field
-    return ident ? launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankAtomicOr, kDigitIdent, MINB>(st, kin, kout, vin, vout, base, lookback, n, shift, tf, gate)
-                 : launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankAtomicOr, kDigitTransform, MINB>(st, kin, kout, vin, vout, base, lookback, n, shift, tf, gate);
+    return ident ? launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankAtomicOr, kDigitIdent, MINB>(st, kin, kout, vin, vout, base, lookback, n, shift, tf, gate, hot)
+                 : launch_pass_impl<K, VB, THREADS, ITEMS, LBATCH, kRankAtomicOr, kDigitTransform, MINB>(st, kin, kout, vin, vout, base, lookback, n, shift, tf, gate, hot);
 }
 
 // the speculative two-sweep pass (keys only, 32- and 64-bit keys)
 template <typename K, int THREADS, int ITEMS, int LBATCH, int MINB>
 static int launch_two_sweep(StreamState *st, const void *kin, void *kout, const unsigned *base, unsigned long long *lookback, size_t n,
-                            int shift, const Transform &tf)
+                            int shift, const Transform &tf, const unsigned *hot)
 {
     const bool ident = (tf.nm | tf.xc | tf.fa) == 0;
-    return ident ? launch_pass_impl<K, 0, THREADS, ITEMS, LBATCH, kRankTwoSweep, kDigitIdent, MINB>(st, kin, kout, nullptr, nullptr, base, lookback, n, shift, tf)
-                 : launch_pass_impl<K, 0, THREADS, ITEMS, LBATCH, kRankTwoSweep, kDigitTransform, MINB>(st, kin, kout, nullptr, nullptr, base, lookback, n, shift, tf);
+    return ident ? launch_pass_impl<K, 0, THREADS, ITEMS, LBATCH, kRankTwoSweep, kDigitIdent, MINB>(st, kin, kout, nullptr, nullptr, base, lookback, n, shift, tf, nullptr, hot)
+                 : launch_pass_impl<K, 0, THREADS, ITEMS, LBATCH, kRankTwoSweep, kDigitTransform, MINB>(st, kin, kout, nullptr, nullptr, base, lookback, n, shift, tf, nullptr, hot);
 }
 
 // tile shapes of the deterministic pass: (key bytes, value bytes) -> THREADS x ITEMS
@@ -871,10 +883,10 @@ static int run_pass(StreamState *st, const void *kin, void *kout, const void *vi
     if constexpr (VB == 0 && (sizeof(K) == 4 || sizeof(K) == 8)) {
         if (pass_kind == kPassTwoSweep)
             return launch_two_sweep<K, SpecConfig<K>::THREADS, SpecConfig<K>::ITEMS, SpecConfig<K>::LB, SpecConfig<K>::MINB>(
-                st, kin, kout, base, lookback, n, shift, tf);
+                st, kin, kout, base, lookback, n, shift, tf, hot);
     }
     return launch_pass<K, VB, PassConfig<K, VB>::THREADS, PassConfig<K, VB>::ITEMS>(st, kin, kout, vin, vout, base, lookback, n,
-                                                                                     shift, tf, gate);
+                                                                                     shift, tf, gate, hot);
 }
 
 // ---- multi-GPU partition pass: bucket histogram by splitters ---------------------------------------------
@@ -1071,7 +1083,7 @@ static int sort_passes(StreamState *st, void *keys, void *values, size_t n, cons
     unsigned *hist = st->hist;
     unsigned *base = st->hist + 8 * kRadixSize;
     unsigned *hot = st->hist + kHistHotOffset;  // [8 passes][2] digit values the warp-specialised pass ranks by ballot
-    const bool ws_kind = (pass_kind == kPassWs || pass_kind == kPassWsDet) && sort_env().hot;
+    const bool ws_kind = sort_env().hot;  // (every pass kernel takes the hint: the r01 kernels use the constant-digit case only)
     BCB_CUDA_TRY(cudaMemsetAsync(hist, 0, NPASS * kRadixSize * sizeof(unsigned), st->stream));
     {
         BCB_TRY((launch_histogram<K>(st, src_keys, n, hist, tf, gate)));

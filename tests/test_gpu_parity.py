@@ -475,12 +475,13 @@ def test_partition_counts_and_scatter_to_separate_buffers(dtype, value_bytes, ns
                 assert not gv[:lo].any() and not gv[lo + sel.size * value_bytes:].any()
 
 
-@pytest.mark.parametrize("kind", ["small_ints", "two_values", "float_range", "one_hot_rest_uniform", "constant"])
+@pytest.mark.parametrize("kind", ["small_ints", "two_values", "float_range", "one_hot_rest_uniform", "constant", "small_u64", "small_u16_in_u32"])
 def test_hot_digit_values_are_ranked_by_ballot_bit_exact(kind, gpu):
     """Keys whose digits are far from uniform (constant high bytes of small integers, the exponent byte of floats, a
     handful of distinct keys): the warp-specialised pass ranks the lanes of the one or two most frequent digit values of
     a pass by ballot instead of same-address shared atomics.  >= 2^23 keys so that kernel runs (tests/conftest.py);
-    byte-exact against the oracle."""
+    A digit value that holds ALL keys turns the pass into a streaming copy (both kernel families); byte-exact against the
+    oracle."""
     n = (1 << 23) + 7777
     rng = np.random.default_rng(5)
     if kind == "small_ints":
@@ -492,6 +493,10 @@ def test_hot_digit_values_are_ranked_by_ballot_bit_exact(kind, gpu):
     elif kind == "one_hot_rest_uniform":
         k = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
         k[rng.random(n) < 0.3] = np.uint32(0xABABABAB)                 # one hot value in every digit, 70 % uniform
+    elif kind == "small_u64":
+        k = rng.integers(0, 70000, size=(1 << 22) + 333).astype(np.uint64)   # five constant digits: streaming copies (r01 kernels)
+    elif kind == "small_u16_in_u32":
+        k = rng.integers(0, 65536, size=n).astype(np.uint32)                   # two constant digits (warp-specialised kernel)
     else:
         k = np.full(n, 12345, dtype=np.int32)
     for desc in (False, True):
@@ -593,7 +598,8 @@ def test_hot_digit_values_with_the_deterministic_ranking(value_bytes, gpu):
     rng = np.random.default_rng(6)
     if value_bytes:
         k = rng.integers(0, 700, size=n).astype(np.int32)              # three constant digits
-        k[rng.random(n) < 0.01] = -5                                    # ... with a few stragglers in another value
+        if value_bytes == 4:
+            k[rng.random(n) < 0.01] = -5                                # ... with a few stragglers in another value (no copy pass)
         v = np.arange(n * (value_bytes // 4), dtype=np.uint32).reshape(n, value_bytes // 4)
         for desc in (False, True):
             gk, gv = gpu.radix_sort(k, desc, v)
