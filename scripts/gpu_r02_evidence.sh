@@ -7,7 +7,7 @@ echo "== launch list (default bench, 2 steps)"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches_bench_sort_u32.csv python bench.py --steps 2 --warmup 1 $B > gpurun_out/launches_sort_u32.log 2>&1; tail -1 gpurun_out/launches_sort_u32.log | cut -c1-200
 echo "== dram traffic per launch"
 for w in sort_u32 scan_i32 reduce_i32; do
-  case $w in sort_u32) k=onesweep_ws; skip=4;; scan_i32) k=scan_tma; skip=1;; reduce_i32) k=reduce_tma; skip=1;; esac
+  case $w in sort_u32) k=onesweep_ws; skip=4;; scan_i32) k=scan_ws; skip=1;; reduce_i32) k=reduce_tma; skip=1;; esac
   timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:$k -s $skip -c 1 --csv --log-file gpurun_out/traffic_$w.csv python bench.py --workload $w --steps 1 --warmup 1 $B > gpurun_out/traffic_$w.log 2>&1
   tail -3 gpurun_out/traffic_$w.csv | cut -c1-60,200-330
 done
