@@ -438,14 +438,24 @@ class Context:
         dist.all_gather_into_tensor(out, t, group=self.group)
         return out.cpu().numpy().view(arr.dtype).reshape((self.world,) + arr.shape)  # one device->host copy
 
-    def _gather_partials(self, local: np.ndarray, has: bool):
-        """One all-gather of (partial value, "shard not empty") -> (partials[world], present[world])."""
-        w = local.dtype.itemsize
-        packed = np.zeros(16, dtype=np.uint8)
-        packed[:w] = local.reshape(-1)[:1].view(np.uint8)
-        packed[8] = 1 if has else 0
-        allp = self._all_gather_np(packed)
-        return allp[:, :w].copy().view(local.dtype).reshape(-1), allp[:, 8].astype(np.int32)
+    def _gather_partials(self, part, np_dt):
+        """One all-gather of (partial value, "shard not empty") -> (partials[world], present[world]).  ``part`` is the
+        1-element DEVICE tensor a local reduction left behind, or None for an empty shard: the record is assembled and
+        gathered on the device, so the call costs ONE device->host synchronisation (the partial never visits the host on
+        its own)."""
+        w = np.dtype(np_dt).itemsize
+        dev = "cuda" if self.ops.device_type == "cuda" else "cpu"
+        packed = torch.zeros(16, dtype=torch.uint8, device=dev)
+        if part is not None:
+            packed[:w] = part.view(torch.uint8).reshape(-1)[:w]
+            packed[8] = 1
+        if self.world == 1:
+            allp = packed.cpu().numpy()[None]
+        else:
+            out = torch.empty(self.world * 16, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(out, packed, group=self.group)
+            allp = out.cpu().numpy().reshape(self.world, 16)                     # the one device->host copy
+        return allp[:, :w].copy().view(np_dt).reshape(-1), allp[:, 8].astype(np.int32)
 
     def _all_to_all(self, src: torch.Tensor, send_counts: np.ndarray, recv_counts: np.ndarray) -> torch.Tensor:
         """variable-size all-to-all of contiguous row slices (bitwise; rows may be wider than one element)."""
@@ -629,9 +639,7 @@ class Context:
             return out
         part = self.ops.reduce_to(x, op, out.dtype) if x.numel() else None
         np_dt = NP_OF_CODE[dtype_code(out.dtype)].type
-        w = np.dtype(np_dt).itemsize
-        local = (part.view(_BITS_VIEW[w]).cpu().numpy().view(np_dt) if part is not None else np.zeros(1, np_dt))
-        partials, present = self._gather_partials(local, bool(x.numel()))
+        partials, present = self._gather_partials(part, np_dt)
         carry = None if not exclusive else np_dt(0 if init is None else init)
         fn = _NP_OPS[op]
         with np.errstate(over="ignore"):
@@ -656,15 +664,8 @@ class Context:
         """Global reduction; every rank returns the same host scalar (None if the global range is empty)."""
         rdt = result_dtype if result_dtype is not None else x.dtype
         np_dt = NP_OF_CODE[dtype_code(rdt)].type
-        w = np.dtype(np_dt).itemsize
-        if x.numel():
-            part = self.ops.reduce_to(x, op, rdt)
-            local = part.view(_BITS_VIEW[w]).cpu().numpy().view(np_dt)
-        else:
-            local = np.zeros(1, np_dt)
-        if self.world == 1:
-            return local[0] if x.numel() else None
-        partials, present = self._gather_partials(local, bool(x.numel()))
+        part = self.ops.reduce_to(x, op, rdt) if x.numel() else None
+        partials, present = self._gather_partials(part, np_dt)
         acc = None
         fn = _NP_OPS[op]
         with np.errstate(over="ignore"):
