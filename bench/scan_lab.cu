@@ -33,7 +33,8 @@ static float run(const T *in, T *out, size_t n, void *desc, int sms, int reps, i
     float best = 1e30f, sum = 0;
     for (int r = 0; r < reps + 2; r++) {
         unsigned epoch = ++g_epoch;
-        void *args[] = {(void *)&in, (void *)&out, (void *)&n, (void *)&exclusive, (void *)&init, (void *)&ts, (void *)&epoch, (void *)&tiles};
+        const T *init_dev = nullptr;
+        void *args[] = {(void *)&in, (void *)&out, (void *)&n, (void *)&exclusive, (void *)&init, (void *)&ts, (void *)&epoch, (void *)&tiles, (void *)&init_dev};
         CK(cudaEventRecord(e0));
         CK(cudaLaunchCooperativeKernel((const void *)kernel, dim3((unsigned)grid), dim3(kSwThreads), args, C::SMEM_BYTES, 0));
         CK(cudaEventRecord(e1));

@@ -56,6 +56,7 @@ SIGNATURES = {
     "bcb_ipc_open": ([_vp, ctypes.POINTER(_vp)], _i),
     "bcb_ipc_close": ([_vp], _i),
     "bcb_scan": ([_vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp], _i),
+    "bcb_scan_with_carry": ([_vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp, _vp, _i], _i),
     "bcb_reduce": ([_vp, _i, _i, _i, _vp, _sz, _vp, _i], _i),
     "bcb_accumulate": ([_vp, _i, _i, _i, _i, _vp, _sz, _vp, _vp], _i),
     "bcb_transform_if": ([_vp, _i, _vp, _sz, _i, _vp, _vp, ctypes.POINTER(_sz)], _i),

@@ -49,6 +49,7 @@ struct StreamState {
     //   [2]   u64 number of speculative sorts that fell back to the deterministic kernel
     //   [3]   u32 blocks-done counter of the one-launch reductions (reset by the last block)
     //   [4]   u64 element counter of count_if
+    //   [5]   carry of a block-distributed scan, folded on the device (bcb_scan_with_carry)
     unsigned long long *control = nullptr;
     unsigned long long ticket_base = 0;
     // decoupled look-back descriptors (scan + sort); zeroed at (re)allocation, validated by epoch tags.  One arena per
@@ -102,7 +103,8 @@ int next_epoch(StreamState *st, int arena, uint32_t *epoch);
 // persistent kernels draw tile ids from the per-stream ticket counter: returns the base of `draws` fresh tickets
 unsigned long long ticket_reserve(StreamState *st, unsigned long long draws);
 
-constexpr int kControlTicket = 0, kControlSpecFlag = 1, kControlSpecFallbacks = 2, kControlReduceDone = 3, kControlCount = 4;
+constexpr int kControlTicket = 0, kControlSpecFlag = 1, kControlSpecFallbacks = 2, kControlReduceDone = 3, kControlCount = 4,
+              kControlCarry = 5 /* carry of a block-distributed scan (bcb_scan_with_carry) */;
 
 // ---- device helpers ------------------------------------------------------------------------
 #ifdef __CUDACC__

@@ -32,8 +32,9 @@ constexpr int kScanTile = kScanThreads * kScanItems;   // 4096
 template <typename T, int OP>
 __global__ void __launch_bounds__(kScanThreads)
 scan_kernel(const T *in, T *out, size_t n, int exclusive, T init, TileState<T> ts, unsigned epoch,
-            unsigned long long *ticket, unsigned long long ticket_base)
+            unsigned long long *ticket, unsigned long long ticket_base, const T *__restrict__ init_dev = nullptr)
 {
+    if (init_dev) init = *init_dev;  // the seed lives on the device (bcb_scan_with_carry)
     typedef Op<OP, T> O;
     constexpr int VEC = 16 / sizeof(T);        // elements per 128-bit vector
     constexpr int NV = kScanItems / VEC;       // vectors per thread
@@ -190,8 +191,10 @@ template <typename T> struct ScanRing {
 // have a whole phase A of slack, and the bulk loads of the next two tiles are in flight all the time.
 template <typename T, int OP>
 __global__ void __launch_bounds__(kRoundThreads)
-scan_tma_kernel(const T *in, T *out, size_t n, int exclusive, T init, TileState<T> ts, unsigned epoch, size_t num_tiles)
+scan_tma_kernel(const T *in, T *out, size_t n, int exclusive, T init, TileState<T> ts, unsigned epoch, size_t num_tiles,
+                const T *__restrict__ init_dev = nullptr)
 {
+    if (init_dev) init = *init_dev;  // the seed lives on the device (bcb_scan_with_carry)
     typedef Op<OP, T> O;
     typedef ScanRing<T> R;
     constexpr int VEC = 16 / sizeof(T);
@@ -414,10 +417,12 @@ __global__ void convert_kernel(const void *in, int in_dtype, A *out, size_t n)
 }
 
 template <typename T, int OP>
-static int launch_scan(StreamState *st, const void *in, void *out, size_t n, int exclusive, const void *init_host)
+static int launch_scan(StreamState *st, const void *in, void *out, size_t n, int exclusive, const void *init_host,
+                       const void *init_dev_v = nullptr)
 {
     T init = (T)0;
     if (init_host) std::memcpy(&init, init_host, sizeof(T));
+    const T *init_dev = (const T *)init_dev_v;  // overrides init when set
     const size_t tiles = (n + kScanTile - 1) / kScanTile;
     if (tiles > 0x7fffffffull) return BCB_ETOOLARGE;
     constexpr int kArena = sizeof(T) <= 4 ? kArenaPacked : kArenaWide;
@@ -461,7 +466,8 @@ static int launch_scan(StreamState *st, const void *in, void *out, size_t n, int
         // guarantees (or it fails loudly) whatever else runs on the device
         const T *in_t = (const T *)in;
         T *out_t = (T *)out;
-        void *args[] = {(void *)&in_t, (void *)&out_t, (void *)&n, (void *)&exclusive, (void *)&init, (void *)&wts, (void *)&epoch, (void *)&wtiles};
+        void *args[] = {(void *)&in_t, (void *)&out_t, (void *)&n, (void *)&exclusive, (void *)&init, (void *)&wts, (void *)&epoch, (void *)&wtiles,
+                        (void *)&init_dev};
         BCB_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)kernel, dim3((unsigned)grid), dim3(kSwThreads), args, C::SMEM_BYTES, st->stream));
         return BCB_SUCCESS;
     }
@@ -489,7 +495,8 @@ static int launch_scan(StreamState *st, const void *in, void *out, size_t n, int
         // fails loudly) whatever else runs on the device.
         const T *in_t = (const T *)in;
         T *out_t = (T *)out;
-        void *args[] = {(void *)&in_t, (void *)&out_t, (void *)&n, (void *)&exclusive, (void *)&init, (void *)&ts, (void *)&epoch, (void *)&rtiles};
+        void *args[] = {(void *)&in_t, (void *)&out_t, (void *)&n, (void *)&exclusive, (void *)&init, (void *)&ts, (void *)&epoch, (void *)&rtiles,
+                        (void *)&init_dev};
         BCB_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)kernel, dim3((unsigned)grid), dim3(kRoundThreads), args, R::kBytes, st->stream));
         return BCB_SUCCESS;
     }
@@ -499,14 +506,65 @@ static int launch_scan(StreamState *st, const void *in, void *out, size_t n, int
     const unsigned long long base = ticket_reserve(st, tiles);
     LaunchTimer timer(st, BCB_K_SCAN);
     scan_kernel<T, OP><<<(unsigned)tiles, kScanThreads, 0, st->stream>>>(
-        (const T *)in, (T *)out, n, exclusive, init, ts, epoch, st->control + kControlTicket, base);
+        (const T *)in, (T *)out, n, exclusive, init, ts, epoch, st->control + kControlTicket, base, init_dev);
     BCB_CUDA_TRY(cudaGetLastError());
     return BCB_SUCCESS;
 }
 
-template <typename T>
-static int dispatch_scan_op(StreamState *st, int op, const void *in, void *out, size_t n, int exclusive, const void *init_host)
+// carry of a block-distributed scan, folded on the device: (init op) partial_0 op ... op partial_(rank-1) in rank order over
+// the records {value at byte 0, "shard not empty" at byte 8} an all-gather left in `records` (16 bytes per rank)
+template <typename T, int OP>
+__global__ void fold_carry_kernel(const unsigned char *__restrict__ records, int rank, T init, int have_init, T *__restrict__ carry)
 {
+    typedef Op<OP, T> O;
+    T acc = have_init ? init : O::identity();
+    for (int r = 0; r < rank; r++) {
+        if (records[r * 16 + 8]) {
+            T v;
+            unsigned char *q = reinterpret_cast<unsigned char *>(&v);
+            for (int b = 0; b < (int)sizeof(T); b++) q[b] = records[r * 16 + b];
+            acc = O::apply(acc, v);
+        }
+    }
+    *carry = acc;
+}
+
+template <typename T, int OP>
+static int launch_scan_with_carry(StreamState *st, const void *in, void *out, size_t n, int exclusive, const void *init_host,
+                                  const void *records_dev, int rank)
+{
+    T init = (T)0;
+    if (init_host) std::memcpy(&init, init_host, sizeof(T));
+    T *carry = reinterpret_cast<T *>(st->control + kControlCarry);
+    fold_carry_kernel<T, OP><<<1, 1, 0, st->stream>>>((const unsigned char *)records_dev, rank, init, exclusive ? 1 : 0, carry);
+    BCB_CUDA_TRY(cudaGetLastError());
+    // exclusive: seeded with init op carry; inclusive: mode 2 = inclusive scan seeded with a carry (the identity when
+    // nothing precedes this rank, which leaves integer results -- and float sums: the identity of plus is -0.0 -- unchanged)
+    return launch_scan<T, OP>(st, in, out, n, exclusive ? 1 : 2, nullptr, carry);
+}
+
+template <typename T>
+static int dispatch_scan_op(StreamState *st, int op, const void *in, void *out, size_t n, int exclusive, const void *init_host,
+                            const void *records_dev = nullptr, int rank = 0)
+{
+    if (records_dev) {
+        switch (op) {
+        case BCB_PLUS: return launch_scan_with_carry<T, BCB_PLUS>(st, in, out, n, exclusive, init_host, records_dev, rank);
+        case BCB_MULTIPLIES: return launch_scan_with_carry<T, BCB_MULTIPLIES>(st, in, out, n, exclusive, init_host, records_dev, rank);
+        case BCB_MIN: return launch_scan_with_carry<T, BCB_MIN>(st, in, out, n, exclusive, init_host, records_dev, rank);
+        case BCB_MAX: return launch_scan_with_carry<T, BCB_MAX>(st, in, out, n, exclusive, init_host, records_dev, rank);
+        default: break;
+        }
+        if constexpr (!is_fp<T>::value) {
+            switch (op) {
+            case BCB_BIT_AND: return launch_scan_with_carry<T, BCB_BIT_AND>(st, in, out, n, exclusive, init_host, records_dev, rank);
+            case BCB_BIT_OR: return launch_scan_with_carry<T, BCB_BIT_OR>(st, in, out, n, exclusive, init_host, records_dev, rank);
+            case BCB_BIT_XOR: return launch_scan_with_carry<T, BCB_BIT_XOR>(st, in, out, n, exclusive, init_host, records_dev, rank);
+            default: break;
+            }
+        }
+        return BCB_EUNSUPPORTED;
+    }
     switch (op) {
     case BCB_PLUS: return launch_scan<T, BCB_PLUS>(st, in, out, n, exclusive, init_host);
     case BCB_MULTIPLIES: return launch_scan<T, BCB_MULTIPLIES>(st, in, out, n, exclusive, init_host);
@@ -529,8 +587,25 @@ static int dispatch_scan_op(StreamState *st, int op, const void *in, void *out, 
 
 using namespace bcb;
 
+static int scan_impl(bcb_stream stream, int in_dtype, int out_dtype, int op, int exclusive, const void *in, void *out, size_t n,
+                     const void *init_host, const void *records_dev, int rank);
+
 extern "C" int bcb_scan(bcb_stream stream, int in_dtype, int out_dtype, int op, int exclusive, const void *in, void *out,
                         size_t n, const void *init_host)
+{
+    return scan_impl(stream, in_dtype, out_dtype, op, exclusive, in, out, n, init_host, nullptr, 0);
+}
+
+extern "C" int bcb_scan_with_carry(bcb_stream stream, int in_dtype, int out_dtype, int op, int exclusive, const void *in, void *out,
+                                   size_t n, const void *init_host, const void *records_dev, int rank)
+{
+    if (!records_dev || rank < 0) return BCB_EINVAL;
+    if (exclusive != 0 && exclusive != 1) return BCB_EINVAL;
+    return scan_impl(stream, in_dtype, out_dtype, op, exclusive, in, out, n, init_host, records_dev, rank);
+}
+
+static int scan_impl(bcb_stream stream, int in_dtype, int out_dtype, int op, int exclusive, const void *in, void *out, size_t n,
+                     const void *init_host, const void *records_dev, int rank)
 {
     if (n == 0) return BCB_SUCCESS;  // scan_on_gpu.hpp:316-318
     if (!in || !out) return BCB_EINVAL;
@@ -558,7 +633,7 @@ extern "C" int bcb_scan(bcb_stream stream, int in_dtype, int out_dtype, int op, 
         src = tmp;
     }
     switch (out_dtype) {
-#define X(DT, T) case DT: return dispatch_scan_op<T>(st, op, src, out, n, exclusive, init_host);
+#define X(DT, T) case DT: return dispatch_scan_op<T>(st, op, src, out, n, exclusive, init_host, records_dev, rank);
         BCB_FOR_EACH_TYPE(X)
 #undef X
     default: return BCB_EINVAL;

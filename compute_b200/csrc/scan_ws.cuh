@@ -90,8 +90,10 @@ template <typename T> struct WsTileState {
 // the identity: wrong results, shows what the chain costs), 2 = bulk copy in / bulk copy out only.
 template <typename T, int OP, int NV, int S, int D, int MODE = 0>
 __global__ void __launch_bounds__(kSwThreads, 1)
-scan_ws_kernel(const T *in, T *out, size_t n, int exclusive, T init, WsTileState<T> ts, unsigned epoch, size_t num_tiles)
+scan_ws_kernel(const T *in, T *out, size_t n, int exclusive, T init, WsTileState<T> ts, unsigned epoch, size_t num_tiles,
+               const T *__restrict__ init_dev = nullptr)
 {
+    if (init_dev) init = *init_dev;  // the seed lives on the device (multi-GPU scan: the carry of the ranks before this one)
     typedef Op<OP, T> O;
     typedef ScanWsShape<T, NV, S> C;
     constexpr int VEC = C::VEC, TILE = C::TILE;

@@ -318,6 +318,14 @@ class CudaLocalOps:
         self._check(self._lib.bcb_scan(self.queue.handle, dtype_code(x.dtype), out_code, op_code(op), mode, x.data_ptr(),
                                        out.data_ptr(), x.numel(), init_arr.ctypes.data))
 
+    def scan_with_carry(self, x, out, exclusive: bool, init, op, records, rank: int) -> None:
+        """This rank's block of a block-distributed scan, seeded on the device with the partials of the ranks before it
+        (``records``: the all-gathered 16-byte records, a device tensor).  Asynchronous."""
+        out_code = dtype_code(out.dtype)
+        init_arr = np.array([0 if init is None else init]).astype(NP_OF_CODE[out_code])
+        self._check(self._lib.bcb_scan_with_carry(self.queue.handle, dtype_code(x.dtype), out_code, op_code(op), int(exclusive),
+                                                  x.data_ptr(), out.data_ptr(), x.numel(), init_arr.ctypes.data, records.data_ptr(), rank))
+
     def empty(self, n, like):
         return torch.empty((n,) + tuple(like.shape[1:]), dtype=like.dtype, device=like.device)
 
@@ -438,23 +446,26 @@ class Context:
         dist.all_gather_into_tensor(out, t, group=self.group)
         return out.cpu().numpy().view(arr.dtype).reshape((self.world,) + arr.shape)  # one device->host copy
 
-    def _gather_partials(self, part, np_dt):
-        """One all-gather of (partial value, "shard not empty") -> (partials[world], present[world]).  ``part`` is the
-        1-element DEVICE tensor a local reduction left behind, or None for an empty shard: the record is assembled and
-        gathered on the device, so the call costs ONE device->host synchronisation (the partial never visits the host on
-        its own)."""
-        w = np.dtype(np_dt).itemsize
+    def _gather_records(self, part, w: int):
+        """All-gather of the 16-byte record {partial at byte 0, "shard not empty" at byte 8} -> device tensor uint8[world * 16]."""
         dev = "cuda" if self.ops.device_type == "cuda" else "cpu"
         packed = torch.zeros(16, dtype=torch.uint8, device=dev)
         if part is not None:
             packed[:w] = part.view(torch.uint8).reshape(-1)[:w]
             packed[8] = 1
         if self.world == 1:
-            allp = packed.cpu().numpy()[None]
-        else:
-            out = torch.empty(self.world * 16, dtype=torch.uint8, device=dev)
-            dist.all_gather_into_tensor(out, packed, group=self.group)
-            allp = out.cpu().numpy().reshape(self.world, 16)                     # the one device->host copy
+            return packed
+        out = torch.empty(self.world * 16, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(out, packed, group=self.group)
+        return out
+
+    def _gather_partials(self, part, np_dt):
+        """One all-gather of (partial value, "shard not empty") -> (partials[world], present[world]).  ``part`` is the
+        1-element DEVICE tensor a local reduction left behind, or None for an empty shard: the record is assembled and
+        gathered on the device, so the call costs ONE device->host synchronisation (the partial never visits the host on
+        its own)."""
+        w = np.dtype(np_dt).itemsize
+        allp = self._gather_records(part, w).cpu().numpy().reshape(self.world, 16)   # the one device->host copy
         return allp[:, :w].copy().view(np_dt).reshape(-1), allp[:, 8].astype(np.int32)
 
     def _all_to_all(self, src: torch.Tensor, send_counts: np.ndarray, recv_counts: np.ndarray) -> torch.Tensor:
@@ -639,6 +650,13 @@ class Context:
             return out
         part = self.ops.reduce_to(x, op, out.dtype) if x.numel() else None
         np_dt = NP_OF_CODE[dtype_code(out.dtype)].type
+        if hasattr(self.ops, "scan_with_carry"):
+            # everything stays on the device: partial -> all-gather -> carry folded in rank order by a one-thread kernel ->
+            # the scan reads its seed from device memory.  No host synchronisation: the call is enqueue-and-return.
+            records = self._gather_records(part, np.dtype(np_dt).itemsize)
+            if x.numel():
+                self.ops.scan_with_carry(x, out, exclusive, init, op, records, self.rank)
+            return out
         partials, present = self._gather_partials(part, np_dt)
         carry = None if not exclusive else np_dt(0 if init is None else init)
         fn = _NP_OPS[op]

@@ -232,6 +232,13 @@ BCB_API int bcb_ipc_close(void *device_ptr);
  * (out[i] = init op x0 op ... op xi), the per-rank step of the multi-GPU inclusive scan. */
 BCB_API int bcb_scan(bcb_stream stream, int in_dtype, int out_dtype, int op, int exclusive,
              const void *in, void *out, size_t n, const void *init_host);
+/* The scan of ONE BLOCK of a block-distributed range (multi-GPU, new functionality): rank r scans its block seeded with
+ * init op partial_0 op ... op partial_(r-1), the partials of the blocks before it, folded in rank order ON THE DEVICE
+ * from records_dev -- `rank` records of 16 bytes as an all-gather leaves them: the partial (out_dtype) at byte 0, a
+ * "block not empty" flag at byte 8 -- so the whole distributed scan (local reduce, all-gather, this call) is enqueued
+ * without a host synchronisation.  exclusive: 0 or 1; init_host only counts for exclusive scans. */
+BCB_API int bcb_scan_with_carry(bcb_stream stream, int in_dtype, int out_dtype, int op, int exclusive, const void *in,
+                                void *out, size_t n, const void *init_host, const void *records_dev, int rank);
 
 /* ---- reduce / accumulate ---- */
 /* reduce (algorithm/reduce.hpp:275-305): result = x0 op ... op x(n-1) in result_dtype (= result_of<F(T,T)>,

@@ -532,6 +532,55 @@ def test_sort_by_field_matches_the_stable_comparator_sort(record_bytes, offset, 
         assert gpu.is_sorted_by_field(rec, offset, dtype, unary, desc) == oracle.is_sorted_by_field(rec, offset, dtype, unary, desc)
 
 
+@pytest.mark.parametrize("dtype,op", [("int", "plus"), ("uint", "max"), ("long", "plus"), ("float", "plus"), ("double", "min"), ("int", "bit_xor"), ("short", "multiplies")])
+def test_scan_with_carry_folds_the_partials_on_the_device(dtype, op, gpu):
+    """bcb_scan_with_carry: one block of a block-distributed scan, seeded on the device with the partials of the blocks
+    before it (records as an all-gather leaves them; an empty block in between is skipped).  Integer results equal the
+    oracle's scan of the concatenated range bit for bit; float results within the scan tolerance."""
+    import torch
+    import compute_b200 as cb
+    from compute_b200.core import dtype_code, op_code
+    npdt = np.dtype(NPD[dtype])
+    rng = np.random.default_rng(12)
+    sizes = [5000, 0, 70_001, (1 << 20) + 17]        # blocks of four "ranks"; the second is empty
+    n = sum(sizes)
+    if npdt.kind == "f":
+        full = rng.random(n).astype(npdt)
+    elif op == "multiplies":
+        full = rng.choice(np.array([1, 1, 1, -1, 3], dtype=npdt), size=n)
+    else:
+        full = rng.integers(-1000 if npdt.kind == "i" else 0, 1000, size=n).astype(npdt)
+    cuts = np.concatenate([[0], np.cumsum(sizes)])
+    lib, q = cb.lib(), cb.command_queue()
+    records = np.zeros((len(sizes), 16), dtype=np.uint8)
+    for r in range(len(sizes)):
+        blk = full[cuts[r]:cuts[r + 1]]
+        if blk.size:
+            part = np.sum(blk, dtype=np.float64) if (npdt.kind == "f" and op == "plus") else oracle.reduce(blk, op)
+            records[r, :npdt.itemsize] = np.array([part], dtype=npdt).view(np.uint8)
+            records[r, 8] = 1
+    drec = gpu.to_dev(records.reshape(-1))
+    for exclusive, init in ((1, 7), (0, None)):
+        exp = oracle.scan(full, op, bool(exclusive), init if init is not None else 0)
+        for r in range(len(sizes)):
+            blk = full[cuts[r]:cuts[r + 1]]
+            if blk.size == 0:
+                continue
+            dx = gpu.to_dev(blk)
+            out = torch.empty_like(dx)
+            init_arr = np.array([init if init is not None else 0]).astype(npdt)
+            cb._capi.check(lib.bcb_scan_with_carry(q.handle, dtype_code(npdt), dtype_code(npdt), op_code(op), exclusive, dx.data_ptr(),
+                                                   out.data_ptr(), blk.size, init_arr.ctypes.data, drec.data_ptr(), r))
+            q.finish()
+            got = gpu.to_host(out, npdt)
+            want = exp[cuts[r]:cuts[r + 1]]
+            if npdt.kind == "f" and op == "plus":   # positive data: the bound 4 ceil(log2 n) eps sum|x| is relative to the prefix
+                ref = (np.cumsum(full, dtype=np.float64) - (full if exclusive else 0) + (init or 0))[cuts[r]:cuts[r + 1]]
+                np.testing.assert_allclose(got, ref, rtol=4 * 21 * np.finfo(npdt).eps, atol=1e-6, err_msg=f"{dtype} {op} rank {r}")
+            else:
+                assert got.tobytes() == want.tobytes(), (dtype, op, exclusive, r)
+
+
 def test_exchange_and_field_entry_points_reject_bad_arguments(gpu):
     """Error behaviour of the round-2 entry points: codes, never an exception or a crash (compute_b200.h conventions)."""
     import ctypes
