@@ -94,7 +94,7 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
     static_assert(VB == 0 || DET, "a payload needs the deterministic ranking (its stability cannot be verified afterwards)");
     const V *vals_in = reinterpret_cast<const V *>(vals_in_v);
     V *vals_out = reinterpret_cast<V *>(vals_out_v);
-    constexpr int ITEMS = C::ITEMS, TILE = C::TILE, A = C::A, SEG = C::SEG, CHUNK = C::CHUNK;
+    constexpr int ITEMS = C::ITEMS, TILE = C::TILE, A = C::A, SEG = C::SEG;
     constexpr int ROW = kRadixSize;  // words per (warp, tile) table row.  (16-bit counters packed two per word would let
                                      // the tile grow to 49152 keys, but measured 4.0 instead of 3.35 wavefronts per atomic:
                                      // twice as many lanes share a word -- and five more ALU instructions per key)
@@ -254,7 +254,7 @@ onesweep_ws(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void 
             WS_PROF_END(2);
             if (!first) named_bar_sync(kBarDrained, kWsThreads);  // the previous tile's bulk copies have read the buffer
             WS_PROF_END(3);
-            unsigned *mrow = masks + w * ROW;
+            [[maybe_unused]] unsigned *mrow = masks + w * ROW;  // (deterministic ranking only)
             unsigned run0 = 0, run1 = 0;  // next position of the hot digit values in this warp's runs
             if constexpr (decltype(hot_tag)::value) {
                 run0 = row[h0];

@@ -215,7 +215,6 @@ __global__ void __launch_bounds__(kRadixSize) digit_scan(const unsigned *__restr
 //                     one warp instruction are applied in lane order, which CUDA does not promise -- usable only where
 //                     the result is verified (keys-only sorts, below).  Keys only.
 enum { kRankAtomicOr = 0, kRankBallot = 2, kRankTwoSweep = 3 };
-static inline bool rank_is_speculative(int rank) { return rank == kRankTwoSweep; }
 
 template <int VB> struct value_type;
 template <> struct value_type<0> { typedef unsigned char type; };
@@ -275,7 +274,7 @@ pass_tile(const K *__restrict__ keys_in, K *__restrict__ keys_out, const void *_
 {
     typedef PassSmem<K, VB, THREADS, ITEMS, RANK> L;
     typedef typename value_type<VB>::type V;
-    constexpr int WARPS = L::WARPS, TILE = L::TILE;
+    constexpr int TILE = L::TILE;
 
     unsigned *out_base = reinterpret_cast<unsigned *>(smem_raw + L::kWarpTab);
     unsigned *misc = out_base + kRadixSize;  // [0..1] tile ids (onesweep_pass), [2..9] warp sums of the digit scan
