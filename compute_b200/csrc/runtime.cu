@@ -167,9 +167,19 @@ int staged_copy_pageable(void *device_ptr, void *host_ptr, size_t bytes, bool to
     BCB_TRY(stage_prepare(device, threads));
     std::vector<int> status(threads, 0);
     std::vector<std::thread> pool;
-    for (int k = 1; k < threads; k++)
-        pool.emplace_back(stage_lane_run, device, &g_stage.lanes[k], k, threads, (char *)device_ptr, (char *)host_ptr, bytes, to_device, &status[k]);
+    int started = 1;  // lane 0 is this thread
+    try {
+        pool.reserve(threads);
+        for (int k = 1; k < threads; k++) {
+            pool.emplace_back(stage_lane_run, device, &g_stage.lanes[k], k, threads, (char *)device_ptr, (char *)host_ptr, bytes, to_device, &status[k]);
+            started = k + 1;
+        }
+    } catch (...) {
+        // no more threads to be had (nothing may be thrown across the C ABI): this thread takes the lanes that did not start
+    }
     stage_lane_run(device, &g_stage.lanes[0], 0, threads, (char *)device_ptr, (char *)host_ptr, bytes, to_device, &status[0]);
+    for (int k = started; k < threads; k++)
+        stage_lane_run(device, &g_stage.lanes[k], k, threads, (char *)device_ptr, (char *)host_ptr, bytes, to_device, &status[k]);
     for (std::thread &t : pool) t.join();
     for (int k = 0; k < threads; k++)
         if (status[k] != 0) return status[k];
