@@ -643,7 +643,7 @@ def e2e_run(args, cb, L, stream, kind, dt, vb, n, pristine, unit, bpe):
                 pes.append(time.perf_counter() - t0)
             pe = min(pes)
             pageable = {"value": (n / 1e9) / pe, "unit": unit, "ms_per_step": pe * 1e3, "steps": 2, "first_call_ms": pes[0] * 1e3,
-                        "staging": "library: 8 host threads through pinned slots (runtime.cu staged_copy_pageable)",
+                        "staging": "library: up to 16 host threads through pinned slots (runtime.cu staged_copy_pageable)",
                         "checked": bool(np.all(hp[:m][:-1] <= hp[:m][1:]))}
             del hp, src
         except MemoryError:

@@ -70,9 +70,14 @@ int stream_state(cudaStream_t stream, StreamState **out)
 
 // ---- staged copies of pageable host ranges ------------------------------------------------------------------
 namespace {
-constexpr size_t kStageChunk = (size_t)8 << 20;       // bytes per pinned slot
+constexpr size_t kStageChunkMax = (size_t)8 << 20;    // bytes per pinned slot
+static const size_t kStageChunk = [] {                // (BCB_STAGED_CHUNK_LOG2: tuning hook, at most the slot size)
+    const char *e = std::getenv("BCB_STAGED_CHUNK_LOG2");
+    const int k = e ? std::atoi(e) : 21;  // measured on the 16-core B200 host, 2^30 keys: 16 threads x 2 MB 200 ms, 8 x 8 MB 216 ms, 4 x 8 MB 291 ms
+    return (size_t)1 << (k < 16 ? 16 : (k > 23 ? 23 : k));
+}();
 constexpr size_t kStageMinBytes = (size_t)32 << 20;   // below this the driver's own staging is not worth beating
-constexpr int kStageMaxThreads = 8;
+constexpr int kStageMaxThreads = 16;
 struct StageLane {
     cudaStream_t stream = nullptr;
     void *slot[2] = {nullptr, nullptr};
@@ -102,7 +107,7 @@ int stage_prepare(int device, int threads)
     for (StageLane &l : lanes) {
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking);
         for (int s = 0; s < 2 && e == cudaSuccess; s++) {
-            e = cudaHostAlloc(&l.slot[s], kStageChunk, cudaHostAllocDefault);
+            e = cudaHostAlloc(&l.slot[s], kStageChunkMax, cudaHostAllocDefault);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&l.done[s], cudaEventDisableTiming);
         }
     }
@@ -161,8 +166,12 @@ int staged_copy_pageable(void *device_ptr, void *host_ptr, size_t bytes, bool to
     int device = 0;
     BCB_CUDA_TRY(cudaGetDevice(&device));
     unsigned hw = std::thread::hardware_concurrency();
-    int threads = hw >= 4 ? (int)(hw / 2) : 1;
+    int threads = hw >= 2 ? (int)hw : 1;
     if (threads > kStageMaxThreads) threads = kStageMaxThreads;
+    if (const char *e = std::getenv("BCB_STAGED_THREADS")) {  // tuning hook
+        const int t = std::atoi(e);
+        if (t >= 1 && t <= 64) threads = t;
+    }
     std::lock_guard<std::mutex> lock(g_stage.mutex);
     BCB_TRY(stage_prepare(device, threads));
     std::vector<int> status(threads, 0);
