@@ -50,8 +50,10 @@ struct StreamState {
     //   [3]   u32 blocks-done counter of the one-launch reductions (reset by the last block)
     //   [4]   u64 element counter of count_if
     //   [5]   carry of a block-distributed scan, folded on the device (bcb_scan_with_carry)
+    //   [6]   u64 arrival counter of the grid barriers of the one-launch small sort (monotonic; launchers pass the base)
     unsigned long long *control = nullptr;
     unsigned long long ticket_base = 0;
+    unsigned long long gridbar_base = 0;  // arrivals handed out so far on the grid-barrier counter (control[6])
     // decoupled look-back descriptors (scan + sort); zeroed at (re)allocation, validated by epoch tags.  One arena per
     // descriptor LAYOUT, each with its own epoch counter: a slot is only ever read under the layout it was written in,
     // so a stale word can never alias a valid tag of another layout (kArenaPacked: u64 {tag:32 | payload:32} words of
@@ -104,7 +106,8 @@ int next_epoch(StreamState *st, int arena, uint32_t *epoch);
 unsigned long long ticket_reserve(StreamState *st, unsigned long long draws);
 
 constexpr int kControlTicket = 0, kControlSpecFlag = 1, kControlSpecFallbacks = 2, kControlReduceDone = 3, kControlCount = 4,
-              kControlCarry = 5 /* carry of a block-distributed scan (bcb_scan_with_carry) */;
+              kControlCarry = 5 /* carry of a block-distributed scan (bcb_scan_with_carry) */,
+              kControlGridBar = 6 /* monotonic arrival counter of the one-launch small sort's grid barriers */;
 
 // ---- device helpers ------------------------------------------------------------------------
 #ifdef __CUDACC__
@@ -126,6 +129,12 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
 {
     unsigned long long v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v)

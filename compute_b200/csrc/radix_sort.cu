@@ -1329,12 +1329,224 @@ static int sort_segments_typed(StreamState *st, void *recv_keys, void *recv_valu
     return BCB_SUCCESS;
 }
 
+// ---- small ranges: the whole sort in ONE launch ---------------------------------------------------------------
+// A small sort is all latency in the multi-launch path: six launches and a memset, ~60 us however few keys there are.
+// Here every tile has its own CTA, all CTAs are resident (cooperative launch), and
+// a pass is: rank the tile in shared memory (the deterministic atomic-OR ranking, keys kept in registers) -> publish the
+// tile's 256 digit counts -> grid barrier -> every CTA sums the counts of ALL tiles itself (a few hundred coalesced
+// L2 reads per digit thread: no serial chain) -> scatter straight to the other buffer (the whole range lives in L2)
+// -> grid barrier.  No histogram pass, no descriptors, no look-back.  Keys stay raw in memory; stable by construction.
+constexpr int kSmThreads = 512, kSmWarps = kSmThreads / 32;
+// largest launch, measured on B200 (us per sort, one launch / six launches): u32 keys 2^10 23 / 61, 2^14 44 / 60, 2^16 48 / 58,
+// 2^18 (43 tiles) 54 / 61; with a u32 payload 2^10 36 / 63, 2^14 66 / 70, 2^16 68 / 69, 2^18 79 / 71; 2^20 keys 124 / 68 --
+// the two grid barriers and the all-tiles sum of every pass grow with the tile count, the launches saved do not
+constexpr size_t kSmallMaxTilesKeys = 48, kSmallMaxTilesPairs = 8;
+template <typename K> struct SmallShape { static constexpr int ITEMS = sizeof(K) == 8 ? 8 : 12; static constexpr int TILE = kSmThreads * ITEMS; };
+
+__device__ __forceinline__ void grid_barrier(unsigned long long *counter, unsigned long long target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();  // this CTA's global writes before the arrival
+        atomicAdd(counter, 1ull);
+        while (ld_acquire_u64(counter) < target) { }
+    }
+    __syncthreads();
+}
+
+template <typename K, int VB>
+__global__ void __launch_bounds__(kSmThreads, 2)
+small_sort_kernel(K *buf_a, K *buf_b, void *val_a_v, void *val_b_v, const K *src, const void *src_vals_v, unsigned *tile_counts, unsigned n,
+                  int npass, const __grid_constant__ Transform tf, unsigned long long *bar, unsigned long long bar_base)
+{
+    typedef typename value_type<VB>::type V;
+    constexpr int ITEMS = SmallShape<K>::ITEMS, TILE = SmallShape<K>::TILE;
+    __shared__ unsigned mask[kSmWarps][kRadixSize];  // peers of the current round, per (warp, digit)
+    __shared__ unsigned cnt[kSmWarps][kRadixSize];   // keys of (warp, digit) so far; after the ranking: start of the warp's run in the tile's digit run
+    __shared__ unsigned base[kRadixSize];            // where this tile's run of each digit value starts in the output
+    __shared__ unsigned wsum[kRadixSize / 32];
+    __shared__ unsigned cnt_total[kRadixSize];       // single-tile launches: the tile's digit counts never leave the CTA
+    const unsigned tid = threadIdx.x, lane = tid & 31u, w = tid >> 5, tile = blockIdx.x, G = gridDim.x;
+    const unsigned seg = tile * TILE + w * (32 * ITEMS) + lane;  // this thread's item i is element seg + 32 * i: memory order = (i, lane) order
+    unsigned long long target = bar_base;
+    for (int p = 0; p < npass; p++) {
+        const K *in = p == 0 ? src : ((p & 1) ? buf_b : buf_a);
+        K *out = (p & 1) ? buf_a : buf_b;
+        const V *vin = reinterpret_cast<const V *>(p == 0 ? src_vals_v : ((p & 1) ? val_b_v : val_a_v));
+        V *vout = reinterpret_cast<V *>((p & 1) ? val_a_v : val_b_v);
+        const int shift = p * kRadixBits;
+        for (unsigned i = tid; i < kSmWarps * kRadixSize; i += kSmThreads) { (&mask[0][0])[i] = 0; (&cnt[0][0])[i] = 0; }
+        __syncthreads();
+        K key[ITEMS];
+        unsigned short rank[ITEMS];
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) key[i] = (seg + 32 * i < n) ? __ldcg(in + seg + 32 * i) : (K)0;  // (L2 only: other SMs wrote this buffer a pass ago)
+        // rank inside the warp: the lanes OR their bit into the mask of their digit; after a warp barrier the mask holds the
+        // complete peer set whatever order the atomics were applied in; the highest peer clears it and bumps the count
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            const bool valid = seg + 32 * i < n;
+            const unsigned d = digit_of<K>(key[i], shift, tf);
+            if (valid) atomicOr(&mask[w][d], 1u << lane);
+            __syncwarp();
+            const unsigned m = valid ? mask[w][d] : 0u, c = valid ? cnt[w][d] : 0u;
+            __syncwarp();
+            if (valid && (m >> lane) == 1u) {
+                mask[w][d] = 0;
+                cnt[w][d] = c + __popc(m);
+            }
+            __syncwarp();
+            rank[i] = (unsigned short)(c + __popc(m & lanemask_lt()));
+        }
+        __syncthreads();
+        if (tid < kRadixSize) {  // per digit: exclusive prefix over the warps, the tile's count to global memory
+            unsigned run = 0;
+#pragma unroll
+            for (int v = 0; v < kSmWarps; v++) {
+                const unsigned c = cnt[v][tid];
+                cnt[v][tid] = run;
+                run += c;
+            }
+            if (G > 1) tile_counts[tile * kRadixSize + tid] = run;
+            else cnt_total[tid] = run;
+        }
+        if (G > 1) {
+            target += G;
+            grid_barrier(bar, target);
+        } else {
+            __syncthreads();
+        }
+        {
+            // counts of this digit value in ALL tiles (total) and in the tiles before this one (below): both halves of the
+            // CTA take every other tile, eight loads in flight per thread -- a handful of L2 round trips, no serial chain
+            const unsigned d = tid & (kRadixSize - 1), half = tid >> 8;
+            unsigned total = 0, below = 0;
+            if (G > 1) {
+                unsigned t = half;
+                for (; t + 14 < G; t += 16) {
+                    unsigned c[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) c[u] = __ldcg(tile_counts + (t + 2 * u) * kRadixSize + d);
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        total += c[u];
+                        below += (t + 2 * u < tile) ? c[u] : 0u;
+                    }
+                }
+                for (; t < G; t += 2) {
+                    const unsigned c = __ldcg(tile_counts + t * kRadixSize + d);
+                    total += c;
+                    below += t < tile ? c : 0u;
+                }
+            } else if (half == 0) {
+                total = cnt_total[d];
+            }
+            if (half == 1) { mask[0][d] = total; mask[1][d] = below; }  // (the mask table is idle between the ranking and the next pass)
+            __syncthreads();
+            if (half == 0) {
+                total += mask[0][d];
+                below += mask[1][d];
+                unsigned incl = total;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const unsigned o = __shfl_up_sync(0xffffffffu, incl, off);
+                    if ((int)lane >= off) incl += o;
+                }
+                if (lane == 31) wsum[w] = incl;
+                base[d] = incl - total + below;  // (+ the digit values of the earlier warps, below)
+            }
+        }
+        __syncthreads();
+        if (tid < kRadixSize) {
+            unsigned add = 0;
+            for (unsigned v = 0; v < w; v++) add += wsum[v];
+            base[tid] += add;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            const unsigned idx = seg + 32 * i;
+            if (idx < n) {
+                const unsigned d = digit_of<K>(key[i], shift, tf);
+                const unsigned pos = base[d] + cnt[w][d] + rank[i];
+                out[pos] = key[i];
+                if constexpr (VB > 0) vout[pos] = __ldcg(vin + idx);
+            }
+        }
+        if (G > 1) {
+            target += G;
+            grid_barrier(bar, target);  // the pass's output is complete (and the tile counts have been read) before anyone goes on
+        } else {
+            __threadfence_block();
+            __syncthreads();
+        }
+    }
+}
+
+// resident CTAs of the small-sort kernel on the device (0 = not asked yet)
+template <typename K, int VB>
+static int small_sort_capacity(StreamState *st)
+{
+    static std::atomic<int> cached[64];
+    int cap = st->device < 64 ? cached[st->device].load(std::memory_order_acquire) : 0;
+    if (cap == 0) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, small_sort_kernel<K, VB>, kSmThreads, 0) != cudaSuccess) { (void)cudaGetLastError(); per_sm = 0; }
+        cap = per_sm > 0 ? per_sm * st->sm_count : -1;
+        if (st->device < 64) cached[st->device].store(cap, std::memory_order_release);
+    }
+    return cap;
+}
+
+// BCB_EUNSUPPORTED: not a small range (or switched off): the caller goes on with the multi-launch sort
+template <typename K, int VB>
+static int small_sort(StreamState *st, void *keys, void *values, size_t n, const Transform &tf, const void *src_keys, const void *src_vals)
+{
+    {
+        const char *e = std::getenv("BCB_SORT_SMALL");  // 0: always the multi-launch sort (A/B comparison, test hook; read per call)
+        if (e && e[0] == '0') return BCB_EUNSUPPORTED;
+    }
+    constexpr size_t TILE = SmallShape<K>::TILE;
+    const size_t tiles = (n + TILE - 1) / TILE;
+    const int cap = small_sort_capacity<K, VB>(st);
+    if (cap <= 0 || tiles > (size_t)cap || tiles > (VB ? kSmallMaxTilesPairs : kSmallMaxTilesKeys)) return BCB_EUNSUPPORTED;
+    constexpr int NPASS = sizeof(K);
+    const size_t kbytes = align_up(n * sizeof(K), 256), vbytes = align_up(n * (size_t)VB, 256);
+    void *scratch;
+    BCB_TRY(scratch_reserve(st, kbytes + vbytes + tiles * kRadixSize * sizeof(unsigned), &scratch));
+    K *tmp_keys = (K *)scratch;
+    void *tmp_vals = VB ? (void *)((char *)scratch + kbytes) : nullptr;
+    unsigned *tile_counts = (unsigned *)((char *)scratch + kbytes + vbytes);
+    K *buf_a = (K *)keys;
+    const K *src = (const K *)src_keys;
+    unsigned n32 = (unsigned)n;
+    int npass = NPASS;
+    unsigned long long *bar = st->control + kControlGridBar;
+    unsigned long long bar_base = st->gridbar_base;
+    {
+        LaunchTimer timer(st, BCB_K_ONESWEEP_PASS);
+        void *args[] = {(void *)&buf_a, (void *)&tmp_keys, (void *)&values, (void *)&tmp_vals, (void *)&src, (void *)&src_vals, (void *)&tile_counts,
+                        (void *)&n32, (void *)&npass, (void *)&tf, (void *)&bar, (void *)&bar_base};
+        BCB_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)small_sort_kernel<K, VB>, dim3((unsigned)tiles), dim3(kSmThreads), args, 0, st->stream));
+    }
+    if (tiles > 1) st->gridbar_base += 2ull * NPASS * tiles;  // (only once the launch is in: the counter and the base must stay in step)
+    if (NPASS & 1) {  // 8-bit keys: one pass, the result is in the temporary
+        BCB_CUDA_TRY(cudaMemcpyAsync(keys, tmp_keys, n * sizeof(K), cudaMemcpyDeviceToDevice, st->stream));
+        if (VB) BCB_CUDA_TRY(cudaMemcpyAsync(values, tmp_vals, n * (size_t)VB, cudaMemcpyDeviceToDevice, st->stream));
+    }
+    return BCB_SUCCESS;
+}
+
 template <typename K, int VB>
 static int sort_typed(StreamState *st, void *keys, void *values, size_t n, const Transform &tf, const void *src_keys = nullptr,
                       const void *src_vals = nullptr)
 {
     // src_keys / src_vals: read the input from there instead (sorted copy; the source is left untouched)
     if (!src_keys) { src_keys = keys; src_vals = values; }
+    {
+        const int rc = small_sort<K, VB>(st, keys, values, n, tf, src_keys, src_vals);
+        if (rc != BCB_EUNSUPPORTED) return rc;
+    }
     int pass_kind = kPassDeterministic;
     {   // large sorts the warp-specialised kernel covers with its deterministic ranking: payloads, non-injective transforms
         const SortEnv &env = sort_env();

@@ -58,12 +58,20 @@ def random_keys(dtype, n, seed, mode="bits"):
     raise ValueError(mode)
 
 
-SORT_SIZES = [2, 31, 32, 33, 100, 1000, 7679, 7680, 7681, 50_000, 300_001]
+SORT_SIZES = [2, 31, 32, 33, 100, 1000, 6143, 6144, 6145, 7679, 7680, 7681, 50_000, 300_001]
+
+
+# small ranges are sorted by the one-launch kernel (small_sort_kernel); BCB_SORT_SMALL=0 (read per call) sends them through
+# the multi-launch sort instead, so both families see every size
+@pytest.fixture(params=["one-launch", "multi-launch"])
+def small_path(request, monkeypatch):
+    monkeypatch.setenv("BCB_SORT_SMALL", "1" if request.param == "one-launch" else "0")
+    return request.param
 
 
 @pytest.mark.parametrize("dtype", ALL)
 @pytest.mark.parametrize("descending", [False, True], ids=["asc", "desc"])
-def test_radix_sort_keys_bit_exact(dtype, descending, gpu):
+def test_radix_sort_keys_bit_exact(dtype, descending, small_path, gpu):
     for n in SORT_SIZES:
         for mode in (["bits"] if n not in (1000, 50_000) else ["bits", "few", "equal", "sorted"]):
             k = random_keys(dtype, n, seed=n * 7 + len(mode), mode=mode)
@@ -87,7 +95,7 @@ def test_public_sort_dispatch_bit_exact(dtype, gpu):
 
 @pytest.mark.parametrize("key_dtype", ["uchar", "short", "int", "uint", "float", "long", "ulong", "double"])
 @pytest.mark.parametrize("value_bytes", [1, 2, 4, 8, 16, 12, 3])
-def test_radix_sort_pairs_bit_exact_and_stable(key_dtype, value_bytes, gpu):
+def test_radix_sort_pairs_bit_exact_and_stable(key_dtype, value_bytes, small_path, gpu):
     for n, mode in ((40, "few"), (5000, "few"), (7681, "bits"), (100_003, "few")):
         for desc in (False, True):
             k = random_keys(key_dtype, n, seed=n + value_bytes, mode=mode)
@@ -98,6 +106,21 @@ def test_radix_sort_pairs_bit_exact_and_stable(key_dtype, value_bytes, gpu):
             ek, ev = oracle.radix_sort(k, desc, v)
             assert gk.tobytes() == ek.tobytes(), (key_dtype, value_bytes, n, desc)
             assert gv.tobytes() == ev.tobytes(), (key_dtype, value_bytes, n, desc)
+
+
+@pytest.mark.parametrize("dtype,n", [("uint", 294_912), ("uint", 294_913), ("ulong", 196_608), ("uchar", 290_003), ("ushort", 12_289), ("float", 250_001)])
+def test_one_launch_sort_near_its_size_limit(dtype, n, gpu):
+    """The one-launch small sort at (and one key past) its largest size of 48 tiles, every key width (1 / 2 / 4 / 8 passes;
+    8-bit keys end in the temporary buffer and are copied back), keys and a payload, repeated on the same queue (the grid
+    barrier counter is monotonic across launches)."""
+    k = random_keys(dtype, n, seed=n, mode="bits")
+    v = np.arange(n, dtype=np.uint32)
+    for desc in (False, True):
+        assert gpu.radix_sort(k, desc).tobytes() == oracle.radix_sort(k, desc).tobytes(), (dtype, n, desc)
+        m = min(n, 8 * 6144)   # (with a payload the one-launch sort stops at 8 tiles)
+        gk, gv = gpu.radix_sort(k[:m], desc, v[:m])
+        ek, ev = oracle.radix_sort(k[:m], desc, v[:m])
+        assert gk.tobytes() == ek.tobytes() and gv.tobytes() == ev.tobytes(), (dtype, n, desc)
 
 
 def test_sort_by_key_dispatch(gpu):
