@@ -1,7 +1,7 @@
 """The digit-exchange plan of the multi-GPU sort with all ranks emulated on ONE GPU (the placement of
 compute_b200.distributed.digit_exchange_plan, every "peer" buffer local): times bcb_radix_exchange_scatter and
 bcb_radix_sort_segments with CUDA events and checks the concatenated result.  Also the target of the ncu captures of the
-segment kernels (scripts/gpu_s4_evidence.sh).  usage: digit_exchange_emulation.py [world] [log2 keys per rank]"""
+segment kernels (scripts/gpu_digit_exchange_evidence.sh).  usage: digit_exchange_emulation.py [world] [log2 keys per rank]"""
 import ctypes, os, sys
 import numpy as np
 import torch

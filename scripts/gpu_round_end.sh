@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: gpu_s4_final.sh N -- what the driver runs at round end: the GPU test suite (N = 1 only), the default bench line, the
+# usage: gpu_round_end.sh N -- what the driver runs at round end: the GPU test suite (N = 1 only), the default bench line, the
 # reference arm; for N > 1 under torchrun
 N=${1:-1}
 mkdir -p gpurun_out
