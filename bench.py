@@ -568,6 +568,7 @@ def ours(args):
         if world == 1:
             configs["sort_f32_desc"] = desc_float_check(env)
             configs["sort_u32_2^20"] = measure(env, "sort_u32", 20, 5, 3, "weak")  # small-n: the pre-speculation path
+            configs["sort_u32_2^16"] = measure(env, "sort_u32", 16, 10, 3, "weak")  # the one-launch small sort
         else:
             other = "strong" if args.scaling == "weak" else "weak"
             configs[f"sort_u32_{other}"] = measure(env, "sort_u32", 0, 3, 3, other)
