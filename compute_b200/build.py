@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libcompute_b200.so")
-SOURCES = ["runtime.cu", "reduce.cu", "scan.cu", "radix_sort.cu", "radix_pass_ws.cu", "radix_exchange_ws.cu", "stream_ops.cu", "set_ops.cu"]
+SOURCES = ["runtime.cu", "reduce.cu", "scan.cu", "radix_sort.cu", "radix_pass_ws.cu", "radix_exchange_ws.cu", "radix_exchange.cu", "radix_field.cu", "stream_ops.cu", "set_ops.cu"]
 HEADERS = ["common.cuh", "ops.cuh", "radix_common.cuh", "tma.cuh", "tile_state.cuh", "scan_ws.cuh", os.path.join("..", "..", "include", "compute_b200.h")]
 NVCC = os.environ.get("NVCC", "nvcc")
 FLAGS = [

@@ -204,6 +204,12 @@ constexpr int kHistHotOffset = 5120;
 size_t ws_tile_size(int key_bytes, int value_bytes, bool deterministic);
 bool ws_supports(int key_bytes, int value_bytes, bool deterministic);
 
+// radix_sort.cu, for the other radix translation units: the device sort behind bcb_radix_sort, the second half of a
+// speculative keys-only sort (verification + gated deterministic re-sort; key_bytes 4 or 8), BCB_SORT_SPECULATIVE
+int radix_sort_device(StreamState *st, int key_dtype, int ascending, void *keys, size_t n, void *values, size_t value_bytes);
+int radix_verify_and_fix(StreamState *st, int key_bytes, void *keys, size_t n, const Transform &tf);
+bool radix_speculation_enabled();
+
 // warp-specialised exchange pass of the multi-GPU sort (radix_exchange_ws.cu): bucket b of the stable partition by the
 // splitters in tf goes to tf.dst_keys[b] / tf.dst_vals[b].  BCB_EUNSUPPORTED for shapes it does not cover.
 int ws_exchange_pass(StreamState *st, int key_bytes, const void *kin, const void *vin, int value_bytes, size_t n, const Transform &tf);
