@@ -275,6 +275,26 @@ class OracleLocalOps:
         return torch.empty((n,) + tuple(like.shape[1:]), dtype=like.dtype)
 
 
+class OracleLocalOpsDeviceCarry(OracleLocalOps):
+    """The same with the stand-in for bcb_scan_with_carry: the carry is folded from the all-gathered 16-byte records
+    ({partial at byte 0, "block not empty" at byte 8}) in rank order, as fold_carry_kernel does on the device."""
+
+    def scan_with_carry(self, x, out, exclusive, init, op, records, rank):
+        o = self._np(out)
+        rec = records.numpy().reshape(-1, 16)
+        carry = o.dtype.type(init if (exclusive and init is not None) else 0) if exclusive else None
+        fn = cbd._NP_OPS[op]
+        with np.errstate(over="ignore"):
+            for r in range(rank):
+                if rec[r, 8]:
+                    v = rec[r, :o.dtype.itemsize].copy().view(o.dtype)[0]
+                    carry = v if carry is None else o.dtype.type(fn(carry, v))
+        if carry is None:
+            self.scan(x, out, 0, None, op)
+        else:
+            self.scan(x, out, 1 if exclusive else 2, carry, op)
+
+
 def _scan_cuts(world, n):
     if world == 2:
         return [0, 3000, n]
@@ -349,6 +369,14 @@ def _worker(rank, world, port, results):
         out["incl"] = o.numpy().copy()
         ctx.inclusive_scan(mine, o, "max")
         out["incl_max"] = o.numpy().copy()
+        # the same scans with the carry folded from the gathered records (the path the CUDA ops take: no host round trip)
+        ctxd = cbd.Context(local_ops=OracleLocalOpsDeviceCarry(), samples_per_rank=64)
+        ctxd.exclusive_scan(mine, o, 11)
+        out["excl_d"] = o.numpy().copy()
+        ctxd.inclusive_scan(mine, o, "plus")
+        out["incl_d"] = o.numpy().copy()
+        ctxd.inclusive_scan(mine, o, "max")
+        out["incl_max_d"] = o.numpy().copy()
         out["sum"] = ctx.reduce(mine)
         out["min"] = ctx.reduce(mine, "min")
         out["acc"] = ctx.accumulate(mine, 5)
@@ -418,6 +446,9 @@ def test_gloo_ranks_match_single_device_oracle(world):
     np.testing.assert_array_equal(np.concatenate([r["excl"] for r in res]), oracle.scan(x, "plus", True, 11))
     np.testing.assert_array_equal(np.concatenate([r["incl"] for r in res]), oracle.scan(x, "plus", False, 0))
     np.testing.assert_array_equal(np.concatenate([r["incl_max"] for r in res]), oracle.scan(x, "max", False, 0))
+    np.testing.assert_array_equal(np.concatenate([r["excl_d"] for r in res]), oracle.scan(x, "plus", True, 11))
+    np.testing.assert_array_equal(np.concatenate([r["incl_d"] for r in res]), oracle.scan(x, "plus", False, 0))
+    np.testing.assert_array_equal(np.concatenate([r["incl_max_d"] for r in res]), oracle.scan(x, "max", False, 0))
     for r in res:
         assert r["sum"] == oracle.reduce(x, "plus")
         assert r["min"] == oracle.reduce(x, "min")
