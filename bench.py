@@ -692,15 +692,26 @@ def e2e_run_distributed(args, ctx, kind, vb, n, world, pristine, unit, bpe):
     host_out = torch.empty(cap, dtype=pristine.dtype, pin_memory=True) if kind != "reduce" else None
     dev = torch.empty_like(pristine)
     out = torch.empty_like(pristine) if kind == "scan" else None
-    if kind == "sort" and vb:
-        return None
+    vhost_in = vhost_out = vdev = None
+    if kind == "sort" and vb:  # payload = index inside the shard, like the device-timed arm
+        vdt = torch.int32 if vb == 4 else torch.int64
+        vhost_in = torch.arange(n, dtype=vdt).pin_memory()
+        vhost_out = torch.empty(cap, dtype=vdt, pin_memory=True)
+        vdev = torch.empty(n, dtype=vdt, device=dev.device)
     times, d2h = [], 0
     for i in range(steps + 1):
         torch.cuda.synchronize()
         dist.barrier()
         t0 = time.perf_counter()
         dev.copy_(host_in, non_blocking=True)
-        if kind == "sort":
+        if kind == "sort" and vb:
+            vdev.copy_(vhost_in, non_blocking=True)
+            res, resv = ctx.sort(dev, vdev)
+            m = min(res.numel(), cap)
+            host_out[:m].copy_(res[:m], non_blocking=True)
+            vhost_out[:m].copy_(resv[:m], non_blocking=True)
+            d2h = m * (w + vb)
+        elif kind == "sort":
             res = ctx.sort(dev, None)
             m = min(res.numel(), cap)  # (a receive imbalance above 25 % would truncate the copy-back; never seen with regular sampling)
             host_out[:m].copy_(res[:m], non_blocking=True)
@@ -722,7 +733,7 @@ def e2e_run_distributed(args, ctx, kind, vb, n, world, pristine, unit, bpe):
     sec = float(t.item())
     total = n * world
     value = (total / 1e9) / sec if unit == "Gkeys/s" else (total * bpe / 1e9) / sec
-    return {"value": value, "unit": unit, "h2d_bytes_per_step": n * w * world, "d2h_bytes_per_step": d2h * world, "ms_per_step": sec * 1e3,
+    return {"value": value, "unit": unit, "h2d_bytes_per_step": n * (w + (vb if kind == "sort" else 0)) * world, "d2h_bytes_per_step": d2h * world, "ms_per_step": sec * 1e3,
             "entry": "compute_b200.distributed.Context (pinned host shard -> H2D -> distributed algorithm -> D2H)", "steps": steps}
 
 
