@@ -96,6 +96,51 @@ def test_digit_exchange_plan_places_every_run():
     assert cbd.digit_exchange_plan(np.zeros((2, 256), np.int64), 2) is None
 
 
+def test_digit_exchange_plan_invariants_on_random_histograms():
+    """Property check of the placement: for random (also ragged, sparse, partly empty) histograms every (source, digit)
+    run lies inside its digit's segment, runs of one segment tile it exactly in source order, segments of one owner are
+    disjoint, aligned and ascending, and the owners' receive counts add up."""
+    rng = np.random.default_rng(2024)
+    accepted = 0
+    for trial in range(300):
+        world = int(rng.integers(2, 9))
+        kind = trial % 4
+        if kind == 0:
+            h = rng.integers(0, 5000, size=(world, 256))
+        elif kind == 1:   # sparse: most digit values unused
+            h = rng.integers(0, 5000, size=(world, 256)) * (rng.random((1, 256)) < 0.2)
+        elif kind == 2:   # some ranks hold nothing
+            h = rng.integers(0, 3000, size=(world, 256))
+            h[rng.random(world) < 0.3] = 0
+        else:             # tiny counts
+            h = rng.integers(0, 3, size=(world, 256))
+        h = h.astype(np.int64)
+        plan = cbd.digit_exchange_plan(h, world, max_imbalance=1e9)
+        if h.sum() == 0:
+            assert plan is None
+            continue
+        accepted += 1
+        owner, first, seg_begin, seg_len, recv, span, _ = plan
+        tot = h.sum(axis=0)
+        np.testing.assert_array_equal(seg_len, tot)
+        assert np.all(np.diff(owner) >= 0) and owner.min() >= 0 and owner.max() < world
+        assert np.all(seg_begin % 32 == 0)
+        for d in range(world):
+            mine = np.flatnonzero(owner == d)
+            assert int(tot[mine].sum()) == int(recv[d])
+            end = 0
+            for g in mine:                                   # ascending, disjoint, inside the span
+                assert seg_begin[g] >= end
+                end = seg_begin[g] + seg_len[g]
+            assert end <= span[d] or mine.size == 0
+        # runs of a segment tile it exactly, in source order
+        ends = first + h
+        assert np.all(first[0] == seg_begin)
+        assert np.all(first[1:] == ends[:-1])
+        assert np.all(ends[-1] == seg_begin + seg_len)
+    assert accepted > 250
+
+
 class OracleLocalOps:
     """CPU stand-in for CudaLocalOps used ONLY by this test: same interface, oracle semantics, CPU tensors."""
     device_type = "cpu"
